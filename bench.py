@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+# -*- coding: utf-8 -*-
+"""bench.py -- MC steps/s of the McSAS fitting core on B200 (BASELINE.json metric).
+
+Workload (configs[1]): Sphere model, synthetic 1000-point q curve, nContribs=300,
+nRep=100 per GPU, convergenceCriterion=1, production mode (fp32 form factors, fp64 LSQ,
+in-kernel Philox).  One bench "step" = one complete McSAS.analyse of the 100
+repetitions (a fresh seed per step); MC steps = sum of numIter over all chains.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 is launched with torchrun, one rank per GPU; ranks fit independent repetition
+sets (weak scaling) and gather the final contribution sets over NCCL.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NQ, N_CONTRIBS, N_REPS = 1000, 300, 100
+RADIUS_RANGE = (1e-9, 100e-9)
+MUFU_PER_STEP = 6 * NQ          # 2 evaluations x (sin, cos, rcp) per q point
+FLOP_PER_STEP = 44 * NQ         # ~14 flop per evaluation + 16 flop LSQ per q point
+METRIC = "MC steps/s (nRep=100 sphere fit, 1000 q, 300 contributions)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        super(ClockSampler, self).__init__(daemon=True)
+        self.gpu, self.rows, self._stop_evt = gpu, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def finish(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                  "sw_power_cap"), r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_cpu_steps_per_s(steps_per_chain, threads):
+    """CPU baseline: the oracle's C restatement of McSAS.mcFit on `threads` host threads,
+    one independent chain each (the reference itself is single-threaded Python)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    from mcsas_b200 import synth
+    orc.lib()
+    q, I, sig = synth.sphere_curve(nq=NQ)
+    om = orc.Model("Sphere", ranges={"radius": RADIUS_RANGE})
+    st = orc.settings(n_contribs=N_CONTRIBS, conv_crit=0.0, max_iter=steps_per_chain)
+    done = [0] * threads
+
+    def work(i):
+        stream = np.random.RandomState(1000 + i).uniform(size=N_CONTRIBS + steps_per_chain)
+        o = orc.chain(om, st, q, I, sig, stream)
+        done[i] = o["num_iter"]
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    el = time.perf_counter() - t0
+    return sum(done) / el, el
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = host_threads()
+    per_chain = 4000
+    vals, tot_t = [], 0.0
+    for i in range(args.warmup + args.steps):
+        v, el = oracle_cpu_steps_per_s(per_chain, threads)
+        if i >= args.warmup:
+            vals.append(v); tot_t += el
+    value = float(np.mean(vals))
+    sample = ("%d threads x 1 chain x %d MC steps (+300 initial contributions) of the config-2 "
+              "workload per bench step; oracle/mcsas_oracle.c (C port of McSAS.mcFit; the "
+              "reference itself is single-threaded Python: 1312 steps/s/core measured in the "
+              "build container, BASELINE.md)" % (threads, per_chain))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "MC steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1]: Sphere, synthetic 1000-point q curve, nContribs=300, "
+                                   "nRep=100 (bounded sample)", "nq": NQ, "n_contribs": N_CONTRIBS},
+            "cpu_baseline": {"value": value, "unit": "MC steps/s", "cores": threads, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": "MC steps/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from mcsas_b200 import synth
+    from mcsas_b200.mcsas import McSAS
+    from mcsas_b200.models import Sphere
+    from mcsas_b200.data import SASData
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    q, I, sig = synth.sphere_curve(nq=NQ)
+    data = SASData(q, I, sig)
+
+    def make_algo(seed):
+        model = Sphere()
+        model.radius.setActiveRange(RADIUS_RANGE)
+        algo = McSAS(device=local_rank, seed=seed, first_chain=rank * N_REPS)
+        algo.model, algo.data = model, data
+        algo.numContribs.setValue(N_CONTRIBS)
+        algo.numReps.setValue(N_REPS)
+        algo.convergenceCriterion.setValue(1.0)
+        return algo
+
+    algo = make_algo(0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(i, gather):
+        """One complete analyse() of N_REPS repetitions with host buffers in and out."""
+        flush.zero_()
+        torch.cuda.synchronize()
+        algo.seed = 7919 * (i + 1)
+        t0 = time.perf_counter()
+        algo.analyse()                       # upload (H2D) + chains + fetch (D2H)
+        res = algo.result[0]
+        if gather and world > 1:
+            algo.gatherResults()             # NCCL all_gather of the contribution sets
+        t1 = time.perf_counter()
+        return res, algo.lastKernelMs, t1 - t0
+
+    for i in range(args.warmup):
+        one_step(i, True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    mc_steps, kern_ms, e2e_s, evals, t2c, nconv = 0, 0.0, 0.0, 0, [], 0
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        res, kms, el = one_step(args.warmup + i, True)
+        mc_steps += int(res["numIterAll"].sum())
+        evals += int(res["evals"].sum())
+        nconv += int((res["conval"] <= 1.0).sum())
+        kern_ms += kms
+        e2e_s += el
+        t2c.append(kms)
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.finish()
+
+    # max over ranks of the time, sum over ranks of the work
+    tt = torch.tensor([kern_ms, e2e_s, wall], dtype=torch.float64, device="cuda")
+    ww = torch.tensor([mc_steps, evals, nconv], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ww, op=dist.ReduceOp.SUM)
+    kern_ms, e2e_s, wall = [float(x) for x in tt.tolist()]
+    mc_steps, evals, nconv = [float(x) for x in ww.tolist()]
+
+    if rank == 0:
+        peaks = algo.engine.measure_peaks()
+        info = algo.engine.device_info()
+        value = mc_steps / (kern_ms * 1e-3)
+        e2e_value = mc_steps / e2e_s
+        # the roofline is per GPU: rank-0-equivalent share of the work
+        per_gpu = value / world
+        mufu_ach = per_gpu * MUFU_PER_STEP * 1e-9
+        fp32_ach = per_gpu * FLOP_PER_STEP * 1e-12
+        h2d = 3 * NQ * 8 + 256
+        d2h = N_REPS * (N_CONTRIBS * 8 + NQ * 8 + 8 * 8)
+        line = {
+            "metric": METRIC, "value": value, "unit": "MC steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": kern_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 form factors / f64 LSQ sums", "data": "synthetic",
+            "config": {"workload": "configs[1]: Sphere, synthetic 1000-point q curve, nContribs=300, "
+                                   "nRep=100 per GPU, convergenceCriterion=1",
+                       "nq": NQ, "n_contribs": N_CONTRIBS, "n_reps_per_gpu": N_REPS,
+                       "precision": "fp32 production (Philox proposals)",
+                       "l2": "256 MB flush between steps; the chain's working set is register/"
+                             "shared-memory resident (24 KB of input per launch)"},
+            "time_to_convergence_ms": float(np.mean(t2c)),
+            "converged_fraction": nconv / (args.steps * N_REPS * world),
+            "mc_steps_per_fit": mc_steps / (args.steps * world),
+            "speculation_efficiency": 2.0 * mc_steps / max(1.0, evals),
+            "e2e": {"value": e2e_value, "unit": "MC steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps},
+            "wall_s": wall,
+            "gpu_launches": args.steps,      # one persistent chain kernel per analyse()
+            "clocks": clocks,
+            "roofline": {"bound": "sfu", "achieved": mufu_ach, "peak": peaks["mufu_gops"],
+                         "unit": "GMUFU/s", "frac": mufu_ach / peaks["mufu_gops"],
+                         "traffic": None,
+                         "peak_source": "measured live: mcsas_measure_peaks (sin+cos+rcp MUFU mix)",
+                         "fp32": {"achieved": fp32_ach, "peak": peaks["ffma_tflops"],
+                                  "unit": "TFLOP/s", "frac": fp32_ach / peaks["ffma_tflops"]},
+                         "hbm_note": "HBM traffic ~0: 24 KB in, 1.1 MB out per launch",
+                         "sm_count": info["sm_count"], "ctas": N_REPS},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            threads = host_threads()
+            v, el = oracle_cpu_steps_per_s(4000, threads)
+            line["cpu_baseline"] = {
+                "value": v, "unit": "MC steps/s", "cores": threads, "kind": "port",
+                "sample": "%d threads x 1 chain x 4000 MC steps of the same workload (%.1f s); "
+                          "oracle/mcsas_oracle.c" % (threads, el)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,160 @@
+/*
+ * mcsas_b200.h -- C-ABI of libmcsas_b200.so: the B200 (sm_100a) replacement for the
+ * Monte-Carlo fitting core of McSAS (BAMresearch/McSAS 1.3.1).
+ *
+ * The reference is pure Python and has no FFI; its "operator API" for this path is
+ *   McSAS.analyse / McSAS.mcFit            src/mcsas/mcsas/mcsas.py:191-439
+ *   BackgroundScalingFit.calc              src/mcsas/mcsas/backgroundscalingfit.py:112-139
+ *   ScatteringModel.calc / generateParameters   src/mcsas/bases/model/scatteringmodel.py:79-127
+ *   SASModel.calcIntensity / weight        src/mcsas/bases/model/sasmodel.py:37-79
+ *   <Model>.formfactor / volume / absVolume / surface   src/mcsas/models/*.py
+ * Each entry point below names the reference call it replaces.  The Python host
+ * (mcsas_b200/) binds these with ctypes; INTEGRATION.md shows the stub a McSAS
+ * maintainer would add.
+ *
+ * Conventions: all pointers are caller-owned HOST memory (plain malloc/numpy buffers);
+ * every function returns 0 on success or a negative mcsas_status and never throws;
+ * mcsas_last_error(ctx) gives the message.  One context per GPU; a context is not
+ * thread-safe, distinct contexts are independent.  All quantities are float64 in SI
+ * units exactly as the reference hands them to the hot path (q in 1/m, lengths in m).
+ */
+#ifndef MCSAS_B200_H
+#define MCSAS_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCSAS_MAX_PARAMS 16
+#define MCSAS_MAX_ACTIVE 4
+#define MCSAS_MAX_NQ 4096
+#define MCSAS_MAX_SPEC 32
+
+typedef struct mcsas_ctx mcsas_ctx;
+
+enum mcsas_status {
+    MCSAS_OK = 0,
+    MCSAS_ERR_CUDA = -1,        /* CUDA runtime error, see mcsas_last_error */
+    MCSAS_ERR_ARG = -2,         /* invalid argument */
+    MCSAS_ERR_STATE = -3,       /* call order (no datasets / no model / nothing to fetch) */
+    MCSAS_ERR_NO_DEVICE = -4,   /* no usable CUDA device: there is NO CPU fallback */
+    MCSAS_ERR_STREAM = -5       /* uploaded proposal stream too short */
+};
+
+/* Model plug-ins of the reference (src/mcsas/models/<file>.py); parameter vectors
+ * follow each class's `parameters` tuple order. */
+enum mcsas_model_id {
+    MCSAS_SPHERE = 0,                 /* sphere.py:              radius, sld */
+    MCSAS_LMA_DENSE_SPHERE = 1,       /* lmadensesphere.py:      radius, volFrac, mf, sld */
+    MCSAS_SPHERICAL_CORE_SHELL = 2,   /* sphericalcoreshell.py:  radius, t, eta_c, eta_s, eta_sol */
+    MCSAS_ELLIPSOIDAL_CORE_SHELL = 3, /* ellipsoidalcoreshell.py: a, b, t, eta_c, eta_s, eta_sol, intDiv */
+    MCSAS_ELLIPSOIDS_ISOTROPIC = 4,   /* ellipsoidsisotropic.py: a, useAspect, c, aspect, intDiv, sld */
+    MCSAS_CYLINDERS_ISOTROPIC = 5,    /* cylindersisotropic.py:  radius, useAspect, length, aspect, intDiv, sld */
+    MCSAS_GAUSSIAN_CHAIN = 6,         /* gaussianchain.py:       rg, bp, etas, k */
+    MCSAS_KHOLODENKO = 7,             /* kholodenko.py:          radius, lenKuhn, lenContour */
+    MCSAS_N_MODELS = 8
+};
+
+/* Number generators, src/mcsas/bases/algorithm/numbergenerator.py:28-31,168-189 */
+enum mcsas_generator {
+    MCSAS_GEN_UNIFORM = 0,   /* RandomUniform */
+    MCSAS_GEN_EXP1 = 1,      /* RandomExponential / RandomExponential1 (upper = 1) */
+    MCSAS_GEN_EXP2 = 2,      /* RandomExponential2 */
+    MCSAS_GEN_EXP3 = 3       /* RandomExponential3 */
+};
+
+enum mcsas_quad_rule {
+    MCSAS_QUAD_REFERENCE = 0,      /* the reference's own rule: linspace + mean/trapz (intDiv nodes) */
+    MCSAS_QUAD_GAUSS_LEGENDRE = 1  /* Gauss-Legendre with quad_nodes nodes */
+};
+
+enum mcsas_precision {
+    MCSAS_FP64 = 0,   /* parity mode: all float64, reference operation order */
+    MCSAS_FP32 = 1    /* production: fp32 form factors (MUFU), fp64 LSQ sums */
+};
+
+/* Settings of McSAS (src/mcsas/mcsas/mcsasparameters.json) that reach the hot path. */
+typedef struct mcsas_run_config {
+    int n_contribs;            /* numContribs */
+    int n_reps;                /* numReps: chains per dataset */
+    double conv_crit;          /* convergenceCriterion */
+    long long max_iter;        /* maxIterations */
+    int max_retries;           /* maxRetries: up to max_retries+2 attempts (mcsas.py:220-246) */
+    double comp_exp;           /* compensationExponent */
+    int find_background;       /* findBackground */
+    int positive_background;   /* positiveBackground */
+    int start_from_minimum;    /* startFromMinimum */
+    int precision;             /* mcsas_precision */
+    unsigned long long seed;   /* Philox key (production proposals) */
+    int spec_max;              /* max speculative proposals per batch, 0 = default (32), 1 = none */
+    int record_trace;          /* 1: keep per-step accept flag + chi-squared (parity tests) */
+    int first_chain;           /* global index of this context's first chain (multi-GPU partition) */
+} mcsas_run_config;
+
+/* -- context ------------------------------------------------------------- */
+int mcsas_ctx_create(int device, mcsas_ctx **out);
+void mcsas_ctx_destroy(mcsas_ctx *ctx);
+const char *mcsas_last_error(const mcsas_ctx *ctx);
+/* Device facts for roofline reporting: sm_count, clock kHz. */
+int mcsas_device_info(mcsas_ctx *ctx, int *sm_count, int *clock_khz, char *name, int name_len);
+
+/* -- data: replaces the reads of data.q / data.f.binnedData / data.f.binnedDataU in
+ *    mcFit (sasdata.py:51-54, datavector.py:96-117).  Concatenated over datasets. */
+int mcsas_upload_datasets(mcsas_ctx *ctx, int n_sets, const int *nq,
+                          const double *q, const double *intensity, const double *sigma);
+
+/* -- model: replaces the ScatteringModel instance state (parameter values, which
+ *    FitParameters are active, their activeRange ∩ valueRange and generator). */
+int mcsas_set_model(mcsas_ctx *ctx, int model_id, const double *params, int n_params,
+                    const int *active_idx, int n_active,
+                    const double *active_lo, const double *active_hi, const int *generator_kind,
+                    int quad_rule, int quad_nodes);
+
+/* -- ScatteringModel.calc(data, pset, compExp) (scatteringmodel.py:79-105) for M
+ *    single contributions of dataset `set`: intensity[M][nq] (=F^2*w), v, w, s [M]. */
+int mcsas_eval(mcsas_ctx *ctx, int set, const double *pset, int m, double comp_exp, int precision,
+               double *intensity, double *v, double *w, double *s);
+
+/* -- McSAS.analyse (mcsas.py:191-285): run n_sets * n_reps independent mcFit chains
+ *    (mcsas.py:287-439), one CTA each.  proposal_stream: NULL (in-kernel Philox) or
+ *    [n_chains][stream_stride] number-generator outputs in [0,1) in the reference's
+ *    consumption order (deterministic parity mode, single attempt per chain).
+ *    stop_flag: NULL or a host int the caller may set non-zero to stop (McSAS.stop). */
+int mcsas_run(mcsas_ctx *ctx, const mcsas_run_config *cfg,
+              const double *proposal_stream, long long stream_stride,
+              volatile int *stop_flag);
+/* Split form for timing: launch asynchronously / wait; mcsas_run == launch + wait. */
+int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
+                    const double *proposal_stream, long long stream_stride,
+                    volatile int *stop_flag);
+int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms);
+/* Ask a running launch to stop at its next batch boundary (McSAS.stop). */
+int mcsas_request_stop(mcsas_ctx *ctx);
+
+/* -- results of the last run (any pointer may be NULL).  Layouts:
+ *    contribs [set][N][P][R] (numpy zeros((N,P,R)) per set, mcsas.py:203-205),
+ *    fit_meas [set][nq][R] (mcsas.py:210), everything else [set][R]. */
+int mcsas_fetch(mcsas_ctx *ctx, double *contribs, double *fit_meas,
+                double *scaling, double *background, double *conval, double *conval0,
+                long long *num_iter, long long *num_moves, int *attempts, double *elapsed_s,
+                long long *evals);
+/* Per-step trace of chain `chain` (record_trace=1): accept[num_iter], chi[num_iter]. */
+int mcsas_fetch_trace(mcsas_ctx *ctx, int chain, unsigned char *accept, double *chi,
+                      long long capacity);
+
+/* -- McSAS.histogram per-repetition part (mcsas.py:548-604): volume/number/intensity/
+ *    surface fractions and minimum-observability limits of the fetched contributions.
+ *    All outputs [set][N][R]; totals [set][4][R]; sc [set][2][R]. */
+int mcsas_fractions(mcsas_ctx *ctx, const mcsas_run_config *cfg, const double *contribs,
+                    double *vol_frac, double *num_frac, double *volsqr_frac, double *surf_frac,
+                    double *min_vol, double *min_num, double *min_volsqr, double *min_surf,
+                    double *totals, double *sc);
+
+/* -- measured pipe peaks of this GPU for the FP32/SFU roofline (bench.py):
+ *    MUFU (sin+cos+rcp mix) Gop/s and FP32 FMA TFLOP/s, whole chip. */
+int mcsas_measure_peaks(mcsas_ctx *ctx, double *mufu_gops, double *ffma_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

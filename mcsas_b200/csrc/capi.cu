@@ -1,0 +1,625 @@
+// capi.cu -- the C-ABI of libmcsas_b200.so (include/mcsas_b200.h): context, uploads,
+// launch of the chain / eval / fraction kernels, result fetch.  No torch types, no CPU
+// fallback: every compute entry point needs a CUDA device.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <chrono>
+#include <thread>
+
+#include "common.cuh"
+#include "launch.cuh"
+
+cudaError_t mcsas_launch_fractions(int prec, int model, int grid, size_t smem, cudaStream_t st,
+                                   const FractionArgs &a);
+cudaError_t mcsas_launch_peaks(int which, int grid, int threads, int iters, float *out,
+                               cudaStream_t st);
+
+static const chain_launch_fn CHAIN_FN[MCSAS_N_MODELS] = {
+    mcsas_launch_chain_0, mcsas_launch_chain_1, mcsas_launch_chain_2, mcsas_launch_chain_3,
+    mcsas_launch_chain_4, mcsas_launch_chain_5, mcsas_launch_chain_6, mcsas_launch_chain_7};
+static const eval_launch_fn EVAL_FN[MCSAS_N_MODELS] = {
+    mcsas_launch_eval_0, mcsas_launch_eval_1, mcsas_launch_eval_2, mcsas_launch_eval_3,
+    mcsas_launch_eval_4, mcsas_launch_eval_5, mcsas_launch_eval_6, mcsas_launch_eval_7};
+
+struct mcsas_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaDeviceProp prop;
+    std::string err;
+    // datasets
+    int n_sets = 0;
+    int nq_max = 0;
+    std::vector<DatasetDesc> sets;
+    DatasetDesc *d_sets = nullptr;
+    double *d_data = nullptr;
+    // model
+    bool have_model = false;
+    ModelParams mp;
+    double *d_quad = nullptr;     // [2][quad_nodes]
+    // run state
+    int n_chains = 0, n_contribs = 0, n_reps = 0, n_active = 0;
+    long long max_iter = 0;
+    bool have_run = false, have_trace = false, running = false;
+    double *d_stream = nullptr;
+    size_t stream_cap = 0;
+    double *d_rset = nullptr, *d_fit = nullptr, *d_scal = nullptr;   // scal: 5 doubles per chain
+    long long *d_cnt = nullptr;                                       // 3 per chain
+    int *d_att = nullptr;
+    unsigned char *d_tacc = nullptr;
+    double *d_tchi = nullptr;
+    size_t out_cap = 0, trace_cap = 0;
+    int *h_stop = nullptr;        // mapped pinned host int
+    int *d_stop = nullptr;
+};
+
+static int fail(mcsas_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                             \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return fail(ctx, MCSAS_ERR_CUDA, "%s failed: %s (%s:%d)", #call,                 \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                         \
+    } while (0)
+
+static thread_local std::string g_create_err;
+
+extern "C" int mcsas_ctx_create(int device, mcsas_ctx **out)
+{
+    if (!out) return MCSAS_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+        g_create_err = std::string("no usable CUDA device (") +
+                       (e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range") +
+                       "); mcsas_b200 has no CPU fallback";
+        return MCSAS_ERR_NO_DEVICE;
+    }
+    mcsas_ctx *ctx = new mcsas_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess
+        || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess
+        || cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess
+        || cudaHostAlloc((void **)&ctx->h_stop, sizeof(int), cudaHostAllocMapped) != cudaSuccess
+        || cudaHostGetDevicePointer((void **)&ctx->d_stop, ctx->h_stop, 0) != cudaSuccess) {
+        g_create_err = std::string("CUDA context setup failed: ") + cudaGetErrorString(cudaGetLastError());
+        delete ctx;
+        return MCSAS_ERR_CUDA;
+    }
+    *ctx->h_stop = 0;
+    *out = ctx;
+    return MCSAS_OK;
+}
+
+extern "C" void mcsas_ctx_destroy(mcsas_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_sets); cudaFree(ctx->d_data); cudaFree(ctx->d_quad); cudaFree(ctx->d_stream);
+    cudaFree(ctx->d_rset); cudaFree(ctx->d_fit); cudaFree(ctx->d_scal); cudaFree(ctx->d_cnt);
+    cudaFree(ctx->d_att); cudaFree(ctx->d_tacc); cudaFree(ctx->d_tchi);
+    cudaFreeHost(ctx->h_stop);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char *mcsas_last_error(const mcsas_ctx *ctx)
+{
+    return ctx ? ctx->err.c_str() : g_create_err.c_str();
+}
+
+extern "C" int mcsas_device_info(mcsas_ctx *ctx, int *sm_count, int *clock_khz, char *name, int name_len)
+{
+    if (!ctx) return MCSAS_ERR_ARG;
+    if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+    if (clock_khz) {
+        int khz = 0;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
+        *clock_khz = khz;
+    }
+    if (name && name_len > 0) snprintf(name, name_len, "%s", ctx->prop.name);
+    return MCSAS_OK;
+}
+
+extern "C" int mcsas_upload_datasets(mcsas_ctx *ctx, int n_sets, const int *nq, const double *q,
+                                     const double *intensity, const double *sigma)
+{
+    if (!ctx) return MCSAS_ERR_ARG;
+    if (n_sets <= 0 || !nq || !q || !intensity || !sigma)
+        return fail(ctx, MCSAS_ERR_ARG, "upload_datasets: null/empty input");
+    CK(cudaSetDevice(ctx->device));
+    std::vector<DatasetDesc> sets(n_sets);
+    long long off = 0, src = 0;
+    int nq_max = 0;
+    for (int s = 0; s < n_sets; ++s) {
+        if (nq[s] < 1 || nq[s] > MCSAS_MAX_NQ)
+            return fail(ctx, MCSAS_ERR_ARG, "dataset %d: nq=%d outside [1,%d]", s, nq[s], MCSAS_MAX_NQ);
+        sets[s].nq = nq[s];
+        sets[s].nq_pad = (nq[s] + 1) & ~1;
+        sets[s].offset = off;
+        off += 3LL * sets[s].nq_pad;
+        if (nq[s] > nq_max) nq_max = nq[s];
+    }
+    std::vector<double> packed((size_t)off, 0.0);
+    for (int s = 0; s < n_sets; ++s) {
+        double *dst = packed.data() + sets[s].offset;
+        double qmax = -INFINITY;
+        for (int i = 0; i < nq[s]; ++i) {
+            dst[i] = q[src + i];
+            dst[sets[s].nq_pad + i] = intensity[src + i];
+            dst[2 * sets[s].nq_pad + i] = sigma[src + i];
+            if (q[src + i] > qmax) qmax = q[src + i];
+            if (!std::isfinite(q[src + i]) || !std::isfinite(intensity[src + i]) || !std::isfinite(sigma[src + i]))
+                return fail(ctx, MCSAS_ERR_ARG, "dataset %d: non-finite value at point %d", s, i);
+        }
+        sets[s].q_max = qmax;
+        src += nq[s];
+    }
+    cudaFree(ctx->d_sets); cudaFree(ctx->d_data);
+    ctx->d_sets = nullptr; ctx->d_data = nullptr;
+    CK(cudaMalloc(&ctx->d_sets, sizeof(DatasetDesc) * n_sets));
+    CK(cudaMalloc(&ctx->d_data, sizeof(double) * packed.size()));
+    CK(cudaMemcpyAsync(ctx->d_sets, sets.data(), sizeof(DatasetDesc) * n_sets, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_data, packed.data(), sizeof(double) * packed.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->sets = sets;
+    ctx->n_sets = n_sets;
+    ctx->nq_max = nq_max;
+    ctx->have_run = false;
+    return MCSAS_OK;
+}
+
+// Gauss-Legendre nodes/weights on [-1,1] (Newton on P_n).
+static void gauss_legendre(int n, std::vector<double> &x, std::vector<double> &w)
+{
+    x.resize(n); w.resize(n);
+    for (int i = 0; i < n; ++i) {
+        double z = cos(M_PI * (i + 0.75) / (n + 0.5)), pp = 1.;
+        for (int it = 0; it < 100; ++it) {
+            double p1 = 1., p2 = 0.;
+            for (int j = 0; j < n; ++j) {
+                double p3 = p2; p2 = p1;
+                p1 = ((2. * j + 1.) * z * p2 - j * p3) / (j + 1.);
+            }
+            pp = n * (z * p1 - p2) / (z * z - 1.);
+            double dz = p1 / pp;
+            z -= dz;
+            if (fabs(dz) < 1e-15) break;
+        }
+        x[i] = z;
+        w[i] = 2. / ((1. - z * z) * pp * pp);
+    }
+}
+
+// numpy.linspace(start, stop, n): arange(n) * step + start, last element = stop
+static double linspace_at(double start, double stop, int n, int j)
+{
+    if (n == 1) return start;
+    if (j == n - 1) return stop;
+    return j * ((stop - start) / (n - 1)) + start;
+}
+
+extern "C" int mcsas_set_model(mcsas_ctx *ctx, int model_id, const double *params, int n_params,
+                               const int *active_idx, int n_active, const double *active_lo,
+                               const double *active_hi, const int *generator_kind, int quad_rule,
+                               int quad_nodes)
+{
+    if (!ctx) return MCSAS_ERR_ARG;
+    if (model_id < 0 || model_id >= MCSAS_N_MODELS) return fail(ctx, MCSAS_ERR_ARG, "unknown model id %d", model_id);
+    if (n_params < 1 || n_params > MCSAS_MAX_PARAMS || !params) return fail(ctx, MCSAS_ERR_ARG, "bad n_params %d", n_params);
+    if (n_active < 0 || n_active > MCSAS_MAX_ACTIVE) return fail(ctx, MCSAS_ERR_ARG, "n_active %d outside [0,%d]", n_active, MCSAS_MAX_ACTIVE);
+    CK(cudaSetDevice(ctx->device));
+    ModelParams mp;
+    memset(&mp, 0, sizeof mp);
+    mp.model_id = model_id; mp.n_params = n_params; mp.n_active = n_active;
+    for (int i = 0; i < n_params; ++i) mp.params[i] = params[i];
+    for (int i = 0; i < n_active; ++i) {
+        if (active_idx[i] < 0 || active_idx[i] >= n_params) return fail(ctx, MCSAS_ERR_ARG, "active_idx[%d]=%d out of range", i, active_idx[i]);
+        if (!(active_lo[i] <= active_hi[i])) return fail(ctx, MCSAS_ERR_ARG, "active range %d is empty", i);
+        if (generator_kind[i] < 0 || generator_kind[i] > 3) return fail(ctx, MCSAS_ERR_ARG, "generator kind %d unknown", generator_kind[i]);
+        mp.active_idx[i] = active_idx[i];
+        mp.lo[i] = active_lo[i]; mp.hi[i] = active_hi[i];
+        mp.gen_kind[i] = generator_kind[i];
+    }
+    int narr = MODEL_NARR[model_id];
+    int D = 0;
+    std::vector<double> qx, qw;
+    if (narr) {
+        D = quad_nodes;
+        if (D < 2 || D > MCSAS_MAX_NODES) return fail(ctx, MCSAS_ERR_ARG, "quad_nodes %d outside [2,%d]", D, MCSAS_MAX_NODES);
+        qx.resize(D); qw.resize(D);
+        std::vector<double> gx, gw;
+        if (quad_rule == MCSAS_QUAD_GAUSS_LEGENDRE) gauss_legendre(D, gx, gw);
+        else if (quad_rule != MCSAS_QUAD_REFERENCE) return fail(ctx, MCSAS_ERR_ARG, "unknown quad rule %d", quad_rule);
+        for (int j = 0; j < D; ++j) {
+            if (model_id == MCSAS_ELLIPSOIDAL_CORE_SHELL) {       // ellipsoidalcoreshell.py:75,:90
+                if (gx.empty()) { qx[j] = linspace_at(0., 1., D, j); qw[j] = 1. / D; }
+                else { qx[j] = 0.5 * (gx[j] + 1.); qw[j] = 0.5 * gw[j]; }
+            } else if (model_id == MCSAS_ELLIPSOIDS_ISOTROPIC) {  // ellipsoidsisotropic.py:65,:71
+                if (gx.empty()) { qx[j] = linspace_at(0., M_PI / 2., D, j); qw[j] = sin(qx[j]) / D; }
+                else { qx[j] = 0.25 * M_PI * (gx[j] + 1.); qw[j] = 0.25 * M_PI * gw[j] * sin(qx[j]); }
+            } else {                                              // cylindersisotropic.py:56,:90
+                if (gx.empty()) {
+                    double step = 1. / (D - 1);
+                    qx[j] = linspace_at(0., 1., D, j);
+                    qw[j] = 16. * ((j == 0 || j == D - 1) ? 0.5 * step : step);
+                } else { qx[j] = 0.5 * (gx[j] + 1.); qw[j] = 16. * 0.5 * gw[j]; }
+            }
+        }
+    }
+    mp.quad_rule = quad_rule;
+    mp.quad_nodes = D;
+    cudaFree(ctx->d_quad);
+    ctx->d_quad = nullptr;
+    CK(cudaMalloc(&ctx->d_quad, sizeof(double) * 2 * (D + 1)));
+    if (D) {
+        CK(cudaMemcpy(ctx->d_quad, qx.data(), sizeof(double) * D, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->d_quad + D, qw.data(), sizeof(double) * D, cudaMemcpyHostToDevice));
+    }
+    ctx->mp = mp;
+    ctx->have_model = true;
+    ctx->have_run = false;
+    return MCSAS_OK;
+}
+
+extern "C" int mcsas_eval(mcsas_ctx *ctx, int set, const double *pset, int m, double comp_exp,
+                          int precision, double *intensity, double *v, double *w, double *s)
+{
+    if (!ctx) return MCSAS_ERR_ARG;
+    if (!ctx->n_sets || !ctx->have_model) return fail(ctx, MCSAS_ERR_STATE, "eval: upload datasets and set a model first");
+    if (set < 0 || set >= ctx->n_sets || m < 1 || !pset) return fail(ctx, MCSAS_ERR_ARG, "eval: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const int P = ctx->mp.n_active, nq = ctx->sets[set].nq, D = ctx->mp.quad_nodes;
+    double *d_p = nullptr, *d_out = nullptr;
+    size_t nout = (size_t)m * nq + 3 * (size_t)m;
+    CK(cudaMalloc(&d_p, sizeof(double) * (size_t)m * (P > 0 ? P : 1)));
+    CK(cudaMalloc(&d_out, sizeof(double) * nout));
+    if (P) CK(cudaMemcpyAsync(d_p, pset, sizeof(double) * (size_t)m * P, cudaMemcpyHostToDevice, ctx->stream));
+    EvalArgs a;
+    a.mp = ctx->mp; a.sets = ctx->d_sets; a.data = ctx->d_data;
+    a.quad_x = ctx->d_quad; a.quad_w = ctx->d_quad + D;
+    a.set = set; a.m = m; a.comp_exp = comp_exp; a.pset = d_p;
+    a.intensity = d_out; a.v = d_out + (size_t)m * nq; a.w = a.v + m; a.s = a.w + m;
+    size_t real = precision == MCSAS_FP64 ? 8 : 4;
+    size_t smem = real * (2 * (D + 1) + (size_t)MODEL_NARR[ctx->mp.model_id] * D) + 16;
+    cudaError_t e = EVAL_FN[ctx->mp.model_id](precision, m, smem, ctx->stream, a);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    std::vector<double> h(nout);
+    if (e == cudaSuccess) e = cudaMemcpy(h.data(), d_out, sizeof(double) * nout, cudaMemcpyDeviceToHost);
+    cudaFree(d_p); cudaFree(d_out);
+    if (e != cudaSuccess) return fail(ctx, MCSAS_ERR_CUDA, "eval kernel: %s", cudaGetErrorString(e));
+    if (intensity) memcpy(intensity, h.data(), sizeof(double) * (size_t)m * nq);
+    if (v) memcpy(v, h.data() + (size_t)m * nq, sizeof(double) * m);
+    if (w) memcpy(w, h.data() + (size_t)m * nq + m, sizeof(double) * m);
+    if (s) memcpy(s, h.data() + (size_t)m * nq + 2 * m, sizeof(double) * m);
+    return MCSAS_OK;
+}
+
+// Shared-memory footprint of chain_kernel (mirrors its carve-up).
+static size_t chain_smem(int nq_pad, int N, int P, int D, int narr, size_t real, int kcap)
+{
+    auto al = [](size_t b) { return (b + 15) & ~size_t(15); };
+    size_t s = 16;
+    s += al(8 * 3 * (size_t)nq_pad);
+    s += al(8 * (size_t)N * (P > 0 ? P : 1));
+    s += al(8 * MCSAS_MAX_SPEC * MCSAS_MAX_ACTIVE);
+    s += al(8 * 16 * MCSAS_MAX_SPEC * 3);
+    s += al(8 * MCSAS_MAX_SPEC * 3);
+    s += al(8 * 8);
+    s += al(real * 8 * MCSAS_MAX_SPEC * 2);
+    s += 2 * al(real * (D + 1));
+    s += real * (size_t)kcap * 2 * narr * D + 16;
+    return s;
+}
+
+static int pick_layout(int nq)
+{
+    const char *env = getenv("MCSAS_B200_LAYOUT");
+    if (env) {
+        int l = atoi(env);
+        if (l >= 0 && l < N_CHAIN_LAYOUTS && CHAIN_LAYOUTS[l].qpt * CHAIN_LAYOUTS[l].max_threads >= nq) return l;
+    }
+    if (nq <= 128) return 0;
+    if (nq <= 256) return 1;
+    if (nq <= 512) return 2;
+    if (nq <= 1024) return 3;
+    if (nq <= 2048) return 5;
+    return 6;
+}
+
+template <class T> static cudaError_t regrow(T **p, size_t n)
+{
+    cudaFree(*p);
+    *p = nullptr;
+    return cudaMalloc((void **)p, sizeof(T) * (n ? n : 1));
+}
+
+extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
+                               const double *proposal_stream, long long stream_stride,
+                               volatile int *stop_flag)
+{
+    (void)stop_flag;
+    if (!ctx || !cfg) return MCSAS_ERR_ARG;
+    if (!ctx->n_sets || !ctx->have_model) return fail(ctx, MCSAS_ERR_STATE, "run: upload datasets and set a model first");
+    if (ctx->running) return fail(ctx, MCSAS_ERR_STATE, "run: previous run not waited for");
+    const ModelParams &mp = ctx->mp;
+    if (mp.n_active < 1) return fail(ctx, MCSAS_ERR_ARG, "run: model has no active fit parameter");
+    if (cfg->n_contribs < 1 || cfg->n_reps < 1 || cfg->max_iter < 0)
+        return fail(ctx, MCSAS_ERR_ARG, "run: n_contribs/n_reps/max_iter invalid");
+    if (cfg->precision != MCSAS_FP64 && cfg->precision != MCSAS_FP32) return fail(ctx, MCSAS_ERR_ARG, "run: unknown precision");
+    CK(cudaSetDevice(ctx->device));
+    const int N = cfg->n_contribs, P = mp.n_active, D = mp.quad_nodes;
+    const int n_chains = ctx->n_sets * cfg->n_reps;
+    const int narr = MODEL_NARR[mp.model_id];
+    const size_t real = cfg->precision == MCSAS_FP64 ? 8 : 4;
+    const int layout = pick_layout(ctx->nq_max);
+    int nq_pad_max = (ctx->nq_max + 1) & ~1;
+    int kcap = cfg->spec_max <= 0 ? MCSAS_MAX_SPEC : (cfg->spec_max > MCSAS_MAX_SPEC ? MCSAS_MAX_SPEC : cfg->spec_max);
+    const size_t smem_limit = (size_t)ctx->prop.sharedMemPerBlockOptin;
+    while (kcap > 1 && chain_smem(nq_pad_max, N, P, D, narr, real, kcap) > smem_limit) kcap /= 2;
+    size_t smem = chain_smem(nq_pad_max, N, P, D, narr, real, kcap);
+    if (smem > smem_limit)
+        return fail(ctx, MCSAS_ERR_ARG, "run: configuration needs %zu B shared memory (> %zu)", smem, smem_limit);
+
+    // proposal stream (deterministic parity mode)
+    const double *d_stream = nullptr;
+    if (proposal_stream) {
+        long long need = (cfg->start_from_minimum ? 0 : (long long)N * P);
+        if (stream_stride < need) return fail(ctx, MCSAS_ERR_STREAM, "proposal stream shorter than the initial draws");
+        long long steps_cover = (stream_stride - need) / P;
+        if (steps_cover < cfg->max_iter)
+            return fail(ctx, MCSAS_ERR_STREAM, "proposal stream covers %lld steps < max_iter %lld",
+                        steps_cover, cfg->max_iter);
+        size_t n = (size_t)n_chains * (size_t)stream_stride;
+        if (n > ctx->stream_cap) { CK(regrow(&ctx->d_stream, n)); ctx->stream_cap = n; }
+        CK(cudaMemcpyAsync(ctx->d_stream, proposal_stream, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+        d_stream = ctx->d_stream;
+    }
+    // outputs
+    size_t need_out = (size_t)n_chains * ((size_t)N * P + ctx->nq_max + 8);
+    if (need_out > ctx->out_cap || n_chains > ctx->n_chains || (size_t)N * P > (size_t)ctx->n_contribs * ctx->n_active) {
+        CK(regrow(&ctx->d_rset, (size_t)n_chains * N * P));
+        CK(regrow(&ctx->d_fit, (size_t)n_chains * ctx->nq_max));
+        CK(regrow(&ctx->d_scal, (size_t)n_chains * 5));
+        CK(regrow(&ctx->d_cnt, (size_t)n_chains * 3));
+        CK(regrow(&ctx->d_att, (size_t)n_chains));
+        ctx->out_cap = need_out;
+    }
+    ctx->have_trace = false;
+    if (cfg->record_trace) {
+        size_t n = (size_t)n_chains * (size_t)cfg->max_iter;
+        if (n > ctx->trace_cap) {
+            CK(regrow(&ctx->d_tacc, n));
+            CK(regrow(&ctx->d_tchi, n));
+            ctx->trace_cap = n;
+        }
+        ctx->have_trace = true;
+    }
+    ChainArgs a;
+    memset(&a, 0, sizeof a);
+    a.mp = mp;
+    a.n_contribs = N; a.n_reps = cfg->n_reps; a.n_chains = n_chains;
+    a.max_attempts = proposal_stream ? 1 : (cfg->max_retries < 0 ? 1 : cfg->max_retries + 2);
+    a.max_iter = cfg->max_iter; a.conv_crit = cfg->conv_crit; a.comp_exp = cfg->comp_exp;
+    a.find_bg = cfg->find_background != 0; a.pos_bg = cfg->positive_background != 0;
+    a.start_min = cfg->start_from_minimum != 0;
+    a.spec_max = kcap; a.first_chain = cfg->first_chain; a.record_trace = cfg->record_trace;
+    a.seed = cfg->seed;
+    a.sets = ctx->d_sets; a.data = ctx->d_data;
+    a.quad_x = ctx->d_quad; a.quad_w = ctx->d_quad + D;
+    a.stream = d_stream; a.stream_stride = stream_stride;
+    *ctx->h_stop = 0;
+    a.stop_flag = ctx->d_stop;
+    a.rset = ctx->d_rset; a.fit_meas = ctx->d_fit; a.nq_stride = ctx->nq_max;
+    a.scaling = ctx->d_scal; a.background = ctx->d_scal + n_chains; a.conval = ctx->d_scal + 2 * n_chains;
+    a.conval0 = ctx->d_scal + 3 * n_chains; a.elapsed_s = ctx->d_scal + 4 * n_chains;
+    a.num_iter = ctx->d_cnt; a.num_moves = ctx->d_cnt + n_chains; a.evals = ctx->d_cnt + 2 * n_chains;
+    a.attempts = ctx->d_att;
+    a.trace_accept = cfg->record_trace ? ctx->d_tacc : nullptr;
+    a.trace_chi = cfg->record_trace ? ctx->d_tchi : nullptr;
+
+    const ChainLayout lay = CHAIN_LAYOUTS[layout];
+    int threads = ((ctx->nq_max + lay.qpt - 1) / lay.qpt + 31) & ~31;
+    if (threads < 32) threads = 32;
+    if (threads > lay.max_threads) threads = lay.max_threads;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    cudaError_t e = CHAIN_FN[mp.model_id](cfg->precision, layout, n_chains, threads, smem, ctx->stream, a);
+    if (e != cudaSuccess) return fail(ctx, MCSAS_ERR_CUDA, "chain kernel launch: %s", cudaGetErrorString(e));
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->n_chains = n_chains; ctx->n_contribs = N; ctx->n_reps = cfg->n_reps; ctx->n_active = P;
+    ctx->max_iter = cfg->max_iter;
+    ctx->running = true;
+    ctx->have_run = false;
+    return MCSAS_OK;
+}
+
+extern "C" int mcsas_request_stop(mcsas_ctx *ctx)
+{
+    if (!ctx) return MCSAS_ERR_ARG;
+    *(volatile int *)ctx->h_stop = 1;
+    return MCSAS_OK;
+}
+
+extern "C" int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms)
+{
+    if (!ctx) return MCSAS_ERR_ARG;
+    if (!ctx->running) return fail(ctx, MCSAS_ERR_STATE, "wait: nothing running");
+    ctx->running = false;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1));
+    ctx->have_run = true;
+    return MCSAS_OK;
+}
+
+extern "C" int mcsas_run(mcsas_ctx *ctx, const mcsas_run_config *cfg, const double *proposal_stream,
+                         long long stream_stride, volatile int *stop_flag)
+{
+    int rc = mcsas_run_async(ctx, cfg, proposal_stream, stream_stride, stop_flag);
+    if (rc) return rc;
+    if (stop_flag) {
+        // McSAS.stop (mcsas.py:357): the caller's flag is forwarded to the kernel's mapped flag
+        while (cudaStreamQuery(ctx->stream) == cudaErrorNotReady) {
+            if (*stop_flag) *(volatile int *)ctx->h_stop = 1;
+            std::this_thread::sleep_for(std::chrono::microseconds(200));
+        }
+    }
+    return mcsas_wait(ctx, nullptr);
+}
+
+extern "C" int mcsas_fetch(mcsas_ctx *ctx, double *contribs, double *fit_meas, double *scaling,
+                           double *background, double *conval, double *conval0, long long *num_iter,
+                           long long *num_moves, int *attempts, double *elapsed_s, long long *evals)
+{
+    if (!ctx) return MCSAS_ERR_ARG;
+    if (!ctx->have_run) return fail(ctx, MCSAS_ERR_STATE, "fetch: no finished run");
+    CK(cudaSetDevice(ctx->device));
+    const int C = ctx->n_chains, N = ctx->n_contribs, P = ctx->n_active, R = ctx->n_reps;
+    if (contribs) {
+        std::vector<double> h((size_t)C * N * P);
+        CK(cudaMemcpy(h.data(), ctx->d_rset, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+        // [chain][N][P] -> [set][N][P][R]
+        for (int c = 0; c < C; ++c) {
+            int s = c / R, r = c % R;
+            for (int i = 0; i < N * P; ++i)
+                contribs[((size_t)s * N * P + i) * R + r] = h[(size_t)c * N * P + i];
+        }
+    }
+    if (fit_meas) {
+        std::vector<double> h((size_t)C * ctx->nq_max);
+        CK(cudaMemcpy(h.data(), ctx->d_fit, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
+        size_t base = 0;
+        for (int s = 0; s < ctx->n_sets; ++s) {
+            int nq = ctx->sets[s].nq;
+            for (int r = 0; r < R; ++r)
+                for (int i = 0; i < nq; ++i)
+                    fit_meas[base + (size_t)i * R + r] = h[(size_t)(s * R + r) * ctx->nq_max + i];
+            base += (size_t)nq * R;
+        }
+    }
+    std::vector<double> sc((size_t)C * 5);
+    CK(cudaMemcpy(sc.data(), ctx->d_scal, sizeof(double) * sc.size(), cudaMemcpyDeviceToHost));
+    if (scaling) memcpy(scaling, sc.data(), sizeof(double) * C);
+    if (background) memcpy(background, sc.data() + C, sizeof(double) * C);
+    if (conval) memcpy(conval, sc.data() + 2 * (size_t)C, sizeof(double) * C);
+    if (conval0) memcpy(conval0, sc.data() + 3 * (size_t)C, sizeof(double) * C);
+    if (elapsed_s) memcpy(elapsed_s, sc.data() + 4 * (size_t)C, sizeof(double) * C);
+    if (num_iter) CK(cudaMemcpy(num_iter, ctx->d_cnt, sizeof(long long) * C, cudaMemcpyDeviceToHost));
+    if (num_moves) CK(cudaMemcpy(num_moves, ctx->d_cnt + C, sizeof(long long) * C, cudaMemcpyDeviceToHost));
+    if (evals) CK(cudaMemcpy(evals, ctx->d_cnt + 2 * (size_t)C, sizeof(long long) * C, cudaMemcpyDeviceToHost));
+    if (attempts) CK(cudaMemcpy(attempts, ctx->d_att, sizeof(int) * C, cudaMemcpyDeviceToHost));
+    return MCSAS_OK;
+}
+
+extern "C" int mcsas_fetch_trace(mcsas_ctx *ctx, int chain, unsigned char *accept, double *chi,
+                                 long long capacity)
+{
+    if (!ctx) return MCSAS_ERR_ARG;
+    if (!ctx->have_run || !ctx->have_trace) return fail(ctx, MCSAS_ERR_STATE, "fetch_trace: last run recorded no trace");
+    if (chain < 0 || chain >= ctx->n_chains) return fail(ctx, MCSAS_ERR_ARG, "fetch_trace: chain out of range");
+    CK(cudaSetDevice(ctx->device));
+    long long nit = 0;
+    CK(cudaMemcpy(&nit, ctx->d_cnt + chain, sizeof(long long), cudaMemcpyDeviceToHost));
+    if (nit > capacity) nit = capacity;
+    if (accept && nit) CK(cudaMemcpy(accept, ctx->d_tacc + (size_t)chain * ctx->max_iter, (size_t)nit, cudaMemcpyDeviceToHost));
+    if (chi && nit) CK(cudaMemcpy(chi, ctx->d_tchi + (size_t)chain * ctx->max_iter, sizeof(double) * (size_t)nit, cudaMemcpyDeviceToHost));
+    return MCSAS_OK;
+}
+
+extern "C" int mcsas_fractions(mcsas_ctx *ctx, const mcsas_run_config *cfg, const double *contribs,
+                               double *vol_frac, double *num_frac, double *volsqr_frac,
+                               double *surf_frac, double *min_vol, double *min_num,
+                               double *min_volsqr, double *min_surf, double *totals, double *sc)
+{
+    if (!ctx || !cfg || !contribs) return MCSAS_ERR_ARG;
+    if (!ctx->n_sets || !ctx->have_model) return fail(ctx, MCSAS_ERR_STATE, "fractions: upload datasets and set a model first");
+    CK(cudaSetDevice(ctx->device));
+    const int N = cfg->n_contribs, R = cfg->n_reps, P = ctx->mp.n_active, D = ctx->mp.quad_nodes;
+    const int C = ctx->n_sets * R;
+    std::vector<double> h((size_t)C * N * P);
+    for (int c = 0; c < C; ++c) {                   // [set][N][P][R] -> [chain][N][P]
+        int s = c / R, r = c % R;
+        for (int i = 0; i < N * P; ++i) h[(size_t)c * N * P + i] = contribs[((size_t)s * N * P + i) * R + r];
+    }
+    double *d_r = nullptr, *d_o = nullptr;
+    size_t nout = (size_t)C * N * 8 + (size_t)C * 6;
+    CK(cudaMalloc(&d_r, sizeof(double) * h.size()));
+    CK(cudaMalloc(&d_o, sizeof(double) * nout));
+    CK(cudaMemcpyAsync(d_r, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
+    FractionArgs a;
+    a.mp = ctx->mp; a.sets = ctx->d_sets; a.data = ctx->d_data;
+    a.quad_x = ctx->d_quad; a.quad_w = ctx->d_quad + D;
+    a.n_contribs = N; a.n_reps = R; a.n_chains = C; a.comp_exp = cfg->comp_exp;
+    a.find_bg = cfg->find_background != 0; a.pos_bg = cfg->positive_background != 0;
+    a.rset = d_r; a.out = d_o; a.totals = d_o + (size_t)C * N * 8; a.sc = a.totals + (size_t)C * 4;
+    size_t real = cfg->precision == MCSAS_FP64 ? 8 : 4;
+    size_t smem = real * (2 * (D + 1) + (size_t)MODEL_NARR[ctx->mp.model_id] * D) + 8 * (size_t)ctx->nq_max + 64 * 8 + 64;
+    cudaError_t e = mcsas_launch_fractions(cfg->precision, ctx->mp.model_id, C, smem, ctx->stream, a);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    std::vector<double> o(nout);
+    if (e == cudaSuccess) e = cudaMemcpy(o.data(), d_o, sizeof(double) * nout, cudaMemcpyDeviceToHost);
+    cudaFree(d_r); cudaFree(d_o);
+    if (e != cudaSuccess) return fail(ctx, MCSAS_ERR_CUDA, "fractions kernel: %s", cudaGetErrorString(e));
+    double *outs[8] = {vol_frac, num_frac, volsqr_frac, surf_frac, min_vol, min_num, min_volsqr, min_surf};
+    for (int k = 0; k < 8; ++k) {
+        if (!outs[k]) continue;
+        for (int c = 0; c < C; ++c) {               // [k][chain][N] -> [set][N][R]
+            int s = c / R, r = c % R;
+            for (int i = 0; i < N; ++i)
+                outs[k][((size_t)s * N + i) * R + r] = o[((size_t)k * C + c) * N + i];
+        }
+    }
+    const double *tot = o.data() + (size_t)C * N * 8, *scv = tot + (size_t)C * 4;
+    for (int c = 0; c < C; ++c) {
+        int s = c / R, r = c % R;
+        if (totals) for (int k = 0; k < 4; ++k) totals[((size_t)s * 4 + k) * R + r] = tot[(size_t)c * 4 + k];
+        if (sc) for (int k = 0; k < 2; ++k) sc[((size_t)s * 2 + k) * R + r] = scv[(size_t)c * 2 + k];
+    }
+    return MCSAS_OK;
+}
+
+extern "C" int mcsas_measure_peaks(mcsas_ctx *ctx, double *mufu_gops, double *ffma_tflops)
+{
+    if (!ctx) return MCSAS_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    float *d_out = nullptr;
+    const int threads = 256, grid = ctx->prop.multiProcessorCount * 8, iters = 4096;
+    CK(cudaMalloc(&d_out, sizeof(float) * (size_t)grid * threads));
+    double res[2] = {0., 0.};
+    for (int which = 0; which < 2; ++which) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 5; ++rep) {
+            CK(cudaEventRecord(ctx->ev0, ctx->stream));
+            cudaError_t e = mcsas_launch_peaks(which, grid, threads, iters, d_out, ctx->stream);
+            if (e != cudaSuccess) { cudaFree(d_out); return fail(ctx, MCSAS_ERR_CUDA, "peaks kernel: %s", cudaGetErrorString(e)); }
+            CK(cudaEventRecord(ctx->ev1, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        // per thread and iteration: which 0 -> 24 MUFU ops (8 x sin,cos,rcp); 1 -> 64 FFMA = 128 flop
+        double ops = (double)grid * threads * iters * (which == 0 ? 24. : 128.);
+        res[which] = ops / (best * 1e-3);
+    }
+    cudaFree(d_out);
+    if (mufu_gops) *mufu_gops = res[0] * 1e-9;
+    if (ffma_tflops) *ffma_tflops = res[1] * 1e-12;
+    return MCSAS_OK;
+}

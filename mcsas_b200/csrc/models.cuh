@@ -1,0 +1,471 @@
+// models.cuh -- device form factors of the McSAS model plug-ins.
+//
+// Every model is split into
+//   prep():  once per contribution (one thread): volume, weight w = V^(2c), per-node
+//            geometry of the orientation average -> Contrib<Real> (+ node arrays in smem)
+//   eval():  once per (contribution, q point): intensity  it = F(q)^2 * w
+// Real = double: parity mode, SI units, reference operation order.
+// Real = float : production mode, lengths in nm / q in 1/nm, sin/cos/rcp on the MUFU
+//                pipe with an exact-FMA phase reduction; amplitudes are scaled by a
+//                per-run constant G (kept in fp64) so fp32 never leaves its range.
+#pragma once
+#include "common.cuh"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+template <class Real> struct QRep;
+template <> struct QRep<double> {
+    double q;
+    __device__ void set(double q_si) { q = q_si; }
+};
+template <> struct QRep<float> {
+    float q;        // 1/nm
+    float th, tl;   // q/(2 pi) in turns per nm, split hi + lo
+    __device__ void set(double q_si) {
+        double qn = q_si * 1e-9;
+        q = (float)qn;
+        double t = qn * 0.15915494309189535;
+        th = (float)t;
+        tl = (float)(t - (double)th);
+    }
+};
+
+template <class Real> struct Units;
+template <> struct Units<double> { static constexpr double LEN = 1.0; };   // metres
+template <> struct Units<float> { static constexpr double LEN = 1e9; };    // nanometres
+
+// x = q*r and sin/cos(x)
+__device__ __forceinline__ void sincos_qr(const QRep<double> &Q, double r, double &s, double &c,
+                                          double &x)
+{
+    x = Q.q * r;
+    sincos(x, &s, &c);
+}
+
+__device__ __forceinline__ void sincos_qr(const QRep<float> &Q, float r, float &s, float &c,
+                                          float &x)
+{
+    // phase in turns, reduced with an exact FMA residual so that q*r ~ 1e3..1e4 rad keeps
+    // ~1e-7 turn accuracy; then MUFU.SIN / MUFU.COS on [-pi, pi].
+    x = Q.q * r;
+    float t = Q.th * r;
+    float e = fmaf(Q.th, r, -t);
+    float lo = fmaf(Q.tl, r, e);
+    float n = (t + 12582912.f) - 12582912.f;           // rint for |t| < 2^22
+    float fr = (t - n) + lo;
+    float a = fr * 6.2831853071795865f;
+    s = __sinf(a);
+    c = __cosf(a);
+}
+
+__device__ __forceinline__ float fast_rcp(float x)      // MUFU.RCP
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// 3 (sin x - x cos x) / x^3     (sphere.py:62)
+__device__ __forceinline__ double sph_ff(const QRep<double> &Q, double r)
+{
+    double s, c, x;
+    sincos_qr(Q, r, s, c, x);
+    return 3. * (s - x * c) / (x * x * x);
+}
+
+__device__ __forceinline__ float sph_ff(const QRep<float> &Q, float r)
+{
+    float s, c, x;
+    sincos_qr(Q, r, s, c, x);
+    float x2 = x * x;
+    float big = 3.f * (s - x * c) * fast_rcp(x2 * x);
+    // series below x = 1: MUFU's absolute error would be amplified by 3/x^3
+    float ser = 1.f + x2 * (-0.1f + x2 * (3.5714286e-3f + x2 * (-6.6137566e-5f
+                + x2 * (7.5156325e-7f + x2 * -5.7812558e-9f))));
+    return x < 1.f ? ser : big;
+}
+
+template <class Real> struct Contrib {
+    Real amp;        // w (fp64) or w*G*(model scale)^2 (fp32)
+    Real c[7];
+};
+
+// Volume / weight / surface triple returned by prep (fp64, SI).
+struct VWS { double v, w, s, amp_raw; };
+
+template <class Real> struct QuadTab {
+    int D;
+    int rule;
+    const Real *x;
+    const Real *wt;
+};
+
+template <int MODEL, class Real> struct Ops;
+
+// ------------------------------------------------------------------ Sphere --
+template <class Real> struct Ops<MCSAS_SPHERE, Real> {
+    static constexpr int NARR = 0;
+    __device__ static VWS prep(const double *p, double ce, double G, const QuadTab<Real> &,
+                               Contrib<Real> &cc, Real *)
+    {
+        double r = p[0], sld = p[1];
+        VWS o;
+        double vol = (M_PI * 4. / 3.) * (r * r * r);    // sphere.py:44
+        o.v = vol * sld * sld;                          // :53
+        o.s = 4. * M_PI * r * r;                        // :37
+        o.w = pow(vol, 2. * ce);                        // sasmodel.py:44
+        o.amp_raw = o.w;
+        cc.amp = (Real)(o.amp_raw * G);
+        cc.c[0] = (Real)(r * Units<Real>::LEN);
+        return o;
+    }
+    __device__ __forceinline__ static Real eval(const Contrib<Real> &cc, const Real *,
+                                                const QuadTab<Real> &, const QRep<Real> &Q)
+    {
+        Real F = sph_ff(Q, cc.c[0]);
+        return (F * F) * cc.amp;                        // sasmodel.py:77
+    }
+};
+
+// --------------------------------------------------------- LMADenseSphere --
+// The structure factor has x^-5 cancellations (lmadensesphere.py:76-86): it is kept
+// in fp64 in both precision modes.
+template <class Real> struct Ops<MCSAS_LMA_DENSE_SPHERE, Real> {
+    static constexpr int NARR = 0;
+    __device__ static VWS prep(const double *p, double ce, double G, const QuadTab<Real> &,
+                               Contrib<Real> &cc, Real *)
+    {
+        double r = p[0], mu = p[1], mf = p[2], sld = p[3];
+        if (mf == -1.) mf = pow(0.634 / mu, 1. / 3);    // :73-74
+        VWS o;
+        double vol = (M_PI * 4. / 3.) * (r * r * r);
+        o.v = vol * sld * sld;
+        o.s = 0.;
+        o.w = pow(vol, 2. * ce);
+        o.amp_raw = o.w;
+        cc.amp = (Real)(o.amp_raw * G);
+        cc.c[0] = (Real)(r * Units<Real>::LEN);
+        cc.c[1] = (Real)(mf * r * Units<Real>::LEN);
+        cc.c[2] = (Real)mu;
+        return o;
+    }
+    __device__ static double SFG(double A, double mu)
+    {
+        double om = 1. - mu, om4 = om * om * om * om;
+        double alpha = (1. + 2. * mu) * (1. + 2. * mu) / om4;
+        double beta = -6. * mu * (1. + mu / 2.) * (1. + mu / 2.) / om4;
+        double gamma = mu * alpha / 2.;
+        double sA, cA;
+        sincos(A, &sA, &cA);
+        double A2 = A * A, A3 = A2 * A, A4 = A2 * A2, A5 = A4 * A;
+        return alpha * (sA - A * cA) / A2
+             + beta * (2. * A * sA + (2. - A2) * cA - 2.) / A3
+             + gamma * (-1. * A4 * cA + 4. * ((3. * A2 - 6.) * cA + (A3 - 6. * A) * sA + 6.)) / A5;
+    }
+    __device__ static Real eval(const Contrib<Real> &cc, const Real *, const QuadTab<Real> &,
+                                const QRep<Real> &Q)
+    {
+        Real F = sph_ff(Q, cc.c[0]);
+        double A = 2. * (double)Q.q * (double)cc.c[1];                    // :91
+        double S = 1. / (1. + 24. * (double)cc.c[2] * SFG(A, (double)cc.c[2]) / A);   // :93
+        return (Real)((double)(F * F) * S) * cc.amp;                      // :101 squared
+    }
+};
+
+// ------------------------------------------------------ SphericalCoreShell --
+template <class Real> struct Ops<MCSAS_SPHERICAL_CORE_SHELL, Real> {
+    static constexpr int NARR = 0;
+    __device__ static VWS prep(const double *p, double ce, double G, const QuadTab<Real> &,
+                               Contrib<Real> &cc, Real *)
+    {
+        double r = p[0], t = p[1], ec = p[2], es = p[3], esol = p[4];
+        double vc = 4. / 3 * M_PI * (r * r * r), vt = 4. / 3 * M_PI * ((r + t) * (r + t) * (r + t));
+        double vr = vc / vt;                            // :61-63
+        double d1 = es - esol, d2 = vr * (es - ec);     // ks, vRatio*kc prefactors :64-69
+        VWS o;
+        o.v = vt; o.s = 0.;                             // :72-76
+        o.w = pow(vt, 2. * ce);
+        double nrm = 1.;
+        if (sizeof(Real) == 4) {
+            nrm = fmax(fabs(d1), fabs(d2));
+            if (nrm == 0.) nrm = 1.;
+        }
+        o.amp_raw = o.w * nrm * nrm;
+        cc.amp = (Real)(o.amp_raw * G);
+        cc.c[0] = (Real)((r + t) * Units<Real>::LEN);
+        cc.c[1] = (Real)(r * Units<Real>::LEN);
+        cc.c[2] = (Real)(d1 / nrm);
+        cc.c[3] = (Real)(d2 / nrm);
+        return o;
+    }
+    __device__ __forceinline__ static Real eval(const Contrib<Real> &cc, const Real *,
+                                                const QuadTab<Real> &, const QRep<Real> &Q)
+    {
+        Real F = cc.c[2] * sph_ff(Q, cc.c[0]) - cc.c[3] * sph_ff(Q, cc.c[1]);
+        return (F * F) * cc.amp;
+    }
+};
+
+// ---------------------------------------------------- EllipsoidalCoreShell --
+template <class Real> struct Ops<MCSAS_ELLIPSOIDAL_CORE_SHELL, Real> {
+    static constexpr int NARR = 2;
+    __device__ static VWS prep(const double *p, double ce, double G, const QuadTab<Real> &qt,
+                               Contrib<Real> &cc, Real *nodes)
+    {
+        double a = p[0], b = p[1], t = p[2], ec = p[3], es = p[4], esol = p[5];
+        double vc = 4. / 3. * M_PI * a * (b * b);
+        double vt = 4. / 3. * M_PI * (a + t) * ((b + t) * (b + t));
+        double k1 = (ec - es) * (vc / vt), k2 = (es - esol) * 1.;   // :83-88
+        VWS o;
+        o.v = vt; o.s = 0.;                             // :93-97
+        o.w = pow(vt, 2. * ce);
+        double nrm = 1.;
+        if (sizeof(Real) == 4) {
+            nrm = fmax(fabs(k1), fabs(k2));
+            if (nrm == 0.) nrm = 1.;
+        }
+        o.amp_raw = o.w * nrm * nrm;
+        cc.amp = (Real)(o.amp_raw * G);
+        cc.c[0] = (Real)(k1 / nrm);
+        cc.c[1] = (Real)(k2 / nrm);
+        for (int j = 0; j < qt.D; ++j) {
+            double mu = (double)qt.x[j];
+            nodes[j] = (Real)(sqrt(a * a * mu * mu + b * b * (1. - mu * mu)) * Units<Real>::LEN);
+            nodes[qt.D + j] = (Real)(sqrt((a + t) * (a + t) * mu * mu
+                                          + (b + t) * (b + t) * (1. - mu * mu)) * Units<Real>::LEN);
+        }
+        return o;
+    }
+    __device__ static Real eval(const Contrib<Real> &cc, const Real *nodes,
+                                const QuadTab<Real> &qt, const QRep<Real> &Q)
+    {
+        Real acc = 0;
+#pragma unroll 2
+        for (int j = 0; j < qt.D; ++j) {
+            Real f = cc.c[0] * sph_ff(Q, nodes[j]) + cc.c[1] * sph_ff(Q, nodes[qt.D + j]);
+            acc += qt.wt[j] * (f * f);
+        }
+        return acc * cc.amp;                            // sqrt(mean)^2 * w  :90
+    }
+};
+
+// ----------------------------------------------------- EllipsoidsIsotropic --
+template <class Real> struct Ops<MCSAS_ELLIPSOIDS_ISOTROPIC, Real> {
+    static constexpr int NARR = 1;
+    __device__ static VWS prep(const double *p, double ce, double G, const QuadTab<Real> &qt,
+                               Contrib<Real> &cc, Real *nodes)
+    {
+        double Ra = p[0], Rc = (p[1] != 0.) ? p[0] * p[3] : p[2], sld = p[5];   // :60-63
+        VWS o;
+        double vol = 4. / 3. * M_PI * (Ra * Ra) * Rc;   // :80
+        o.v = vol * sld * sld; o.s = 0.;                // :84
+        o.w = pow(vol, 2. * ce);
+        o.amp_raw = o.w;
+        cc.amp = (Real)(o.amp_raw * G);
+        for (int j = 0; j < qt.D; ++j) {
+            double sa, ca;
+            sincos((double)qt.x[j], &sa, &ca);
+            nodes[j] = (Real)(sqrt(Ra * Ra * (sa * sa) + Rc * Rc * (ca * ca)) * Units<Real>::LEN);  // :56
+        }
+        return o;
+    }
+    __device__ static Real eval(const Contrib<Real> &cc, const Real *nodes,
+                                const QuadTab<Real> &qt, const QRep<Real> &Q)
+    {
+        Real acc = 0;
+#pragma unroll 4
+        for (int j = 0; j < qt.D; ++j) {
+            Real f = sph_ff(Q, nodes[j]);               // :67-68
+            acc += qt.wt[j] * (f * f);                  // :71 (weights carry sin(alpha)/D)
+        }
+        return acc * cc.amp;
+    }
+};
+
+// ------------------------------------------------------ CylindersIsotropic --
+__device__ __forceinline__ double bessel_j1(double x) { return j1(x); }
+__device__ __forceinline__ float bessel_j1(float x) { return j1f(x); }
+
+template <class Real> struct Ops<MCSAS_CYLINDERS_ISOTROPIC, Real> {
+    static constexpr int NARR = 2;
+    __device__ static VWS prep(const double *p, double ce, double G, const QuadTab<Real> &qt,
+                               Contrib<Real> &cc, Real *nodes)
+    {
+        double r = p[0], hL = (p[1] != 0.) ? p[0] * p[3] : 0.5 * p[2], sld = p[5];  // :65-68
+        VWS o;
+        double vol = M_PI * (r * r) * (hL * 2.);        // :93-98
+        o.v = vol * sld * sld; o.s = 0.;                // :101
+        o.w = pow(vol, 2. * ce);
+        o.amp_raw = o.w;
+        cc.amp = (Real)(o.amp_raw * G);
+        cc.c[0] = (Real)(r * Units<Real>::LEN);
+        cc.c[1] = (Real)(hL * Units<Real>::LEN);
+        for (int j = 0; j < qt.D; ++j) {
+            double x = (double)qt.x[j];
+            nodes[j] = (Real)(r * sqrt(1. - x * x) * Units<Real>::LEN);    // :70
+            nodes[qt.D + j] = (Real)(hL * x * Units<Real>::LEN);          // :71 (B/2 = q hL x)
+        }
+        return o;
+    }
+    __device__ static Real eval(const Contrib<Real> &cc, const Real *nodes,
+                                const QuadTab<Real> &qt, const QRep<Real> &Q)
+    {
+        Real acc = 0;
+        int j0 = 0, j1e = qt.D;
+        if (qt.rule == MCSAS_QUAD_REFERENCE) {
+            // endpoint columns replaced by their limits (:79-82), trapz half weights (:90)
+            Real s, c, x;
+            Real qr = Q.q * cc.c[0];
+            Real f0 = (Real)0.5 * (bessel_j1(qr) / qr);
+            sincos_qr(Q, cc.c[1], s, c, x);
+            Real f1 = s / x;
+            acc = qt.wt[0] * (f0 * f0) + qt.wt[qt.D - 1] * (f1 * f1);
+            j0 = 1; j1e = qt.D - 1;
+        }
+        for (int j = j0; j < j1e; ++j) {
+            Real s, c, hb;
+            Real A = Q.q * nodes[j];
+            sincos_qr(Q, nodes[qt.D + j], s, c, hb);    // hb = B/2
+            Real f = bessel_j1(A) * s / (A * ((Real)2 * hb));   // :74-76
+            acc += qt.wt[j] * (f * f);
+        }
+        return acc * cc.amp;                            // weights carry the factor 16 (:90)
+    }
+};
+
+// ----------------------------------------------------------- GaussianChain --
+template <class Real> struct Ops<MCSAS_GAUSSIAN_CHAIN, Real> {
+    static constexpr int NARR = 0;
+    __device__ static VWS prep(const double *p, double ce, double G, const QuadTab<Real> &,
+                               Contrib<Real> &cc, Real *)
+    {
+        double rg = p[0], bp = p[1], etas = p[2], k = p[3];
+        double beta = bp - (k * (rg * rg)) * etas;      // :56
+        VWS o;
+        double vol = k * (rg * rg);                     // :64
+        o.v = vol; o.s = 0.;
+        o.w = pow(vol, 2. * ce);
+        if (sizeof(Real) == 4) {
+            o.amp_raw = o.w * beta * beta;
+            cc.c[1] = (Real)1;
+        } else {
+            o.amp_raw = o.w;
+            cc.c[1] = (Real)beta;
+        }
+        cc.amp = (Real)(o.amp_raw * G);
+        cc.c[0] = (Real)(rg * Units<Real>::LEN);
+        return o;
+    }
+    __device__ __forceinline__ static double shape(double u)
+    {
+        return sqrt(2.) * sqrt(expm1(-u) + u) / u;      // :58
+    }
+    __device__ __forceinline__ static float shape(float u)
+    {
+        // 2 (e^-u - 1 + u)/u^2 = 1 - u/3 + u^2/12 - ...  for small u (cancellation)
+        float ser = 1.f + u * (-0.33333333f + u * (0.083333333f + u * (-0.016666667f
+                    + u * (2.7777778e-3f + u * (-3.9682540e-4f + u * 4.9603175e-5f)))));
+        float big = 2.f * (__expf(-u) - 1.f + u) * fast_rcp(u * u);
+        return sqrtf(u < 0.5f ? ser : big);
+    }
+    __device__ __forceinline__ static Real eval(const Contrib<Real> &cc, const Real *,
+                                                const QuadTab<Real> &, const QRep<Real> &Q)
+    {
+        Real x = Q.q * cc.c[0];
+        Real u = x * x;                                 // :57
+        Real F = shape(u) * cc.c[1];
+        if (Q.q <= (Real)0) F = cc.c[1];                // :60
+        return (F * F) * cc.amp;
+    }
+};
+
+// -------------------------------------------------------------- Kholodenko --
+// p0^2 = int_0^x core(z) dz (kholodenko.py:16-38) by composite 16-point Gauss-Legendre:
+// panels follow the oscillation sin(f z) and the decay 1/sinh z; sinh ratios are written
+// with decaying exponentials only (no overflow).  Evaluated in fp64 in both modes (the
+// integrand needs ~1e-10 cancellation accuracy); fp32 mode only changes the LSQ side.
+static __constant__ double GL16_X[8] = {
+    0.0950125098376374401853193, 0.2816035507792589132304605, 0.4580167776572273863424194,
+    0.6178762444026437484466718, 0.7554044083550030338951012, 0.8656312023878317438804679,
+    0.9445750230732325760779884, 0.9894009349916499325961542 };
+static __constant__ double GL16_W[8] = {
+    0.1894506104550684962853967, 0.1826034150449235888667637, 0.1691565193950025381893121,
+    0.1495959888165767320815017, 0.1246289712555338720524763, 0.0951585116824927848099251,
+    0.0622535239386478928628438, 0.0271524594117540948517806 };
+
+static __device__ __noinline__ double kho_core(double z, int regime, double ef, double x)
+{
+    if (z <= 0.0) return 1.0;
+    double fz;
+    double em2 = exp(-2. * z);
+    if (regime < 0) {            // q < 3/lK: sinh(e z)/(e sinh z)
+        fz = exp((ef - 1.) * z) * (1. - exp(-2. * ef * z)) / (ef * (1. - em2));
+    } else if (regime > 0) {     // q > 3/lK: sin(f z)/(f sinh z)
+        fz = 2. * sin(ef * z) * exp(-z) / (ef * (1. - em2));
+    } else {
+        fz = 2. * z * exp(-z) / (1. - em2);
+    }
+    return fz * (2. / x) * (1.0 - z / x);
+}
+
+template <class Real> struct Ops<MCSAS_KHOLODENKO, Real> {
+    static constexpr int NARR = 0;
+    __device__ static VWS prep(const double *p, double ce, double G, const QuadTab<Real> &,
+                               Contrib<Real> &cc, Real *)
+    {
+        double R = p[0], lk = p[1], L = p[2];
+        VWS o;
+        double vol = M_PI * L * (R * R);                // :93
+        o.v = vol; o.s = 0.;
+        o.w = pow(vol, 2. * ce);
+        o.amp_raw = o.w;
+        cc.amp = (Real)(o.amp_raw * G);
+        cc.c[0] = (Real)(R * Units<Real>::LEN);
+        cc.c[1] = (Real)(lk * Units<Real>::LEN);
+        cc.c[2] = (Real)(3. * L / lk);                  // x, :86
+        return o;
+    }
+    __device__ __noinline__ static Real eval(const Contrib<Real> &cc, const Real *,
+                                             const QuadTab<Real> &, const QRep<Real> &Q)
+    {
+        double q = (double)Q.q, R = (double)cc.c[0], lk = (double)cc.c[1], x = (double)cc.c[2];
+        double u = q * R;
+        double pcs = (u <= 0.0) ? 1.0 : 2. * j1(u) / u; // :40-45
+        double t = q * q * lk * lk / 9.;
+        int regime = (q < 3.0 / lk) ? -1 : ((q > 3.0 / lk) ? 1 : 0);
+        double ef = regime < 0 ? sqrt(1.0 - t) : (regime > 0 ? sqrt(t - 1.0) : 0.);
+        // the integrand is negligible beyond zc for the oscillating branch; the
+        // sinh-ratio branch decays like exp(-(1-e) z) and may need the full range
+        double rate = regime < 0 ? (1. - ef) : 1.;
+        double zc = fmin(x, 42. / fmax(rate, 1e-3));
+        double h = 1.0;                                 // panel width
+        if (regime > 0) h = fmin(1.0, 2.5 / ef);
+        int np = (int)ceil(zc / h);
+        if (np < 4) np = 4;
+        h = zc / np;
+        double acc = 0.;
+        for (int i = 0; i < np; ++i) {
+            double c0 = (i + 0.5) * h, s = 0.;
+#pragma unroll 1
+            for (int j = 0; j < 8; ++j) {
+                double dz = 0.5 * h * GL16_X[j];
+                s += GL16_W[j] * (kho_core(c0 - dz, regime, ef, x) + kho_core(c0 + dz, regime, ef, x));
+            }
+            acc += s;
+        }
+        acc *= 0.5 * h;
+        double F2 = acc * (pcs * pcs);                  // (p0 * pcs)^2, :90
+        return (Real)F2 * cc.amp;
+    }
+};
+
+// Patch the active values into the full parameter vector
+// (scatteringmodel.py:94-96  p.setValue(v) for each active parameter).
+__device__ __forceinline__ void patch_params(const ModelParams &mp, const double *pv, double *p)
+{
+#pragma unroll
+    for (int i = 0; i < MCSAS_MAX_PARAMS; ++i) p[i] = mp.params[i];
+    for (int i = 0; i < mp.n_active; ++i) p[mp.active_idx[i]] = pv[i];
+}

@@ -1,0 +1,190 @@
+# -*- coding: utf-8 -*-
+"""Engine: numpy-facing wrapper of one C-ABI context (one GPU).
+
+This is plumbing between the McSAS-compatible host classes (mcsas.py, models.py) and
+libmcsas_b200.so; all arrays are float64 host buffers in SI units, as the reference
+hands them to McSAS.mcFit."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import McSASB200Error, RunConfig
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int)) if a is not None else None
+
+
+def _llp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_longlong)) if a is not None else None
+
+
+class Engine(object):
+    def __init__(self, device=0):
+        self._L = _lib.lib()
+        self._ctx = C.c_void_p()
+        rc = self._L.mcsas_ctx_create(int(device), C.byref(self._ctx))
+        if rc != 0:
+            msg = self._L.mcsas_last_error(None)
+            raise McSASB200Error("mcsas_ctx_create(%d) failed (%d): %s" % (
+                device, rc, msg.decode() if msg else "?"))
+        self.device = device
+        self.nq = None
+        self.n_sets = 0
+        self.n_active = 0
+        self._last = None
+
+    def close(self):
+        if self._ctx:
+            self._L.mcsas_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self._L.mcsas_last_error(self._ctx)
+            raise McSASB200Error("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+    def device_info(self):
+        sm, khz = C.c_int(), C.c_int()
+        name = C.create_string_buffer(128)
+        self._check(self._L.mcsas_device_info(self._ctx, C.byref(sm), C.byref(khz), name, 128),
+                    "device_info")
+        return dict(sm_count=sm.value, clock_khz=khz.value, name=name.value.decode())
+
+    def upload_datasets(self, datasets):
+        """datasets: list of (q, I, sigma) float64 arrays (SI units)."""
+        nq = np.array([len(d[0]) for d in datasets], dtype=np.int32)
+        q = np.ascontiguousarray(np.concatenate([np.asarray(d[0], dtype=np.float64).ravel() for d in datasets]))
+        I = np.ascontiguousarray(np.concatenate([np.asarray(d[1], dtype=np.float64).ravel() for d in datasets]))
+        s = np.ascontiguousarray(np.concatenate([np.asarray(d[2], dtype=np.float64).ravel() for d in datasets]))
+        if not (q.size == I.size == s.size):
+            raise McSASB200Error("q, I, sigma lengths differ")
+        self._check(self._L.mcsas_upload_datasets(self._ctx, len(datasets), _ip(nq), _dp(q), _dp(I), _dp(s)),
+                    "upload_datasets")
+        self.nq = nq.copy()
+        self.n_sets = len(datasets)
+
+    def set_model(self, model_id, params, active_idx, lo, hi, gen_kind, quad_rule=0, quad_nodes=0):
+        params = np.ascontiguousarray(params, dtype=np.float64)
+        active_idx = np.ascontiguousarray(active_idx, dtype=np.int32)
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        gen_kind = np.ascontiguousarray(gen_kind, dtype=np.int32)
+        self._check(self._L.mcsas_set_model(self._ctx, int(model_id), _dp(params), params.size,
+                                            _ip(active_idx), active_idx.size, _dp(lo), _dp(hi),
+                                            _ip(gen_kind), int(quad_rule), int(quad_nodes)),
+                    "set_model")
+        self.n_active = int(active_idx.size)
+
+    def eval(self, pset, comp_exp, set_index=0, precision=_lib.FP64):
+        """ScatteringModel.calc on single contributions -> (it[M,nq], v, w, s)."""
+        pset = np.ascontiguousarray(np.atleast_2d(pset), dtype=np.float64)
+        M = pset.shape[0]
+        nq = int(self.nq[set_index])
+        it = np.zeros((M, nq))
+        v, w, s = np.zeros(M), np.zeros(M), np.zeros(M)
+        self._check(self._L.mcsas_eval(self._ctx, int(set_index), _dp(pset), M, float(comp_exp),
+                                       int(precision), _dp(it), _dp(v), _dp(w), _dp(s)), "eval")
+        return it, v, w, s
+
+    @staticmethod
+    def make_config(n_contribs=300, n_reps=10, conv_crit=1.0, max_iter=100000, max_retries=5,
+                    comp_exp=0.6666666, find_background=True, positive_background=False,
+                    start_from_minimum=False, precision=_lib.FP32, seed=0, spec_max=0,
+                    record_trace=False, first_chain=0):
+        return RunConfig(int(n_contribs), int(n_reps), float(conv_crit), int(max_iter),
+                         int(max_retries), float(comp_exp), int(bool(find_background)),
+                         int(bool(positive_background)), int(bool(start_from_minimum)),
+                         int(precision), int(seed) & 0xFFFFFFFFFFFFFFFF, int(spec_max),
+                         int(bool(record_trace)), int(first_chain))
+
+    def run_async(self, cfg, stream=None):
+        stride = 0
+        sp = None
+        if stream is not None:
+            stream = np.ascontiguousarray(stream, dtype=np.float64)
+            n_chains = self.n_sets * cfg.n_reps
+            stream = stream.reshape(n_chains, -1)
+            stride = stream.shape[1]
+            sp = _dp(stream)
+            self._stream_keepalive = stream
+        self._check(self._L.mcsas_run_async(self._ctx, C.byref(cfg), sp, C.c_longlong(stride), None),
+                    "run_async")
+        self._last = cfg
+
+    def wait(self):
+        ms = C.c_float()
+        self._check(self._L.mcsas_wait(self._ctx, C.byref(ms)), "wait")
+        return ms.value
+
+    def request_stop(self):
+        self._L.mcsas_request_stop(self._ctx)
+
+    def run(self, cfg, stream=None):
+        self.run_async(cfg, stream)
+        return self.wait()
+
+    def fetch(self):
+        cfg = self._last
+        S, R, N, P = self.n_sets, cfg.n_reps, cfg.n_contribs, self.n_active
+        C_ = S * R
+        contribs = np.zeros((S, N, P, R))
+        fit = np.zeros(int(self.nq.sum()) * R)
+        scaling, background, conval, conval0, elapsed = (np.zeros(C_) for _ in range(5))
+        num_iter = np.zeros(C_, dtype=np.int64)
+        num_moves = np.zeros(C_, dtype=np.int64)
+        evals = np.zeros(C_, dtype=np.int64)
+        attempts = np.zeros(C_, dtype=np.int32)
+        self._check(self._L.mcsas_fetch(self._ctx, _dp(contribs), _dp(fit), _dp(scaling), _dp(background),
+                                        _dp(conval), _dp(conval0), _llp(num_iter), _llp(num_moves),
+                                        _ip(attempts), _dp(elapsed), _llp(evals)), "fetch")
+        fits, off = [], 0
+        for s in range(S):
+            n = int(self.nq[s]) * R
+            fits.append(fit[off:off + n].reshape(int(self.nq[s]), R))
+            off += n
+        shp = (S, R)
+        return dict(contribs=contribs, fit_meas=fits, scaling=scaling.reshape(shp),
+                    background=background.reshape(shp), conval=conval.reshape(shp),
+                    conval0=conval0.reshape(shp), num_iter=num_iter.reshape(shp),
+                    num_moves=num_moves.reshape(shp), attempts=attempts.reshape(shp),
+                    elapsed=elapsed.reshape(shp), evals=evals.reshape(shp))
+
+    def fetch_trace(self, chain, capacity):
+        acc = np.zeros(capacity, dtype=np.uint8)
+        chi = np.zeros(capacity)
+        self._check(self._L.mcsas_fetch_trace(self._ctx, int(chain),
+                                              acc.ctypes.data_as(C.POINTER(C.c_ubyte)), _dp(chi),
+                                              C.c_longlong(capacity)), "fetch_trace")
+        return acc, chi
+
+    def fractions(self, cfg, contribs):
+        """McSAS.histogram per-repetition fractions of contribs[S,N,P,R]."""
+        contribs = np.ascontiguousarray(contribs, dtype=np.float64)
+        S, N, P, R = contribs.shape
+        outs = [np.zeros((S, N, R)) for _ in range(8)]
+        totals = np.zeros((S, 4, R))
+        sc = np.zeros((S, 2, R))
+        self._check(self._L.mcsas_fractions(self._ctx, C.byref(cfg), _dp(contribs),
+                                            *[_dp(o) for o in outs], _dp(totals), _dp(sc)), "fractions")
+        keys = ["vol", "num", "volsqr", "surf", "min_vol", "min_num", "min_volsqr", "min_surf"]
+        d = dict(zip(keys, outs))
+        d["totals"] = totals
+        d["sc"] = sc
+        return d
+
+    def measure_peaks(self):
+        a, b = C.c_double(), C.c_double()
+        self._check(self._L.mcsas_measure_peaks(self._ctx, C.byref(a), C.byref(b)), "measure_peaks")
+        return dict(mufu_gops=a.value, ffma_tflops=b.value)
