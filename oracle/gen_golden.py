@@ -274,3 +274,54 @@ if __name__ == "__main__":
     for name, case in CASES.items():
         if not which or name in which or "chains" in which:
             run_chain_case(name, case)
+
+
+def run_histogram_case():
+    """McSAS.calc -> analyse + histogram (mcsas.py:149-179, 445-615) on a small synthetic
+    sphere case: contribs, the per-repetition fractions handed to Histograms.calc, and the
+    resulting Histogram / Moments values (utils/parameter.py:20-122, 420-479)."""
+    rh.install()
+    from mcsas.utils.parameter import Histogram, Histograms
+    case = dict(model="Sphere", active=[("radius", 1 * NM, 100 * NM)], nq=64, N=40, seed=7)
+    model = make_model(case)
+    data = synth_data(case, model)
+    h1 = Histogram(model.radius, 1 * NM, 100 * NM, 20, 'log', 'vol')
+    h2 = Histogram(model.radius, 2 * NM, 60 * NM, 12, 'lin', 'num', autoFollow=False)
+    model.radius.histograms().append(h1)
+    model.radius.histograms().append(h2)
+    algo = rh.make_algo(model, data, numContribs=40, numReps=4, maxIterations=3000,
+                        convergenceCriterion=40.0)
+    captured = {}
+    orig = Histograms.calc
+
+    def calc(self, contribs, paramIndex, fractions):
+        captured["fractions"] = fractions
+        return orig(self, contribs, paramIndex, fractions)
+    Histograms.calc = calc
+    np.random.seed(21)
+    try:
+        algo.calc()
+    finally:
+        Histograms.calc = orig
+    res = algo.result[0]
+    fr = captured["fractions"]
+    out = dict(q=np.asarray(data.q).flatten(), I=np.asarray(data.f.binnedData).flatten(),
+               sigma=np.asarray(data.f.binnedDataU).flatten(), contribs=res["contribs"],
+               comp_exp=float(algo.compensationExponent()))
+    for k in ("vol", "num", "int", "surf"):
+        out["frac_" + k] = fr[k][0]
+        out["minreq_" + k] = fr[k][1]
+    for i, h in enumerate(model.radius.histograms()):
+        out["h%d_edges" % i] = h.xLowerEdge
+        out["h%d_mean" % i] = h.bins.mean
+        out["h%d_std" % i] = h.bins.std
+        out["h%d_cdf" % i] = h.cdf.mean
+        out["h%d_obs" % i] = h.observability
+        out["h%d_moments" % i] = np.array(h.moments.fields)
+        out["h%d_cfg" % i] = np.array([h.lower, h.upper, h.binCount])
+    np.savez_compressed(os.path.join(OUT, "histogram_sphere.npz"), **out)
+    print("histogram case ok; moments", out["h0_moments"][:4])
+
+
+if __name__ == "__main__" and (not sys.argv[1:] or "hist" in sys.argv[1:]):
+    run_histogram_case()

@@ -1,0 +1,132 @@
+"""-m gpu tests of the McSAS-compatible host (mcsas_b200.mcsas.McSAS) -- written like a
+user of the reference would drive it (McSAS.factory()(), .model, .data, .calc(),
+.result[0], param.histograms())."""
+import os
+
+import numpy as np
+import pytest
+
+import common
+
+pytestmark = pytest.mark.gpu
+NM = 1e-9
+
+
+def _cfg1():
+    from mcsas_b200.data import SASData
+    g = common.load_chain("sphere_cfg1")
+    return g, SASData(g["q"], g["I"], g["sigma"])
+
+
+def test_calc_result_dictionary_and_histogram():
+    from mcsas_b200.mcsas import McSAS
+    from mcsas_b200.models import Sphere
+    from mcsas_b200.parameter import Histogram
+    g, data = _cfg1()
+    algo = McSAS.factory()()
+    algo.seed = 99
+    algo.model = Sphere()
+    algo.model.radius.setActiveRange((1 * NM, 100 * NM))
+    algo.model.radius.histograms().append(
+        Histogram(algo.model.radius, 1 * NM, 100 * NM, 50, 'log', 'vol'))
+    algo.data = data
+    algo.numReps.setValue(10)
+    algo.calc()
+    assert len(algo.result) == 1
+    res = algo.result[0]
+    for key in ("contribs", "fitMeasValMean", "fitMeasValStd", "fitX0", "dataX0", "dataMean",
+                "dataStd", "scaling", "background", "times", "numIter"):       # mcsas.py:268-285
+        assert key in res, key
+    assert res["contribs"].shape == (300, 1, 10)
+    assert res["fitMeasValMean"].shape == (1, 100)
+    assert len(res["scaling"]) == 2 and len(res["background"]) == 2
+    assert (res["conval"] <= 1.0).all()
+    # reference, same configuration: 30 282 iterations/rep on average,
+    # scaling 9.95e35 for seed 12345, vol-weighted mean radius 9.7455e-9 +- 3.06e-11 m
+    assert 15000 < res["numIter"] < 60000
+    assert abs(res["scaling"][0] / 9.95e35 - 1) < 0.05
+    h = algo.model.radius.histograms()[0]
+    mean, mean_std = h.moments.mean
+    assert abs(mean - 9.7455e-9) < 4 * 3.06e-11
+    var, var_std = h.moments.variance
+    assert abs(var - 2.019e-18) < 5 * 1.45e-19
+    assert h.bins.mean.shape == (50,) and h.cdf.mean[-1] == pytest.approx(1.0)
+    # fit reproduces the data within its uncertainty on average
+    chi = (((res["fitMeasValMean"][0] - res["dataMean"]) / res["dataStd"]) ** 2).mean()
+    assert chi < 1.5
+    assert len(algo.model.radius.activeValues()) == 10
+
+
+def test_mcfit_api_and_deterministic_stream():
+    from mcsas_b200 import FP64
+    from mcsas_b200.mcsas import McSAS
+    from mcsas_b200.models import Sphere
+    g, data = _cfg1()
+    algo = McSAS(precision=FP64)
+    algo.model = Sphere()
+    algo.model.radius.setActiveRange((1 * NM, 100 * NM))
+    algo.data = data
+    algo.maxIterations.setValue(g["num_iter"])
+    rset, meas, conval, details = algo.mcFit(300, True, True, nRun=0,
+                                             proposalStream=g["stream"])
+    assert details["numIterations"] == g["num_iter"] and details["numMoves"] == g["num_moves"]
+    assert abs(conval / g["conval"] - 1) < 1e-6
+    np.testing.assert_allclose(rset, g["rset"], rtol=1e-12)
+    np.testing.assert_allclose(meas, g["fit_meas"], rtol=1e-6)
+    assert abs(details["scaling"] / g["scaling"] - 1) < 1e-6
+
+
+def test_non_convergence_returns_no_result_unless_show_incomplete():
+    from mcsas_b200.mcsas import McSAS
+    from mcsas_b200.models import Sphere
+    g, data = _cfg1()
+    algo = McSAS(seed=5)
+    algo.model = Sphere()
+    algo.model.radius.setActiveRange((1 * NM, 100 * NM))
+    algo.data = data
+    algo.numReps.setValue(3)
+    algo.maxIterations.setValue(200)          # cannot converge in 200 steps
+    algo.maxRetries.setValue(1)
+    algo.calc()
+    assert algo.result == []                  # mcsas.py:221-230
+    assert (algo.details["attempts"] == 3).all()      # maxRetries + 2 attempts
+    algo.showIncomplete.setValue(True)
+    algo.calc()
+    assert len(algo.result) == 1 and (algo.result[0]["conval"] > 1.0).all()
+
+
+def test_model_calc_on_gpu_matches_reference_vectors():
+    from mcsas_b200.models import MODELS
+    from mcsas_b200.data import SASData
+    g = np.load(os.path.join(common.GOLDEN, "eval_models.npz"))
+    q = g["q"]
+    data = SASData(q, np.ones_like(q), np.ones_like(q))
+    for name in ("Sphere", "EllipsoidsIsotropic", "GaussianChain"):
+        m = MODELS[name]()
+        for p in m.params():
+            if hasattr(p, "setActive"):
+                p.setActive(False)
+        for p, v in zip(m.params(), g[name + "_pvalues"]):
+            p.setValue(type(p())(v), clip=False)
+        for a in g[name + "_active"]:
+            getattr(m, str(a)).setActive(True)
+        md = m.calc(data, g[name + "_pset"], 0.6666666)
+        np.testing.assert_allclose(md.cumInt, g[name + "_it"].sum(0), rtol=1e-9)
+        np.testing.assert_allclose(md.vset, g[name + "_v"], rtol=1e-12)
+        np.testing.assert_allclose(md.wset, g[name + "_w"], rtol=1e-12)
+
+
+def test_stop_flag():
+    from mcsas_b200.mcsas import McSAS
+    from mcsas_b200.models import Sphere
+    g, data = _cfg1()
+    algo = McSAS(seed=1)
+    algo.model = Sphere()                     # default range 1-1000 nm: never converges
+    algo.data = data
+    algo.numReps.setValue(2)
+    algo.showIncomplete.setValue(True)
+    algo.maxIterations.setValue(10 ** 9)
+    algo.maxRetries.setValue(1)
+    algo.stop = True                          # McSAS.stop, mcsas.py:357
+    algo.analyse()
+    assert (algo.details["num_iter"] < 10 ** 7).all()

@@ -1,0 +1,179 @@
+"""CPU tests of the host logic: parameter / histogram mirrors against vectors from the
+reference, the C-ABI library (loads, exports every declared symbol, fails loudly without
+a GPU), partitioning and the gloo world_size=2 gather."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import common
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NM = 1e-9
+
+
+def test_cabi_exports_every_declared_symbol():
+    from mcsas_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "mcsas_b200.h")).read()
+    declared = set(re.findall(r"\b(mcsas_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_model_ids_match_oracle_and_header():
+    import oracle as orc
+    from mcsas_b200.models import MODELS
+    hdr = open(os.path.join(ROOT, "include", "mcsas_b200.h")).read()
+    ids = dict((m.group(1), int(m.group(2))) for m in re.finditer(r"MCSAS_([A-Z_]+) = (\d+),", hdr))
+    for name, cls in MODELS.items():
+        oid, plist, active = orc.MODEL_SPECS[name]
+        assert cls.modelId == oid
+        m = cls()
+        assert [p.name() for p in m.params()] == [p[0] for p in plist]
+        np.testing.assert_allclose([float(p()) for p in m.params()], [float(p[1]) for p in plist],
+                                   rtol=1e-14)
+        assert [p.name() for p in m.activeParams()] == active
+        for p, spec in zip(m.params(), plist):
+            if hasattr(p, "generator"):
+                assert p.generator().kind == spec[2], (name, p.name())
+            if spec[3] is not None:
+                np.testing.assert_allclose(p.activeRange(), spec[3], rtol=1e-14)
+    assert ids["SPHERE"] == 0 and ids["KHOLODENKO"] == 7
+
+
+@pytest.mark.skipif(__import__("torch").cuda.is_available(), reason="CPU-only check")
+def test_no_cpu_fallback():
+    from mcsas_b200 import Engine, McSASB200Error
+    from mcsas_b200.mcsas import McSAS
+    from mcsas_b200.models import Sphere
+    from mcsas_b200.data import SASData
+    with pytest.raises(McSASB200Error, match="no CPU fallback"):
+        Engine(0)
+    algo = McSAS()
+    algo.model = Sphere()
+    algo.data = SASData(np.linspace(1e8, 1e9, 10), np.ones(10), np.ones(10) * 0.01)
+    with pytest.raises(McSASB200Error):
+        algo.calc()
+
+
+def test_user_defined_model_rejected():
+    from mcsas_b200.models import ScatteringModel
+
+    class Mine(ScatteringModel):
+        pass
+    with pytest.raises(NotImplementedError):
+        Mine()
+
+
+def test_parameter_surface():
+    from mcsas_b200.models import Sphere, CylindersIsotropic
+    from mcsas_b200.parameter import ValueRangeError, isActiveFitParam
+    m = Sphere()
+    assert m.radius() == pytest.approx(10e-9) and m.radius.isActive()
+    assert m.radius.activeRange() == pytest.approx((1e-9, 1e-6))
+    m.radius.setActiveRange((100e-9, 1e-9))                 # order-insensitive (:633)
+    assert m.radius.activeRange() == pytest.approx((1e-9, 100e-9))
+    m.radius.setActiveRange((-5., 3e-9))                    # clipped to valueRange (:631)
+    assert m.radius.activeRange() == pytest.approx((0., 3e-9))
+    with pytest.raises(ValueRangeError):
+        m.radius.setActiveRange((1, 2, 3))
+    m.radius.setValue(-1.)                                  # setValue clips (parameter.py:405)
+    assert m.radius() == 0.
+    m.radius.setActiveVal(np.arange(3.), index=2)           # list grows (utils/parameter.py:685)
+    assert len(m.radius.activeValues()) == 3 and m.radius.activeValues()[0] is None
+    assert not isActiveFitParam(m.sld)
+    c = CylindersIsotropic()
+    c.aspect.setActive(True)
+    assert c.activeParamNames() == ["radius", "aspect"]
+    with pytest.raises(ValueError, match="finite"):
+        c.kernelDescription()                               # radius has no activeRange preset
+    c.radius.setActiveRange((1e-9, 50e-9)); c.aspect.setActiveRange((1., 20.))
+    d = c.kernelDescription()
+    assert d["active_idx"] == [0, 3] and d["gen_kind"] == [1, 1] and d["quad_nodes"] == 100
+    np.random.seed(3)
+    g = c.generateParameters(5)
+    assert g.shape == (5, 2) and (g[:, 0] >= 1e-9).all() and (g[:, 0] < 50e-9).all()
+
+
+def test_histogram_and_moments_match_reference():
+    from mcsas_b200.models import Sphere
+    from mcsas_b200.parameter import Histogram
+    g = np.load(os.path.join(common.GOLDEN, "histogram_sphere.npz"))
+    m = Sphere()
+    m.radius.setActiveRange((1 * NM, 100 * NM))
+    fractions = dict((k, (g["frac_" + k], g["minreq_" + k])) for k in ("vol", "num", "int", "surf"))
+    hs = [Histogram(m.radius, 1 * NM, 100 * NM, 20, 'log', 'vol'),
+          Histogram(m.radius, 2 * NM, 60 * NM, 12, 'lin', 'num', autoFollow=False)]
+    for i, h in enumerate(hs):
+        m.radius.histograms().append(h)
+    m.radius.histograms().calc(g["contribs"], 0, fractions)
+    for i, h in enumerate(hs):
+        np.testing.assert_allclose(h.xLowerEdge, g["h%d_edges" % i], rtol=1e-13)
+        np.testing.assert_allclose(h.bins.mean, g["h%d_mean" % i], rtol=1e-11, atol=1e-300)
+        np.testing.assert_allclose(h.bins.std, g["h%d_std" % i], rtol=1e-9, atol=1e-300)
+        np.testing.assert_allclose(h.cdf.mean, g["h%d_cdf" % i], rtol=1e-11)
+        np.testing.assert_allclose(h.observability, g["h%d_obs" % i], rtol=1e-11)
+        np.testing.assert_allclose(h.moments.fields, g["h%d_moments" % i], rtol=1e-10)
+
+
+def test_oracle_fractions_match_reference():
+    import oracle as orc
+    g = np.load(os.path.join(common.GOLDEN, "histogram_sphere.npz"))
+    om = orc.Model("Sphere", ranges={"radius": (1 * NM, 100 * NM)})
+    st = orc.settings(n_contribs=g["contribs"].shape[0], comp_exp=float(g["comp_exp"]))
+    for r in range(g["contribs"].shape[2]):
+        f = orc.fractions(om, st, g["q"], g["I"], g["sigma"], g["contribs"][:, :, r])
+        for mine, ref in (("vol", "vol"), ("num", "num"), ("volsqr", "int"), ("surf", "surf")):
+            np.testing.assert_allclose(f[mine], g["frac_" + ref][:, r], rtol=2e-5)
+            np.testing.assert_allclose(f["min_" + mine], g["minreq_" + ref][:, r], rtol=2e-5)
+
+
+def test_partition():
+    from mcsas_b200.dist import partition
+    for n, w in ((100, 8), (7, 2), (3, 4), (4096 * 100, 8)):
+        parts = [partition(n, w, r) for r in range(w)]
+        assert parts[0][0] == 0 and sum(c for _, c in parts) == n
+        for (f0, c0), (f1, c1) in zip(parts, parts[1:]):
+            assert f1 == f0 + c0 and abs(c0 - c1) <= 1
+
+
+_GLOO_WORKER = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, %r)
+import torch.distributed as dist
+from mcsas_b200 import dist as mdist
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+N, P, R = 6, 2, 3
+first, cnt = mdist.partition(world * R, world, rank)
+rng = np.random.default_rng(rank)
+res = dict(contribs=rng.random((N, P, R)) + rank, scalingAll=np.full(R, 1.0 + rank),
+           backgroundAll=np.full(R, -1.0 * rank), conval=np.full(R, 0.5),
+           numIterAll=np.arange(R) + 10 * rank, numMoves=np.arange(R))
+g = mdist.gather_results(res)
+assert g["contribs"].shape == (N, P, world * R), g["contribs"].shape
+for r in range(world):
+    exp = np.random.default_rng(r).random((N, P, R)) + r
+    assert np.array_equal(g["contribs"][:, :, r * R:(r + 1) * R], exp)
+    assert (g["scalingAll"][r * R:(r + 1) * R] == 1.0 + r).all()
+    assert (g["numIterAll"][r * R:(r + 1) * R] == np.arange(R) + 10 * r).all()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_gloo_world2_gather(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER % ROOT)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                          "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port",
+                          "29731", str(script)], capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2
