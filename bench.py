@@ -204,7 +204,7 @@ def main():
     wall0 = time.perf_counter()
     for i in range(args.steps):
         res, kms, el = one_step(args.warmup + i, True)
-        mc_steps += int(res["numIterAll"].sum())
+        mc_steps += int(res["stepsAll"].sum())      # every executed MC step, retries included
         evals += int(res["evals"].sum())
         nconv += int((res["conval"] <= 1.0).sum())
         kern_ms += kms

@@ -89,6 +89,9 @@ typedef struct mcsas_run_config {
     int spec_max;              /* max speculative proposals per batch, 0 = default (32), 1 = none */
     int record_trace;          /* 1: keep per-step accept flag + chi-squared (parity tests) */
     int first_chain;           /* global index of this context's first chain (multi-GPU partition) */
+    int cluster_size;          /* CTAs per chain (q split over a thread-block cluster): 0 = auto, 1/2/4/8 */
+    long long slice_steps;     /* MC steps per chain and launch before the live chains are re-packed:
+                                  0 = auto, -1 = one launch */
 } mcsas_run_config;
 
 /* -- context ------------------------------------------------------------- */
@@ -119,7 +122,8 @@ int mcsas_eval(mcsas_ctx *ctx, int set, const double *pset, int m, double comp_e
  *    (mcsas.py:287-439), one CTA each.  proposal_stream: NULL (in-kernel Philox) or
  *    [n_chains][stream_stride] number-generator outputs in [0,1) in the reference's
  *    consumption order (deterministic parity mode, single attempt per chain).
- *    stop_flag: NULL or a host int the caller may set non-zero to stop (McSAS.stop). */
+ *    stop_flag: NULL or a host int the caller may set non-zero to stop (McSAS.stop);
+ *    it is polled between time slices. */
 int mcsas_run(mcsas_ctx *ctx, const mcsas_run_config *cfg,
               const double *proposal_stream, long long stream_stride,
               volatile int *stop_flag);
@@ -128,16 +132,20 @@ int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
                     const double *proposal_stream, long long stream_stride,
                     volatile int *stop_flag);
 int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms);
-/* Ask a running launch to stop at its next batch boundary (McSAS.stop). */
+/* Ask a running fit to stop at its next time-slice boundary (McSAS.stop). */
 int mcsas_request_stop(mcsas_ctx *ctx);
+/* Facts about the last run: kernel launches (time slices), last cluster size, summed kernel ms. */
+int mcsas_run_info(mcsas_ctx *ctx, int *n_launches, int *last_cluster, float *kernel_ms);
 
 /* -- results of the last run (any pointer may be NULL).  Layouts:
  *    contribs [set][N][P][R] (numpy zeros((N,P,R)) per set, mcsas.py:203-205),
- *    fit_meas [set][nq][R] (mcsas.py:210), everything else [set][R]. */
+ *    fit_meas [set][nq][R] (mcsas.py:210), everything else [set][R].  num_iter/num_moves are
+ *    those of the final attempt (mcsas.py:249); steps_all counts the MC steps of all attempts,
+ *    evals all contribution evaluations incl. discarded speculative ones. */
 int mcsas_fetch(mcsas_ctx *ctx, double *contribs, double *fit_meas,
                 double *scaling, double *background, double *conval, double *conval0,
                 long long *num_iter, long long *num_moves, int *attempts, double *elapsed_s,
-                long long *evals);
+                long long *evals, long long *steps_all);
 /* Per-step trace of chain `chain` (record_trace=1): accept[num_iter], chi[num_iter]. */
 int mcsas_fetch_trace(mcsas_ctx *ctx, int chain, unsigned char *accept, double *chi,
                       long long capacity);

@@ -44,11 +44,9 @@ __global__ void __launch_bounds__(FR_THREADS) fractions_kernel(const __grid_cons
     if (tid == 0) {
         double G = 1.;
         if (sizeof(Real) == 4) {
-            double p[MCSAS_MAX_PARAMS], pv[MCSAS_MAX_ACTIVE];
-            for (int k = 0; k < P; ++k) pv[k] = a.mp.hi[k];
-            patch_params(a.mp, pv, p);
+            PVec p(a.mp, a.mp.hi);
             Contrib<Real> tmp;
-            VWS o = O::prep(p, a.comp_exp, 1., qt, tmp, s_nodes);
+            VWS o = O::template prep<false>(p, a.comp_exp, 1., qt, tmp, s_nodes);
             G = 1. / o.amp_raw;
             if (!(G > 0.) || isinf(G)) G = 1.;
         }
@@ -67,9 +65,8 @@ __global__ void __launch_bounds__(FR_THREADS) fractions_kernel(const __grid_cons
     // pass 1: per contribution intensity, v/w/s, observability ratio
     for (int c = 0; c < N; ++c) {
         if (tid == 0) {
-            double p[MCSAS_MAX_PARAMS];
-            patch_params(a.mp, a.rset + ((size_t)chain * N + c) * P, p);
-            VWS o = O::prep(p, a.comp_exp, G, qt, s_cc, s_nodes);
+            PVec p(a.mp, a.rset + ((size_t)chain * N + c) * P);
+            VWS o = O::template prep<false>(p, a.comp_exp, G, qt, s_cc, s_nodes);
             s_vws[0] = o.v; s_vws[1] = o.w; s_vws[2] = o.s;
         }
         __syncthreads();

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <map>
 #include <chrono>
 #include <thread>
 
@@ -21,6 +22,9 @@ cudaError_t mcsas_launch_peaks(int which, int grid, int threads, int iters, floa
 static const chain_launch_fn CHAIN_FN[MCSAS_N_MODELS] = {
     mcsas_launch_chain_0, mcsas_launch_chain_1, mcsas_launch_chain_2, mcsas_launch_chain_3,
     mcsas_launch_chain_4, mcsas_launch_chain_5, mcsas_launch_chain_6, mcsas_launch_chain_7};
+static const chain_query_fn QUERY_FN[MCSAS_N_MODELS] = {
+    mcsas_query_chain_0, mcsas_query_chain_1, mcsas_query_chain_2, mcsas_query_chain_3,
+    mcsas_query_chain_4, mcsas_query_chain_5, mcsas_query_chain_6, mcsas_query_chain_7};
 static const eval_launch_fn EVAL_FN[MCSAS_N_MODELS] = {
     mcsas_launch_eval_0, mcsas_launch_eval_1, mcsas_launch_eval_2, mcsas_launch_eval_3,
     mcsas_launch_eval_4, mcsas_launch_eval_5, mcsas_launch_eval_6, mcsas_launch_eval_7};
@@ -55,6 +59,17 @@ struct mcsas_ctx {
     size_t out_cap = 0, trace_cap = 0;
     int *h_stop = nullptr;        // mapped pinned host int
     int *d_stop = nullptr;
+    // time-sliced launch state
+    ChainArgs args;
+    int precision = 0;
+    size_t smem = 0;
+    int forced_cluster = 0;
+    std::vector<int> h_ids;
+    int *d_ids = nullptr;
+    int n_live = 0, n_launches = 0, last_cluster = 1, last_threads = 0, last_qpt = 0, last_resident = 0;
+    float kernel_ms = 0.f;
+    volatile int *stop_flag = nullptr;
+    std::map<long long, int> occ_cache;
 };
 
 static int fail(mcsas_ctx *ctx, int code, const char *fmt, ...)
@@ -113,7 +128,7 @@ extern "C" void mcsas_ctx_destroy(mcsas_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_sets); cudaFree(ctx->d_data); cudaFree(ctx->d_quad); cudaFree(ctx->d_stream);
     cudaFree(ctx->d_rset); cudaFree(ctx->d_fit); cudaFree(ctx->d_scal); cudaFree(ctx->d_cnt);
-    cudaFree(ctx->d_att); cudaFree(ctx->d_tacc); cudaFree(ctx->d_tchi);
+    cudaFree(ctx->d_att); cudaFree(ctx->d_tacc); cudaFree(ctx->d_tchi); cudaFree(ctx->d_ids);
     cudaFreeHost(ctx->h_stop);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -312,38 +327,6 @@ extern "C" int mcsas_eval(mcsas_ctx *ctx, int set, const double *pset, int m, do
     return MCSAS_OK;
 }
 
-// Shared-memory footprint of chain_kernel (mirrors its carve-up).
-static size_t chain_smem(int nq_pad, int N, int P, int D, int narr, size_t real, int kcap)
-{
-    auto al = [](size_t b) { return (b + 15) & ~size_t(15); };
-    size_t s = 16;
-    s += al(8 * 3 * (size_t)nq_pad);
-    s += al(8 * (size_t)N * (P > 0 ? P : 1));
-    s += al(8 * MCSAS_MAX_SPEC * MCSAS_MAX_ACTIVE);
-    s += al(8 * 16 * MCSAS_MAX_SPEC * 3);
-    s += al(8 * MCSAS_MAX_SPEC * 3);
-    s += al(8 * 8);
-    s += al(real * 8 * MCSAS_MAX_SPEC * 2);
-    s += 2 * al(real * (D + 1));
-    s += real * (size_t)kcap * 2 * narr * D + 16;
-    return s;
-}
-
-static int pick_layout(int nq)
-{
-    const char *env = getenv("MCSAS_B200_LAYOUT");
-    if (env) {
-        int l = atoi(env);
-        if (l >= 0 && l < N_CHAIN_LAYOUTS && CHAIN_LAYOUTS[l].qpt * CHAIN_LAYOUTS[l].max_threads >= nq) return l;
-    }
-    if (nq <= 128) return 0;
-    if (nq <= 256) return 1;
-    if (nq <= 512) return 2;
-    if (nq <= 1024) return 3;
-    if (nq <= 2048) return 5;
-    return 6;
-}
-
 template <class T> static cudaError_t regrow(T **p, size_t n)
 {
     cudaFree(*p);
@@ -351,11 +334,97 @@ template <class T> static cudaError_t regrow(T **p, size_t n)
     return cudaMalloc((void **)p, sizeof(T) * (n ? n : 1));
 }
 
+// Thread layout of one chain: cluster size C (q split), q points per eval thread, eval
+// threads per CTA.  More CTAs per chain when few chains are alive, so that freed SMs
+// shorten the tail of the slow chains.
+struct ChainPlan { int cluster, layout, threads, resident; };
+
+// Candidate layouts: cluster size C in {1,2,4,8} x eval threads T in {64,128,256}; QPT is the
+// smallest instantiated value that covers nq.  Only layouts whose clusters are ALL
+// co-resident (cudaOccupancyMaxActiveClusters) are considered, so a slice is one wave;
+// among those the one that spreads the live chains over the most SMs wins, ties go to the
+// smaller cluster (less exchange per batch).
+static int plan_chain(mcsas_ctx *ctx, int nq, int n_live, ChainPlan *out)
+{
+    const int sms = ctx->prop.multiProcessorCount;
+    int forced_c = ctx->forced_cluster, forced_t = 0, forced_q = 0;
+    const char *env;
+    if ((env = getenv("MCSAS_B200_CLUSTER")) && atoi(env) > 0) forced_c = atoi(env);
+    if ((env = getenv("MCSAS_B200_T")) && atoi(env) > 0) forced_t = atoi(env);
+    if ((env = getenv("MCSAS_B200_QPT")) && atoi(env) > 0) forced_q = atoi(env);
+    ChainPlan best = {0, 0, 0, 0};
+    double best_score = -1.;
+    for (int c = 1; c <= MAX_CLUSTER; c *= 2) {
+        if (forced_c > 0 && c != forced_c && !(forced_c > MAX_CLUSTER && c == MAX_CLUSTER)) continue;
+        const int n = (nq + c - 1) / c;                  // q points per CTA
+        for (int tcap = 64; tcap <= CHAIN_MAX_EVAL_THREADS; tcap *= 2) {
+            if (forced_t > 0 && tcap != forced_t) continue;
+            int layout = -1;
+            for (int l = 0; l < N_CHAIN_LAYOUTS; ++l)
+                if (n <= tcap * CHAIN_QPT[l] && (forced_q <= 0 || CHAIN_QPT[l] >= forced_q)) { layout = l; break; }
+            if (layout < 0) continue;
+            const int qpt = CHAIN_QPT[layout];
+            int threads = (((n + qpt - 1) / qpt) + 31) & ~31;
+            if (threads < 32) threads = 32;
+            if (forced_t <= 0 && tcap > 64 && threads * 2 <= tcap) continue;        // same as a smaller tcap
+            int resident = 0, regs = 0;
+            const long long key = ((((long long)ctx->mp.model_id * 2 + ctx->precision) * 16 + c) * 8 + layout) * 1024
+                                  + threads + ((long long)ctx->smem << 24);
+            auto it = ctx->occ_cache.find(key);
+            if (it != ctx->occ_cache.end()) resident = it->second;
+            else {
+                cudaError_t e = QUERY_FN[ctx->mp.model_id](ctx->precision, layout, threads + 32, ctx->smem, c,
+                                                           &resident, &regs);
+                if (e != cudaSuccess) { cudaGetLastError(); resident = 0; }
+                ctx->occ_cache[key] = resident;
+            }
+            if (resident < 1) continue;
+            const bool one_wave = n_live <= resident;
+            // SMs kept busy by the live chains (a CTA occupies at most one SM), in eval warps
+            const double ctas = (double)n_live * c;
+            const double per_sm = ctas / sms;
+            double busy = per_sm >= 1. ? 1. : per_sm;                 // fraction of SMs with work
+            double warps = (per_sm > 1. ? per_sm : 1.) * (threads / 32);   // eval warps per busy SM
+            double score = busy * (warps >= 8. ? 1. : 0.55 + 0.45 * warps / 8.);
+            score *= 1. - 0.03 * (c > 1 ? (1 + (c > 2) + (c > 4)) : 0);   // exchange cost per batch
+            if (!one_wave) score *= 0.4 * resident / (double)n_live;
+            if (score > best_score) { best_score = score; best.cluster = c; best.layout = layout; best.threads = threads; best.resident = resident; }
+        }
+    }
+    if (best.cluster == 0) return fail(ctx, MCSAS_ERR_ARG, "no launchable chain layout for nq=%d", nq);
+    *out = best;
+    return MCSAS_OK;
+}
+
+// Launch one time slice for the chains listed in ctx->h_ids[0..n_live).
+static int launch_slice(mcsas_ctx *ctx, int n_live, bool resume)
+{
+    ChainArgs a = ctx->args;
+    ChainPlan pl;
+    int prc = plan_chain(ctx, ctx->nq_max, n_live, &pl);
+    if (prc) return prc;
+    a.cluster = pl.cluster;
+    ctx->last_threads = pl.threads; ctx->last_qpt = CHAIN_QPT[pl.layout]; ctx->last_resident = pl.resident;
+    a.resume = resume ? 1 : 0;
+    a.chain_ids = nullptr;
+    if (n_live != ctx->n_chains || resume) {
+        CK(cudaMemcpyAsync(ctx->d_ids, ctx->h_ids.data(), sizeof(int) * n_live, cudaMemcpyHostToDevice, ctx->stream));
+        a.chain_ids = ctx->d_ids;
+    }
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    cudaError_t e = CHAIN_FN[a.mp.model_id](ctx->precision, pl.layout, n_live * pl.cluster, pl.threads + 32,
+                                            ctx->smem, ctx->stream, a);
+    if (e != cudaSuccess) return fail(ctx, MCSAS_ERR_CUDA, "chain kernel launch: %s", cudaGetErrorString(e));
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->n_launches++;
+    ctx->last_cluster = pl.cluster;
+    return MCSAS_OK;
+}
+
 extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
                                const double *proposal_stream, long long stream_stride,
                                volatile int *stop_flag)
 {
-    (void)stop_flag;
     if (!ctx || !cfg) return MCSAS_ERR_ARG;
     if (!ctx->n_sets || !ctx->have_model) return fail(ctx, MCSAS_ERR_STATE, "run: upload datasets and set a model first");
     if (ctx->running) return fail(ctx, MCSAS_ERR_STATE, "run: previous run not waited for");
@@ -369,14 +438,16 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     const int n_chains = ctx->n_sets * cfg->n_reps;
     const int narr = MODEL_NARR[mp.model_id];
     const size_t real = cfg->precision == MCSAS_FP64 ? 8 : 4;
-    const int layout = pick_layout(ctx->nq_max);
     int nq_pad_max = (ctx->nq_max + 1) & ~1;
-    int kcap = cfg->spec_max <= 0 ? MCSAS_MAX_SPEC : (cfg->spec_max > MCSAS_MAX_SPEC ? MCSAS_MAX_SPEC : cfg->spec_max);
     const size_t smem_limit = (size_t)ctx->prop.sharedMemPerBlockOptin;
-    while (kcap > 1 && chain_smem(nq_pad_max, N, P, D, narr, real, kcap) > smem_limit) kcap /= 2;
-    size_t smem = chain_smem(nq_pad_max, N, P, D, narr, real, kcap);
+    int ring = N < RING_MAX ? N : RING_MAX;
+    while (ring > 4 && chain_smem_bytes(nq_pad_max, N, P, D, narr, real, ring) > smem_limit) ring /= 2;
+    size_t smem = chain_smem_bytes(nq_pad_max, N, P, D, narr, real, ring);
     if (smem > smem_limit)
         return fail(ctx, MCSAS_ERR_ARG, "run: configuration needs %zu B shared memory (> %zu)", smem, smem_limit);
+    int kcap = cfg->spec_max <= 0 ? MCSAS_MAX_SPEC : (cfg->spec_max > MCSAS_MAX_SPEC ? MCSAS_MAX_SPEC : cfg->spec_max);
+    if (kcap > ring / 4) kcap = ring / 4;
+    if (kcap < 1) kcap = 1;
 
     // proposal stream (deterministic parity mode)
     const double *d_stream = nullptr;
@@ -398,8 +469,9 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
         CK(regrow(&ctx->d_rset, (size_t)n_chains * N * P));
         CK(regrow(&ctx->d_fit, (size_t)n_chains * ctx->nq_max));
         CK(regrow(&ctx->d_scal, (size_t)n_chains * 5));
-        CK(regrow(&ctx->d_cnt, (size_t)n_chains * 3));
-        CK(regrow(&ctx->d_att, (size_t)n_chains));
+        CK(regrow(&ctx->d_cnt, (size_t)n_chains * 4));
+        CK(regrow(&ctx->d_att, (size_t)n_chains * 2));
+        CK(regrow(&ctx->d_ids, (size_t)n_chains));
         ctx->out_cap = need_out;
     }
     ctx->have_trace = false;
@@ -420,31 +492,41 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     a.max_iter = cfg->max_iter; a.conv_crit = cfg->conv_crit; a.comp_exp = cfg->comp_exp;
     a.find_bg = cfg->find_background != 0; a.pos_bg = cfg->positive_background != 0;
     a.start_min = cfg->start_from_minimum != 0;
-    a.spec_max = kcap; a.first_chain = cfg->first_chain; a.record_trace = cfg->record_trace;
+    a.spec_max = kcap; a.ring = ring;
+    a.first_chain = cfg->first_chain; a.record_trace = cfg->record_trace;
     a.seed = cfg->seed;
+    // time slicing: deterministic (uploaded stream / traced) runs are one launch
+    long long slice = cfg->slice_steps;
+    if (slice == 0) slice = (proposal_stream || cfg->record_trace) ? -1 : 8192;
+    const char *env = getenv("MCSAS_B200_SLICE");
+    if (env && !(proposal_stream || cfg->record_trace)) slice = atoll(env);
+    a.slice_steps = slice > 0 ? slice : 0;
     a.sets = ctx->d_sets; a.data = ctx->d_data;
     a.quad_x = ctx->d_quad; a.quad_w = ctx->d_quad + D;
     a.stream = d_stream; a.stream_stride = stream_stride;
-    *ctx->h_stop = 0;
-    a.stop_flag = ctx->d_stop;
     a.rset = ctx->d_rset; a.fit_meas = ctx->d_fit; a.nq_stride = ctx->nq_max;
     a.scaling = ctx->d_scal; a.background = ctx->d_scal + n_chains; a.conval = ctx->d_scal + 2 * n_chains;
     a.conval0 = ctx->d_scal + 3 * n_chains; a.elapsed_s = ctx->d_scal + 4 * n_chains;
     a.num_iter = ctx->d_cnt; a.num_moves = ctx->d_cnt + n_chains; a.evals = ctx->d_cnt + 2 * n_chains;
-    a.attempts = ctx->d_att;
+    a.steps_all = ctx->d_cnt + 3 * (size_t)n_chains;
+    a.attempts = ctx->d_att; a.status = ctx->d_att + n_chains;
     a.trace_accept = cfg->record_trace ? ctx->d_tacc : nullptr;
     a.trace_chi = cfg->record_trace ? ctx->d_tchi : nullptr;
-
-    const ChainLayout lay = CHAIN_LAYOUTS[layout];
-    int threads = ((ctx->nq_max + lay.qpt - 1) / lay.qpt + 31) & ~31;
-    if (threads < 32) threads = 32;
-    if (threads > lay.max_threads) threads = lay.max_threads;
-    CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    cudaError_t e = CHAIN_FN[mp.model_id](cfg->precision, layout, n_chains, threads, smem, ctx->stream, a);
-    if (e != cudaSuccess) return fail(ctx, MCSAS_ERR_CUDA, "chain kernel launch: %s", cudaGetErrorString(e));
-    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->args = a;
+    ctx->precision = cfg->precision;
+    ctx->smem = smem;
+    ctx->forced_cluster = cfg->cluster_size;
     ctx->n_chains = n_chains; ctx->n_contribs = N; ctx->n_reps = cfg->n_reps; ctx->n_active = P;
     ctx->max_iter = cfg->max_iter;
+    ctx->h_ids.resize(n_chains);
+    for (int i = 0; i < n_chains; ++i) ctx->h_ids[i] = i;
+    ctx->n_live = n_chains;
+    ctx->n_launches = 0;
+    ctx->kernel_ms = 0.f;
+    ctx->stop_flag = stop_flag;
+    *ctx->h_stop = 0;
+    int rc = launch_slice(ctx, n_chains, false);
+    if (rc) return rc;
     ctx->running = true;
     ctx->have_run = false;
     return MCSAS_OK;
@@ -457,13 +539,41 @@ extern "C" int mcsas_request_stop(mcsas_ctx *ctx)
     return MCSAS_OK;
 }
 
+// Drives the remaining time slices: after each launch the chains that are still running
+// are compacted and relaunched (with a larger cluster when fewer are alive).  McSAS.stop
+// (mcsas.py:357) is honoured at slice boundaries.
 extern "C" int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms)
 {
     if (!ctx) return MCSAS_ERR_ARG;
     if (!ctx->running) return fail(ctx, MCSAS_ERR_STATE, "wait: nothing running");
     ctx->running = false;
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (kernel_ms) CK(cudaEventElapsedTime(kernel_ms, ctx->ev0, ctx->ev1));
+    std::vector<int> status(ctx->n_chains);
+    for (;;) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->kernel_ms += ms;
+        if (getenv("MCSAS_B200_DEBUG"))
+            fprintf(stderr, "[mcsas_b200] slice %d: live %d cluster %d T %d qpt %d resident %d  %.3f ms\n",
+                    ctx->n_launches, ctx->n_live, ctx->last_cluster, ctx->last_threads, ctx->last_qpt,
+                    ctx->last_resident, ms);
+        if (ctx->args.slice_steps <= 0) break;
+        CK(cudaMemcpy(status.data(), ctx->args.status, sizeof(int) * ctx->n_chains, cudaMemcpyDeviceToHost));
+        int n = 0;
+        for (int i = 0; i < ctx->n_live; ++i) {
+            int c = ctx->h_ids[i];
+            if (status[c] < 0)
+                return fail(ctx, MCSAS_ERR_CUDA, "chain %d: kernel watchdog fired (status %d)", c, status[c]);
+            if (status[c] != 1) ctx->h_ids[n++] = c;       // 0: continue, 2: retry afresh
+        }
+        if (ctx->n_launches > 100000) return fail(ctx, MCSAS_ERR_CUDA, "time-slice loop did not terminate");
+        ctx->n_live = n;
+        bool stop = *(volatile int *)ctx->h_stop != 0 || (ctx->stop_flag && *ctx->stop_flag);
+        if (n == 0 || stop) break;
+        int rc = launch_slice(ctx, n, true);
+        if (rc) return rc;
+    }
+    if (kernel_ms) *kernel_ms = ctx->kernel_ms;
     ctx->have_run = true;
     return MCSAS_OK;
 }
@@ -473,19 +583,22 @@ extern "C" int mcsas_run(mcsas_ctx *ctx, const mcsas_run_config *cfg, const doub
 {
     int rc = mcsas_run_async(ctx, cfg, proposal_stream, stream_stride, stop_flag);
     if (rc) return rc;
-    if (stop_flag) {
-        // McSAS.stop (mcsas.py:357): the caller's flag is forwarded to the kernel's mapped flag
-        while (cudaStreamQuery(ctx->stream) == cudaErrorNotReady) {
-            if (*stop_flag) *(volatile int *)ctx->h_stop = 1;
-            std::this_thread::sleep_for(std::chrono::microseconds(200));
-        }
-    }
     return mcsas_wait(ctx, nullptr);
+}
+
+extern "C" int mcsas_run_info(mcsas_ctx *ctx, int *n_launches, int *last_cluster, float *kernel_ms)
+{
+    if (!ctx) return MCSAS_ERR_ARG;
+    if (n_launches) *n_launches = ctx->n_launches;
+    if (last_cluster) *last_cluster = ctx->last_cluster;
+    if (kernel_ms) *kernel_ms = ctx->kernel_ms;
+    return MCSAS_OK;
 }
 
 extern "C" int mcsas_fetch(mcsas_ctx *ctx, double *contribs, double *fit_meas, double *scaling,
                            double *background, double *conval, double *conval0, long long *num_iter,
-                           long long *num_moves, int *attempts, double *elapsed_s, long long *evals)
+                           long long *num_moves, int *attempts, double *elapsed_s, long long *evals,
+                           long long *steps_all)
 {
     if (!ctx) return MCSAS_ERR_ARG;
     if (!ctx->have_run) return fail(ctx, MCSAS_ERR_STATE, "fetch: no finished run");
@@ -523,6 +636,7 @@ extern "C" int mcsas_fetch(mcsas_ctx *ctx, double *contribs, double *fit_meas, d
     if (num_iter) CK(cudaMemcpy(num_iter, ctx->d_cnt, sizeof(long long) * C, cudaMemcpyDeviceToHost));
     if (num_moves) CK(cudaMemcpy(num_moves, ctx->d_cnt + C, sizeof(long long) * C, cudaMemcpyDeviceToHost));
     if (evals) CK(cudaMemcpy(evals, ctx->d_cnt + 2 * (size_t)C, sizeof(long long) * C, cudaMemcpyDeviceToHost));
+    if (steps_all) CK(cudaMemcpy(steps_all, ctx->d_cnt + 3 * (size_t)C, sizeof(long long) * C, cudaMemcpyDeviceToHost));
     if (attempts) CK(cudaMemcpy(attempts, ctx->d_att, sizeof(int) * C, cudaMemcpyDeviceToHost));
     return MCSAS_OK;
 }

@@ -5,6 +5,10 @@
 #include "../../include/mcsas_b200.h"
 
 #define MCSAS_MAX_NODES 512      // orientation-average nodes kept in shared memory
+#define KCAP MCSAS_MAX_SPEC       // speculative proposals per batch
+#define RING_MAX 128              // ring entries (>= 4 * KCAP)
+#define MAX_CLUSTER 8             // CTAs per chain
+#define MAX_EVAL_WARPS 8          // eval warps per CTA (+ one producer warp)
 
 // Model instance state (replaces the ScatteringModel object, scatteringmodel.py).
 struct ModelParams {
@@ -39,7 +43,13 @@ struct ChainArgs {
     double conv_crit;
     double comp_exp;
     int find_bg, pos_bg, start_min;
-    int spec_max;
+    int spec_max;                // max speculative proposals per batch (<= ring / 4)
+    int ring;                    // ring entries = min(RING_MAX, n_contribs)
+    int cluster;                 // CTAs per chain (q split)
+    int resume;                  // 1: continue from the saved state (rset, counters)
+    long long slice_steps;       // MC steps per chain in this launch, 0 = run to the end
+    const int *chain_ids;        // chains of this launch (grid = n * cluster) or NULL
+    int *status;                 // per chain: 1 finished, 0 needs another slice
     int first_chain;
     int record_trace;
     unsigned long long seed;
@@ -50,13 +60,12 @@ struct ChainArgs {
     const double *quad_w;        // [quad_nodes] weights
     const double *stream;        // NULL or [n_chains][stream_stride]
     long long stream_stride;
-    volatile int *stop_flag;     // mapped host int or NULL
     // outputs, one slot per chain
     double *rset;                // [chain][N][P]
     double *fit_meas;            // [chain][nq_max]
     int nq_stride;
     double *scaling, *background, *conval, *conval0, *elapsed_s;
-    long long *num_iter, *num_moves, *evals;
+    long long *num_iter, *num_moves, *evals, *steps_all;
     int *attempts;
     unsigned char *trace_accept; // [chain][max_iter] or NULL
     double *trace_chi;           // [chain][max_iter] or NULL
@@ -88,3 +97,24 @@ struct FractionArgs {
     double *totals;              // [chain][4]
     double *sc;                  // [chain][2]
 };
+
+// Shared-memory footprint of chain_kernel (mirrors its carve-up).
+__host__ __device__ inline size_t chain_smem_bytes(int nq_pad, int N, int P, int D, int narr,
+                                                   size_t real, int ring)
+{
+#define MCSAS_AL16(b) ((((size_t)(b)) + 15) & ~size_t(15))
+    size_t s = 16;                                               // mbarrier
+    s += MCSAS_AL16(8 * 3 * (size_t)nq_pad);                             // data
+    s += MCSAS_AL16(8 * (size_t)N * (P > 0 ? P : 1));                    // rset replica
+    s += MCSAS_AL16(64);                                                 // ctrl
+    s += MCSAS_AL16((size_t)ring * (8 * MCSAS_MAX_ACTIVE + 2 * real * 8));   // ring entries
+    s += MCSAS_AL16(8 * (MAX_EVAL_WARPS + 1) * KCAP * 3);                // per-warp sums
+    s += MCSAS_AL16(8 * 2 * MAX_CLUSTER * KCAP * 3);                     // cluster partials (2 buffers)
+    s += MCSAS_AL16(8 * 2 * MAX_CLUSTER) + 16;                           // exchange flags + mbarriers
+    s += MCSAS_AL16(8 * KCAP * 3 + 64);                                  // chi/a/b per proposal + decision
+    s += 2 * MCSAS_AL16(real * (D + 1));                                 // quadrature table
+    s += MCSAS_AL16(real * (size_t)ring * 2 * narr * D) + 16;            // node arrays
+    return s;
+#undef MCSAS_AL16
+}
+

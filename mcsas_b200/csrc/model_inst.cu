@@ -9,15 +9,69 @@
 #define CAT2(a, b) a##b
 #define CAT(a, b) CAT2(a, b)
 
-template <class Real, int QPT, int MAXT>
+template <class Real, int QPT>
 static cudaError_t launch_one(int grid, int threads, size_t smem, cudaStream_t st,
                               const ChainArgs &a)
 {
-    auto k = chain_kernel<MODEL_ID, Real, QPT, MAXT>;
+    auto k = chain_kernel<MODEL_ID, Real, QPT>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k<<<grid, threads, smem, st>>>(a);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(threads, 1, 1);          // eval threads + one producer warp
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = a.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k, a);
+}
+
+template <class Real, int QPT>
+static cudaError_t query_one(int threads, size_t smem, int cluster, int *max_clusters, int *regs)
+{
+    auto k = chain_kernel<MODEL_ID, Real, QPT>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, k);
+    if (e != cudaSuccess) return e;
+    *regs = fa.numRegs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(cluster * 1024, 1, 1);
+    cfg.blockDim = dim3(threads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaOccupancyMaxActiveClusters(max_clusters, k, &cfg);
+}
+
+template <class Real>
+static cudaError_t query_prec(int layout, int threads, size_t smem, int cluster, int *mc, int *regs)
+{
+    switch (layout) {
+    case 0: return query_one<Real, 1>(threads, smem, cluster, mc, regs);
+    case 1: return query_one<Real, 2>(threads, smem, cluster, mc, regs);
+    case 2: return query_one<Real, 4>(threads, smem, cluster, mc, regs);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// co-resident clusters of this configuration on the current device
+cudaError_t CAT(mcsas_query_chain_, MODEL_ID)(int prec, int layout, int threads, size_t smem,
+                                              int cluster, int *max_clusters, int *regs)
+{
+    return prec == MCSAS_FP64 ? query_prec<double>(layout, threads, smem, cluster, max_clusters, regs)
+                              : query_prec<float>(layout, threads, smem, cluster, max_clusters, regs);
 }
 
 template <class Real>
@@ -25,13 +79,9 @@ static cudaError_t launch_prec(int layout, int grid, int threads, size_t smem, c
                                const ChainArgs &a)
 {
     switch (layout) {
-    case 0: return launch_one<Real, 1, 128>(grid, threads, smem, st, a);
-    case 1: return launch_one<Real, 2, 128>(grid, threads, smem, st, a);
-    case 2: return launch_one<Real, 4, 128>(grid, threads, smem, st, a);
-    case 3: return launch_one<Real, 8, 128>(grid, threads, smem, st, a);
-    case 4: return launch_one<Real, 4, 256>(grid, threads, smem, st, a);
-    case 5: return launch_one<Real, 8, 256>(grid, threads, smem, st, a);
-    case 6: return launch_one<Real, 8, 512>(grid, threads, smem, st, a);
+    case 0: return launch_one<Real, 1>(grid, threads, smem, st, a);
+    case 1: return launch_one<Real, 2>(grid, threads, smem, st, a);
+    case 2: return launch_one<Real, 4>(grid, threads, smem, st, a);
     }
     return cudaErrorInvalidValue;
 }

@@ -47,14 +47,14 @@ __device__ __forceinline__ void sincos_qr(const QRep<double> &Q, double r, doubl
 __device__ __forceinline__ void sincos_qr(const QRep<float> &Q, float r, float &s, float &c,
                                           float &x)
 {
-    // phase in turns, reduced with an exact FMA residual so that q*r ~ 1e3..1e4 rad keeps
+    // phase in turns: n = rint(th*r); frac = fma(th, r, -n) is exact up to one rounding, the
+    // low part of q/(2 pi) restores the bits a float q loses, so q*r ~ 1e3..1e4 rad keeps
     // ~1e-7 turn accuracy; then MUFU.SIN / MUFU.COS on [-pi, pi].
     x = Q.q * r;
     float t = Q.th * r;
-    float e = fmaf(Q.th, r, -t);
-    float lo = fmaf(Q.tl, r, e);
     float n = (t + 12582912.f) - 12582912.f;           // rint for |t| < 2^22
-    float fr = (t - n) + lo;
+    float fr = fmaf(Q.th, r, -n);
+    fr = fmaf(Q.tl, r, fr);
     float a = fr * 6.2831853071795865f;
     s = __sinf(a);
     c = __cosf(a);
@@ -75,17 +75,60 @@ __device__ __forceinline__ double sph_ff(const QRep<double> &Q, double r)
     return 3. * (s - x * c) / (x * x * x);
 }
 
+// float flavour returns F/3 (the factor 9 of F^2 is folded into the amplitude, SPH_NORM)
 __device__ __forceinline__ float sph_ff(const QRep<float> &Q, float r)
 {
     float s, c, x;
     sincos_qr(Q, r, s, c, x);
     float x2 = x * x;
-    float big = 3.f * (s - x * c) * fast_rcp(x2 * x);
-    // series below x = 1: MUFU's absolute error would be amplified by 3/x^3
-    float ser = 1.f + x2 * (-0.1f + x2 * (3.5714286e-3f + x2 * (-6.6137566e-5f
-                + x2 * (7.5156325e-7f + x2 * -5.7812558e-9f))));
+    float big = fmaf(-x, c, s) * fast_rcp(x2 * x);
+    // series below x = 1: MUFU's absolute error would be amplified by 1/x^3
+    float ser = 0.33333333f + x2 * (-0.033333333f + x2 * (1.1904762e-3f + x2 * (-2.2045855e-5f
+                + x2 * 2.5052108e-7f)));
     return x < 1.f ? ser : big;
 }
+template <class Real> struct SphNorm;
+template <> struct SphNorm<double> { static constexpr double V = 1.0; };
+template <> struct SphNorm<float> { static constexpr double V = 9.0; };
+
+// log2 of a positive double: exponent by bit ops, mantissa on MUFU.LG2 (abs err ~2e-7)
+__device__ __forceinline__ double fast_log2_pos(double v)
+{
+    int e;
+    double m = frexp(v, &e);
+    return (double)e + (double)__log2f((float)m);
+}
+// g * v^y for v, g > 0 with ~3e-7 relative error and no double pow: used for the fp32
+// chain's contribution amplitudes w*G = volume^(2c)*G (sasmodel.py:44)
+__device__ __forceinline__ float fast_amp(double v, double y, double g)
+{
+    double t = y * fast_log2_pos(v) + fast_log2_pos(g);
+    double ti = rint(t);
+    return ldexpf(exp2f((float)(t - ti)), (int)ti);
+}
+
+// Parameter vector view: fixed model parameters with the active values patched in
+// (scatteringmodel.py:94-96  p.setValue(v) for each active parameter) -- no local array.
+struct PVec {
+    const ModelParams &mp;
+    double v0, v1, v2, v3;
+    __device__ __forceinline__ PVec(const ModelParams &m, const double *pv) : mp(m), v0(0.), v1(0.), v2(0.), v3(0.)
+    {
+        if (m.n_active > 0) v0 = pv[0];
+        if (m.n_active > 1) v1 = pv[1];
+        if (m.n_active > 2) v2 = pv[2];
+        if (m.n_active > 3) v3 = pv[3];
+    }
+    __device__ __forceinline__ double operator[](int i) const
+    {
+        double v = mp.params[i];
+        if (mp.n_active > 0 && mp.active_idx[0] == i) v = v0;
+        if (mp.n_active > 1 && mp.active_idx[1] == i) v = v1;
+        if (mp.n_active > 2 && mp.active_idx[2] == i) v = v2;
+        if (mp.n_active > 3 && mp.active_idx[3] == i) v = v3;
+        return v;
+    }
+};
 
 template <class Real> struct Contrib {
     Real amp;        // w (fp64) or w*G*(model scale)^2 (fp32)
@@ -94,6 +137,22 @@ template <class Real> struct Contrib {
 
 // Volume / weight / surface triple returned by prep (fp64, SI).
 struct VWS { double v, w, s, amp_raw; };
+
+// Amplitude of a contribution, amp = w * fac * G * norm with w = vol^(2c) (sasmodel.py:44):
+// exact double pow (parity mode, eval and fraction kernels) or, FAST, the MUFU-based
+// path of the fp32 chain (w and amp_raw are then not produced).
+template <bool FAST, class Real>
+__device__ __forceinline__ void set_amp(VWS &o, Contrib<Real> &cc, double vol, double ce, double fac,
+                                        double G, double norm)
+{
+    if (FAST) {
+        cc.amp = (Real)fast_amp(vol, 2. * ce, fac * G * norm);
+    } else {
+        o.w = pow(vol, 2. * ce);
+        o.amp_raw = o.w * fac;
+        cc.amp = (Real)(o.amp_raw * G * norm);
+    }
+}
 
 template <class Real> struct QuadTab {
     int D;
@@ -107,7 +166,8 @@ template <int MODEL, class Real> struct Ops;
 // ------------------------------------------------------------------ Sphere --
 template <class Real> struct Ops<MCSAS_SPHERE, Real> {
     static constexpr int NARR = 0;
-    __device__ static VWS prep(const double *p, double ce, double G, const QuadTab<Real> &,
+    template <bool FAST, class PV>
+    __device__ static VWS prep(const PV &p, double ce, double G, const QuadTab<Real> &,
                                Contrib<Real> &cc, Real *)
     {
         double r = p[0], sld = p[1];
@@ -115,9 +175,7 @@ template <class Real> struct Ops<MCSAS_SPHERE, Real> {
         double vol = (M_PI * 4. / 3.) * (r * r * r);    // sphere.py:44
         o.v = vol * sld * sld;                          // :53
         o.s = 4. * M_PI * r * r;                        // :37
-        o.w = pow(vol, 2. * ce);                        // sasmodel.py:44
-        o.amp_raw = o.w;
-        cc.amp = (Real)(o.amp_raw * G);
+        set_amp<FAST>(o, cc, vol, ce, 1., G, SphNorm<Real>::V);
         cc.c[0] = (Real)(r * Units<Real>::LEN);
         return o;
     }
@@ -134,18 +192,17 @@ template <class Real> struct Ops<MCSAS_SPHERE, Real> {
 // in fp64 in both precision modes.
 template <class Real> struct Ops<MCSAS_LMA_DENSE_SPHERE, Real> {
     static constexpr int NARR = 0;
-    __device__ static VWS prep(const double *p, double ce, double G, const QuadTab<Real> &,
+    template <bool FAST, class PV>
+    __device__ static VWS prep(const PV &p, double ce, double G, const QuadTab<Real> &,
                                Contrib<Real> &cc, Real *)
     {
         double r = p[0], mu = p[1], mf = p[2], sld = p[3];
-        if (mf == -1.) mf = pow(0.634 / mu, 1. / 3);    // :73-74
+        if (mf == -1.) mf = FAST ? cbrt(0.634 / mu) : pow(0.634 / mu, 1. / 3);    // :73-74
         VWS o;
         double vol = (M_PI * 4. / 3.) * (r * r * r);
         o.v = vol * sld * sld;
         o.s = 0.;
-        o.w = pow(vol, 2. * ce);
-        o.amp_raw = o.w;
-        cc.amp = (Real)(o.amp_raw * G);
+        set_amp<FAST>(o, cc, vol, ce, 1., G, SphNorm<Real>::V);
         cc.c[0] = (Real)(r * Units<Real>::LEN);
         cc.c[1] = (Real)(mf * r * Units<Real>::LEN);
         cc.c[2] = (Real)mu;
@@ -177,7 +234,8 @@ template <class Real> struct Ops<MCSAS_LMA_DENSE_SPHERE, Real> {
 // ------------------------------------------------------ SphericalCoreShell --
 template <class Real> struct Ops<MCSAS_SPHERICAL_CORE_SHELL, Real> {
     static constexpr int NARR = 0;
-    __device__ static VWS prep(const double *p, double ce, double G, const QuadTab<Real> &,
+    template <bool FAST, class PV>
+    __device__ static VWS prep(const PV &p, double ce, double G, const QuadTab<Real> &,
                                Contrib<Real> &cc, Real *)
     {
         double r = p[0], t = p[1], ec = p[2], es = p[3], esol = p[4];
@@ -186,14 +244,12 @@ template <class Real> struct Ops<MCSAS_SPHERICAL_CORE_SHELL, Real> {
         double d1 = es - esol, d2 = vr * (es - ec);     // ks, vRatio*kc prefactors :64-69
         VWS o;
         o.v = vt; o.s = 0.;                             // :72-76
-        o.w = pow(vt, 2. * ce);
         double nrm = 1.;
         if (sizeof(Real) == 4) {
             nrm = fmax(fabs(d1), fabs(d2));
             if (nrm == 0.) nrm = 1.;
         }
-        o.amp_raw = o.w * nrm * nrm;
-        cc.amp = (Real)(o.amp_raw * G);
+        set_amp<FAST>(o, cc, vt, ce, nrm * nrm, G, SphNorm<Real>::V);
         cc.c[0] = (Real)((r + t) * Units<Real>::LEN);
         cc.c[1] = (Real)(r * Units<Real>::LEN);
         cc.c[2] = (Real)(d1 / nrm);
@@ -211,7 +267,8 @@ template <class Real> struct Ops<MCSAS_SPHERICAL_CORE_SHELL, Real> {
 // ---------------------------------------------------- EllipsoidalCoreShell --
 template <class Real> struct Ops<MCSAS_ELLIPSOIDAL_CORE_SHELL, Real> {
     static constexpr int NARR = 2;
-    __device__ static VWS prep(const double *p, double ce, double G, const QuadTab<Real> &qt,
+    template <bool FAST, class PV>
+    __device__ static VWS prep(const PV &p, double ce, double G, const QuadTab<Real> &qt,
                                Contrib<Real> &cc, Real *nodes)
     {
         double a = p[0], b = p[1], t = p[2], ec = p[3], es = p[4], esol = p[5];
@@ -220,14 +277,12 @@ template <class Real> struct Ops<MCSAS_ELLIPSOIDAL_CORE_SHELL, Real> {
         double k1 = (ec - es) * (vc / vt), k2 = (es - esol) * 1.;   // :83-88
         VWS o;
         o.v = vt; o.s = 0.;                             // :93-97
-        o.w = pow(vt, 2. * ce);
         double nrm = 1.;
         if (sizeof(Real) == 4) {
             nrm = fmax(fabs(k1), fabs(k2));
             if (nrm == 0.) nrm = 1.;
         }
-        o.amp_raw = o.w * nrm * nrm;
-        cc.amp = (Real)(o.amp_raw * G);
+        set_amp<FAST>(o, cc, vt, ce, nrm * nrm, G, SphNorm<Real>::V);
         cc.c[0] = (Real)(k1 / nrm);
         cc.c[1] = (Real)(k2 / nrm);
         for (int j = 0; j < qt.D; ++j) {
@@ -254,16 +309,15 @@ template <class Real> struct Ops<MCSAS_ELLIPSOIDAL_CORE_SHELL, Real> {
 // ----------------------------------------------------- EllipsoidsIsotropic --
 template <class Real> struct Ops<MCSAS_ELLIPSOIDS_ISOTROPIC, Real> {
     static constexpr int NARR = 1;
-    __device__ static VWS prep(const double *p, double ce, double G, const QuadTab<Real> &qt,
+    template <bool FAST, class PV>
+    __device__ static VWS prep(const PV &p, double ce, double G, const QuadTab<Real> &qt,
                                Contrib<Real> &cc, Real *nodes)
     {
         double Ra = p[0], Rc = (p[1] != 0.) ? p[0] * p[3] : p[2], sld = p[5];   // :60-63
         VWS o;
         double vol = 4. / 3. * M_PI * (Ra * Ra) * Rc;   // :80
         o.v = vol * sld * sld; o.s = 0.;                // :84
-        o.w = pow(vol, 2. * ce);
-        o.amp_raw = o.w;
-        cc.amp = (Real)(o.amp_raw * G);
+        set_amp<FAST>(o, cc, vol, ce, 1., G, SphNorm<Real>::V);
         for (int j = 0; j < qt.D; ++j) {
             double sa, ca;
             sincos((double)qt.x[j], &sa, &ca);
@@ -290,16 +344,15 @@ __device__ __forceinline__ float bessel_j1(float x) { return j1f(x); }
 
 template <class Real> struct Ops<MCSAS_CYLINDERS_ISOTROPIC, Real> {
     static constexpr int NARR = 2;
-    __device__ static VWS prep(const double *p, double ce, double G, const QuadTab<Real> &qt,
+    template <bool FAST, class PV>
+    __device__ static VWS prep(const PV &p, double ce, double G, const QuadTab<Real> &qt,
                                Contrib<Real> &cc, Real *nodes)
     {
         double r = p[0], hL = (p[1] != 0.) ? p[0] * p[3] : 0.5 * p[2], sld = p[5];  // :65-68
         VWS o;
         double vol = M_PI * (r * r) * (hL * 2.);        // :93-98
         o.v = vol * sld * sld; o.s = 0.;                // :101
-        o.w = pow(vol, 2. * ce);
-        o.amp_raw = o.w;
-        cc.amp = (Real)(o.amp_raw * G);
+        set_amp<FAST>(o, cc, vol, ce, 1., G, 1.);
         cc.c[0] = (Real)(r * Units<Real>::LEN);
         cc.c[1] = (Real)(hL * Units<Real>::LEN);
         for (int j = 0; j < qt.D; ++j) {
@@ -338,7 +391,8 @@ template <class Real> struct Ops<MCSAS_CYLINDERS_ISOTROPIC, Real> {
 // ----------------------------------------------------------- GaussianChain --
 template <class Real> struct Ops<MCSAS_GAUSSIAN_CHAIN, Real> {
     static constexpr int NARR = 0;
-    __device__ static VWS prep(const double *p, double ce, double G, const QuadTab<Real> &,
+    template <bool FAST, class PV>
+    __device__ static VWS prep(const PV &p, double ce, double G, const QuadTab<Real> &,
                                Contrib<Real> &cc, Real *)
     {
         double rg = p[0], bp = p[1], etas = p[2], k = p[3];
@@ -346,15 +400,13 @@ template <class Real> struct Ops<MCSAS_GAUSSIAN_CHAIN, Real> {
         VWS o;
         double vol = k * (rg * rg);                     // :64
         o.v = vol; o.s = 0.;
-        o.w = pow(vol, 2. * ce);
         if (sizeof(Real) == 4) {
-            o.amp_raw = o.w * beta * beta;
+            set_amp<FAST>(o, cc, vol, ce, beta * beta, G, 1.);
             cc.c[1] = (Real)1;
         } else {
-            o.amp_raw = o.w;
+            set_amp<FAST>(o, cc, vol, ce, 1., G, 1.);
             cc.c[1] = (Real)beta;
         }
-        cc.amp = (Real)(o.amp_raw * G);
         cc.c[0] = (Real)(rg * Units<Real>::LEN);
         return o;
     }
@@ -412,16 +464,15 @@ static __device__ __noinline__ double kho_core(double z, int regime, double ef, 
 
 template <class Real> struct Ops<MCSAS_KHOLODENKO, Real> {
     static constexpr int NARR = 0;
-    __device__ static VWS prep(const double *p, double ce, double G, const QuadTab<Real> &,
+    template <bool FAST, class PV>
+    __device__ static VWS prep(const PV &p, double ce, double G, const QuadTab<Real> &,
                                Contrib<Real> &cc, Real *)
     {
         double R = p[0], lk = p[1], L = p[2];
         VWS o;
         double vol = M_PI * L * (R * R);                // :93
         o.v = vol; o.s = 0.;
-        o.w = pow(vol, 2. * ce);
-        o.amp_raw = o.w;
-        cc.amp = (Real)(o.amp_raw * G);
+        set_amp<FAST>(o, cc, vol, ce, 1., G, 1.);
         cc.c[0] = (Real)(R * Units<Real>::LEN);
         cc.c[1] = (Real)(lk * Units<Real>::LEN);
         cc.c[2] = (Real)(3. * L / lk);                  // x, :86
@@ -461,11 +512,3 @@ template <class Real> struct Ops<MCSAS_KHOLODENKO, Real> {
     }
 };
 
-// Patch the active values into the full parameter vector
-// (scatteringmodel.py:94-96  p.setValue(v) for each active parameter).
-__device__ __forceinline__ void patch_params(const ModelParams &mp, const double *pv, double *p)
-{
-#pragma unroll
-    for (int i = 0; i < MCSAS_MAX_PARAMS; ++i) p[i] = mp.params[i];
-    for (int i = 0; i < mp.n_active; ++i) p[mp.active_idx[i]] = pv[i];
-}

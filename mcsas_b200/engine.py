@@ -102,12 +102,13 @@ class Engine(object):
     def make_config(n_contribs=300, n_reps=10, conv_crit=1.0, max_iter=100000, max_retries=5,
                     comp_exp=0.6666666, find_background=True, positive_background=False,
                     start_from_minimum=False, precision=_lib.FP32, seed=0, spec_max=0,
-                    record_trace=False, first_chain=0):
+                    record_trace=False, first_chain=0, cluster_size=0, slice_steps=0):
         return RunConfig(int(n_contribs), int(n_reps), float(conv_crit), int(max_iter),
                          int(max_retries), float(comp_exp), int(bool(find_background)),
                          int(bool(positive_background)), int(bool(start_from_minimum)),
                          int(precision), int(seed) & 0xFFFFFFFFFFFFFFFF, int(spec_max),
-                         int(bool(record_trace)), int(first_chain))
+                         int(bool(record_trace)), int(first_chain), int(cluster_size),
+                         int(slice_steps))
 
     def run_async(self, cfg, stream=None):
         stride = 0
@@ -128,6 +129,11 @@ class Engine(object):
         self._check(self._L.mcsas_wait(self._ctx, C.byref(ms)), "wait")
         return ms.value
 
+    def run_info(self):
+        n, c, ms = C.c_int(), C.c_int(), C.c_float()
+        self._check(self._L.mcsas_run_info(self._ctx, C.byref(n), C.byref(c), C.byref(ms)), "run_info")
+        return dict(launches=n.value, last_cluster=c.value, kernel_ms=ms.value)
+
     def request_stop(self):
         self._L.mcsas_request_stop(self._ctx)
 
@@ -145,10 +151,11 @@ class Engine(object):
         num_iter = np.zeros(C_, dtype=np.int64)
         num_moves = np.zeros(C_, dtype=np.int64)
         evals = np.zeros(C_, dtype=np.int64)
+        steps_all = np.zeros(C_, dtype=np.int64)
         attempts = np.zeros(C_, dtype=np.int32)
         self._check(self._L.mcsas_fetch(self._ctx, _dp(contribs), _dp(fit), _dp(scaling), _dp(background),
                                         _dp(conval), _dp(conval0), _llp(num_iter), _llp(num_moves),
-                                        _ip(attempts), _dp(elapsed), _llp(evals)), "fetch")
+                                        _ip(attempts), _dp(elapsed), _llp(evals), _llp(steps_all)), "fetch")
         fits, off = [], 0
         for s in range(S):
             n = int(self.nq[s]) * R
@@ -159,7 +166,8 @@ class Engine(object):
                     background=background.reshape(shp), conval=conval.reshape(shp),
                     conval0=conval0.reshape(shp), num_iter=num_iter.reshape(shp),
                     num_moves=num_moves.reshape(shp), attempts=attempts.reshape(shp),
-                    elapsed=elapsed.reshape(shp), evals=evals.reshape(shp))
+                    elapsed=elapsed.reshape(shp), evals=evals.reshape(shp),
+                    steps_all=steps_all.reshape(shp))
 
     def fetch_trace(self, chain, capacity):
         acc = np.zeros(capacity, dtype=np.uint8)

@@ -167,6 +167,7 @@ class McSAS(object):
             # extras (not in the reference's dict)
             numIterAll=out["num_iter"][0], numMoves=out["num_moves"][0],
             conval=conval, attempts=out["attempts"][0], evals=out["evals"][0],
+            stepsAll=out["steps_all"][0],
             scalingAll=scalings, backgroundAll=backgrounds))
 
     # ----------------------------------------------------------------- mcFit --

@@ -24,7 +24,7 @@ def engine_for(om, datasets, device=0):
     return eng
 
 
-def run_golden_chain(g, precision, spec_max, pad_steps=8, quad_rule=0):
+def run_golden_chain(g, precision, spec_max, pad_steps=8, quad_rule=0, cluster=0):
     """Replay a golden chain (uploaded generator-output stream) on the GPU."""
     from mcsas_b200 import Engine
     om = common.oracle_model(g, quad_rule=quad_rule)
@@ -39,7 +39,7 @@ def run_golden_chain(g, precision, spec_max, pad_steps=8, quad_rule=0):
                              find_background=g["find_background"],
                              positive_background=g["positive_background"],
                              start_from_minimum=g["start_from_minimum"], precision=precision,
-                             spec_max=spec_max, record_trace=True)
+                             spec_max=spec_max, record_trace=True, cluster_size=cluster)
     eng.run(cfg, stream=stream)
     out = eng.fetch()
     acc, chi = eng.fetch_trace(0, max_iter)

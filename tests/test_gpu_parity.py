@@ -52,10 +52,13 @@ CHAINS = [c for c in common.CHAIN_CASES if c != "sphere_posbg"]
 
 
 @pytest.mark.parametrize("name", CHAINS)
-@pytest.mark.parametrize("spec_max", [1, 32])
-def test_deterministic_chain_matches_reference(name, spec_max):
+@pytest.mark.parametrize("spec_max,cluster", [(1, 1), (32, 1), (32, 2), (8, 4), (32, 8)])
+def test_deterministic_chain_matches_reference(name, spec_max, cluster):
+    """Uploaded reference proposal stream, fp64: sequential (spec_max=1) and speculative
+    batches, q axis on one CTA or split over a 2/4/8-CTA cluster -- all must reproduce the
+    reference's accept/reject sequence."""
     g = common.load_chain(name)
-    out = gpu_common.run_golden_chain(g, FP64, spec_max)
+    out = gpu_common.run_golden_chain(g, FP64, spec_max, cluster=cluster)
     assert int(out["num_iter"][0, 0]) == g["num_iter"]
     assert int(out["num_moves"][0, 0]) == g["num_moves"]
     assert np.array_equal(out["accept"], g["accept"])        # accept/reject sequence
