@@ -175,16 +175,20 @@ extern "C" int mcsas_upload_datasets(mcsas_ctx *ctx, int n_sets, const int *nq, 
     std::vector<double> packed((size_t)off, 0.0);
     for (int s = 0; s < n_sets; ++s) {
         double *dst = packed.data() + sets[s].offset;
-        double qmax = -INFINITY;
+        double qmax = -INFINITY, qmin = INFINITY, imax = 0.;
         for (int i = 0; i < nq[s]; ++i) {
             dst[i] = q[src + i];
             dst[sets[s].nq_pad + i] = intensity[src + i];
             dst[2 * sets[s].nq_pad + i] = sigma[src + i];
             if (q[src + i] > qmax) qmax = q[src + i];
+            if (q[src + i] > 0. && q[src + i] < qmin) qmin = q[src + i];
+            if (fabs(intensity[src + i]) > imax) imax = fabs(intensity[src + i]);
             if (!std::isfinite(q[src + i]) || !std::isfinite(intensity[src + i]) || !std::isfinite(sigma[src + i]))
                 return fail(ctx, MCSAS_ERR_ARG, "dataset %d: non-finite value at point %d", s, i);
         }
         sets[s].q_max = qmax;
+        sets[s].q_ref = (qmin < INFINITY && qmax > 0.) ? sqrt(qmin * qmax) : 1e9;
+        sets[s].i_scale = (imax > 0. && std::isfinite(imax)) ? imax : 1.;
         src += nq[s];
     }
     cudaFree(ctx->d_sets); cudaFree(ctx->d_data);
@@ -337,14 +341,28 @@ template <class T> static cudaError_t regrow(T **p, size_t n)
 // Thread layout of one chain: cluster size C (q split), q points per eval thread, eval
 // threads per CTA.  More CTAs per chain when few chains are alive, so that freed SMs
 // shorten the tail of the slow chains.
-struct ChainPlan { int cluster, layout, threads, resident; };
+struct ChainPlan { int cluster, layout, threads, resident, warps_q; };
 
-// Candidate layouts: cluster size C in {1,2,4,8} x eval threads T in {64,128,256}; QPT is the
-// smallest instantiated value that covers nq.  Only layouts whose clusters are ALL
-// co-resident (cudaOccupancyMaxActiveClusters) are considered, so a slice is one wave;
-// among those the one that spreads the live chains over the most SMs wins, ties go to the
-// smaller cluster (less exchange per batch).
-static int plan_chain(mcsas_ctx *ctx, int nq, int n_live, ChainPlan *out)
+static int query_resident(mcsas_ctx *ctx, int c, int layout, int block_threads, int *resident)
+{
+    const long long key = ((((long long)ctx->mp.model_id * 2 + ctx->precision) * 16 + c) * 8 + layout) * 2048
+                          + block_threads + ((long long)ctx->smem << 26);
+    auto it = ctx->occ_cache.find(key);
+    if (it != ctx->occ_cache.end()) { *resident = it->second; return 0; }
+    int regs = 0;
+    *resident = 0;
+    cudaError_t e = QUERY_FN[ctx->mp.model_id](ctx->precision, layout, block_threads, ctx->smem, c, resident, &regs);
+    if (e != cudaSuccess) { cudaGetLastError(); *resident = 0; }
+    ctx->occ_cache[key] = *resident;
+    return 0;
+}
+
+// Candidate layouts of the fp64 parity kernel: cluster size C in {1,2,4,8} x eval threads T
+// in {64,128,256}; QPT is the smallest instantiated value that covers nq.  Only layouts whose
+// clusters are ALL co-resident (cudaOccupancyMaxActiveClusters) are considered, so a slice is
+// one wave; among those the one that spreads the live chains over the most SMs wins, ties go
+// to the smaller cluster (less exchange per batch).
+static int plan_chain_fp64(mcsas_ctx *ctx, int nq, int n_live, ChainPlan *out)
 {
     const int sms = ctx->prop.multiProcessorCount;
     int forced_c = ctx->forced_cluster, forced_t = 0, forced_q = 0;
@@ -352,7 +370,7 @@ static int plan_chain(mcsas_ctx *ctx, int nq, int n_live, ChainPlan *out)
     if ((env = getenv("MCSAS_B200_CLUSTER")) && atoi(env) > 0) forced_c = atoi(env);
     if ((env = getenv("MCSAS_B200_T")) && atoi(env) > 0) forced_t = atoi(env);
     if ((env = getenv("MCSAS_B200_QPT")) && atoi(env) > 0) forced_q = atoi(env);
-    ChainPlan best = {0, 0, 0, 0};
+    ChainPlan best = {0, 0, 0, 0, 0};
     double best_score = -1.;
     for (int c = 1; c <= MAX_CLUSTER; c *= 2) {
         if (forced_c > 0 && c != forced_c && !(forced_c > MAX_CLUSTER && c == MAX_CLUSTER)) continue;
@@ -367,20 +385,10 @@ static int plan_chain(mcsas_ctx *ctx, int nq, int n_live, ChainPlan *out)
             int threads = (((n + qpt - 1) / qpt) + 31) & ~31;
             if (threads < 32) threads = 32;
             if (forced_t <= 0 && tcap > 64 && threads * 2 <= tcap) continue;        // same as a smaller tcap
-            int resident = 0, regs = 0;
-            const long long key = ((((long long)ctx->mp.model_id * 2 + ctx->precision) * 16 + c) * 8 + layout) * 1024
-                                  + threads + ((long long)ctx->smem << 24);
-            auto it = ctx->occ_cache.find(key);
-            if (it != ctx->occ_cache.end()) resident = it->second;
-            else {
-                cudaError_t e = QUERY_FN[ctx->mp.model_id](ctx->precision, layout, threads + 32, ctx->smem, c,
-                                                           &resident, &regs);
-                if (e != cudaSuccess) { cudaGetLastError(); resident = 0; }
-                ctx->occ_cache[key] = resident;
-            }
+            int resident = 0;
+            query_resident(ctx, c, layout, threads + 32, &resident);
             if (resident < 1) continue;
             const bool one_wave = n_live <= resident;
-            // SMs kept busy by the live chains (a CTA occupies at most one SM), in eval warps
             const double ctas = (double)n_live * c;
             const double per_sm = ctas / sms;
             double busy = per_sm >= 1. ? 1. : per_sm;                 // fraction of SMs with work
@@ -396,6 +404,63 @@ static int plan_chain(mcsas_ctx *ctx, int nq, int n_live, ChainPlan *out)
     return MCSAS_OK;
 }
 
+// Layout of the fp32 production kernel: cluster size C (q split) x q points per thread
+// (1,2,4) x proposal groups PS (1,2,4); eval threads = warps_q * PS * 32.
+// Measured on B200 (tools/tune.py fast, nq = 1000): 8 eval warps with 4 q points per thread
+// are the sweet spot at every cluster size; a cluster pays for its per-batch exchange only
+// when its CTAs get SMs of their own, so C = largest of {1,2,4} with n_live * C <= #SMs.
+static int plan_chain_fp32(mcsas_ctx *ctx, int nq, int n_live, ChainPlan *out)
+{
+    const int sms = ctx->prop.multiProcessorCount;
+    int forced_c = ctx->forced_cluster, forced_q = 0, forced_ps = 0;
+    const char *env;
+    if ((env = getenv("MCSAS_B200_CLUSTER")) && atoi(env) > 0) forced_c = atoi(env);
+    if ((env = getenv("MCSAS_B200_QPT")) && atoi(env) > 0) forced_q = atoi(env);
+    if ((env = getenv("MCSAS_B200_PS")) && atoi(env) > 0) forced_ps = atoi(env);
+    if (forced_c > MAX_CLUSTER) forced_c = MAX_CLUSTER;
+    ChainPlan best = {0, 0, 0, 0, 0};
+    // preference order of cluster sizes: the planned one first, then smaller, then larger
+    int want_c = 1;
+    while (want_c < 4 && (long long)n_live * want_c * 2 <= sms) want_c *= 2;
+    int order[8], no = 0;
+    if (forced_c > 0) order[no++] = forced_c;
+    else {
+        for (int c = want_c; c >= 1; c /= 2) order[no++] = c;
+        for (int c = want_c * 2; c <= MAX_CLUSTER; c *= 2) order[no++] = c;
+    }
+    const int grp_of[3] = {4, 8, 8};                        // proposals per chunk of layout QPT = 1,2,4
+    for (int oi = 0; oi < no && best.cluster == 0; ++oi) {
+        const int c = order[oi];
+        const int n = (nq + c - 1) / c;
+        for (int l = N_CHAIN_LAYOUTS - 1; l >= 0 && best.cluster == 0; --l) {       // QPT = 4 first
+            const int qpt = CHAIN_QPT[l];
+            if (forced_q > 0 && qpt != forced_q) continue;
+            const int wq = (n + 32 * qpt - 1) / (32 * qpt);
+            if (wq * 32 > FAST_MAX_EVAL_THREADS[l]) continue;
+            int ps = 1;
+            while (ps < 4 && wq * ps * 2 <= 8 && wq * ps * 2 * 32 <= FAST_MAX_EVAL_THREADS[l]
+                   && ps * 2 * grp_of[l] <= ctx->args.spec_max) ps *= 2;
+            if (forced_ps > 0) ps = forced_ps;
+            const int threads = wq * ps * 32;
+            if (threads > FAST_MAX_EVAL_THREADS[l] || threads / 32 > FAST_MAX_WARPS) continue;
+            int resident = 0;
+            query_resident(ctx, c, l, threads + 32, &resident);
+            if (resident < 1) continue;
+            if (resident < n_live && forced_c <= 0 && oi + 1 < no) continue;       // prefer one wave
+            best.cluster = c; best.layout = l; best.threads = threads; best.resident = resident; best.warps_q = wq;
+        }
+    }
+    if (best.cluster == 0) return fail(ctx, MCSAS_ERR_ARG, "no launchable fp32 chain layout for nq=%d", nq);
+    *out = best;
+    return MCSAS_OK;
+}
+
+static int plan_chain(mcsas_ctx *ctx, int nq, int n_live, ChainPlan *out)
+{
+    return ctx->precision == MCSAS_FP64 ? plan_chain_fp64(ctx, nq, n_live, out)
+                                        : plan_chain_fp32(ctx, nq, n_live, out);
+}
+
 // Launch one time slice for the chains listed in ctx->h_ids[0..n_live).
 static int launch_slice(mcsas_ctx *ctx, int n_live, bool resume)
 {
@@ -404,6 +469,7 @@ static int launch_slice(mcsas_ctx *ctx, int n_live, bool resume)
     int prc = plan_chain(ctx, ctx->nq_max, n_live, &pl);
     if (prc) return prc;
     a.cluster = pl.cluster;
+    a.warps_q = pl.warps_q;
     ctx->last_threads = pl.threads; ctx->last_qpt = CHAIN_QPT[pl.layout]; ctx->last_resident = pl.resident;
     a.resume = resume ? 1 : 0;
     a.chain_ids = nullptr;
@@ -441,13 +507,28 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     int nq_pad_max = (ctx->nq_max + 1) & ~1;
     const size_t smem_limit = (size_t)ctx->prop.sharedMemPerBlockOptin;
     int ring = N < RING_MAX ? N : RING_MAX;
-    while (ring > 4 && chain_smem_bytes(nq_pad_max, N, P, D, narr, real, ring) > smem_limit) ring /= 2;
-    size_t smem = chain_smem_bytes(nq_pad_max, N, P, D, narr, real, ring);
+    if (cfg->precision == MCSAS_FP32) {                  // fp32 kernel indexes the ring with a mask
+        int p2 = 1;
+        while (p2 * 2 <= ring) p2 *= 2;
+        ring = p2;
+        if (cfg->max_iter >= (1LL << 31)) return fail(ctx, MCSAS_ERR_ARG, "run: max_iter must be < 2^31");
+    }
+    auto smem_of = [&](int rg) {
+        return cfg->precision == MCSAS_FP64 ? chain_smem_bytes(nq_pad_max, N, P, D, narr, real, rg)
+                                            : fast_smem_bytes(nq_pad_max, N, P, D, narr, rg);
+    };
+    while (ring > 4 && smem_of(ring) > smem_limit) ring /= 2;
+    size_t smem = smem_of(ring);
     if (smem > smem_limit)
         return fail(ctx, MCSAS_ERR_ARG, "run: configuration needs %zu B shared memory (> %zu)", smem, smem_limit);
     int kcap = cfg->spec_max <= 0 ? MCSAS_MAX_SPEC : (cfg->spec_max > MCSAS_MAX_SPEC ? MCSAS_MAX_SPEC : cfg->spec_max);
     if (kcap > ring / 4) kcap = ring / 4;
     if (kcap < 1) kcap = 1;
+    if (cfg->precision == MCSAS_FP32) {                  // fp32 kernel: batches are powers of two
+        int p2 = 1;
+        while (p2 * 2 <= kcap) p2 *= 2;
+        kcap = p2;
+    }
 
     // proposal stream (deterministic parity mode)
     const double *d_stream = nullptr;

@@ -1,0 +1,769 @@
+// chain_fast.cuh -- the PRODUCTION (fp32) MC-chain kernel.
+//
+// Same contract as chain_kernel (chain_kernel.cuh): one greedy chain of McSAS.mcFit
+// (src/mcsas/mcsas/mcsas.py:287-439) per thread-block cluster, speculative batches,
+// producer warp + ring, time slices.  What differs is the arithmetic of the inner loop:
+//
+//  * RESIDUAL-DELTA least squares.  The reference re-solves scale/background for every
+//    proposal (backgroundscalingfit.py:112-139).  chi^2(a,b) is an exact quadratic, so for
+//    a proposal that changes the model by d = I_new - I_old (mcsas.py:366) its minimum
+//    follows from FOUR sums over q of the small quantity u = d/sigma,
+//        s1 = sum rho u,  s2 = sum u^2,  s3 = sum mu u,  s4 = sum omega u
+//    (rho = current residual/sigma, mu = current model/sigma, omega = 1/sigma), expanded
+//    around the current fit (a0,b0).  None of them cancels against a large base term, so
+//    fp32 accumulation resolves the accept test `chi2_new < chi2_old` (mcsas.py:379) to
+//    ~1e-6 of the CHANGE of chi2 -- no fp64 and no conversion in the inner loop.  The base
+//    sums of the accepted state are re-accumulated exactly in fp64 inside the next batch.
+//  * the 1/(qr)^3 of the sphere amplitude is split into a per-contribution factor (folded
+//    into the amplitude by the producer warp) and a per-q factor (folded into 1/sigma), so
+//    an evaluation costs MUFU.SIN + MUFU.COS and no MUFU.RCP.
+//  * wide CTAs: up to 31 eval warps; when the q slice of a CTA needs fewer warps the
+//    spare warps form further PROPOSAL GROUPS that evaluate other proposals of the batch.
+#pragma once
+#include "chain_kernel.cuh"
+
+// ---- per-model fast evaluation: scaled intensity D with  I(q) = D * (q_ref/q)^QS_POW ------
+template <int MODEL> struct FastOps {
+    using O = Ops<MODEL, float>;
+    static constexpr int QS_POW = 0;
+    template <class PV>
+    __device__ static void prep(const PV &p, double ce, double G, float, const QuadTab<float> &qt,
+                                Contrib<float> &cc, float *nodes)
+    {
+        O::template prep<true>(p, ce, G, qt, cc, nodes);
+    }
+    __device__ __forceinline__ static float evalS(const Contrib<float> &cc, const float *nodes,
+                                                  const QuadTab<float> &qt, const QRep<float> &Q)
+    {
+        return O::eval(cc, nodes, qt, Q);
+    }
+    // scaled intensity change of a proposal: D(new) - D(old) for the thread's q points
+    template <int QPT>
+    __device__ __forceinline__ static void diffS(const Contrib<float> &cn, const Contrib<float> &co,
+                                                 const float *nn, const float *no, const QuadTab<float> &qt,
+                                                 const QRep<float> (&Q)[QPT], float (&d)[QPT])
+    {
+#pragma unroll
+        for (int j = 0; j < QPT; ++j) d[j] = evalS(cn, nn, qt, Q[j]) - evalS(co, no, qt, Q[j]);
+    }
+};
+
+// g(x) = sin x - x cos x = x^3 F(x)/3   (sphere.py:62); SER: series below x = 1, where
+// s - x c cancels
+template <bool SER> __device__ __forceinline__ float sph_g(const QRep<float> &Q, float r)
+{
+    float s, c, x;
+    sincos_qr(Q, r, s, c, x);
+    float g = fmaf(-x, c, s);
+    if (SER) {
+        float x2 = x * x;
+        float ser = (x * x2) * (0.33333333f + x2 * (-0.033333333f + x2 * (1.1904762e-3f
+                    + x2 * (-2.2045855e-5f + x2 * 2.5052108e-7f))));
+        g = x < 1.f ? ser : g;
+    }
+    return g;
+}
+
+template <> struct FastOps<MCSAS_SPHERE> {
+    using O = Ops<MCSAS_SPHERE, float>;
+    static constexpr int QS_POW = 6;
+    template <class PV>
+    __device__ static void prep(const PV &p, double ce, double G, float qref, const QuadTab<float> &qt,
+                                Contrib<float> &cc, float *nodes)
+    {
+        O::template prep<true>(p, ce, G, qt, cc, nodes);
+        double xr = (double)cc.c[0] * (double)qref;          // r * q_ref
+        double x3 = xr * xr * xr;
+        cc.c[1] = (float)((double)cc.amp / (x3 * x3));       // amp / (r q_ref)^6
+    }
+    __device__ __forceinline__ static float evalS(const Contrib<float> &cc, const float *,
+                                                  const QuadTab<float> &, const QRep<float> &Q)
+    {
+        float g = sph_g<true>(Q, cc.c[0]);
+        return (g * g) * cc.c[1];
+    }
+    // q ascends along the lanes, so "some x < 1" is warp-uniform for all but one warp per
+    // radius: one vote per proposal selects the variant without the series.  Callers are
+    // warp-convergent.
+    template <int QPT>
+    __device__ __forceinline__ static void diffS(const Contrib<float> &cn, const Contrib<float> &co,
+                                                 const float *, const float *, const QuadTab<float> &,
+                                                 const QRep<float> (&Q)[QPT], float (&d)[QPT])
+    {
+        const float rmin = fminf(cn.c[0], co.c[0]);
+        bool small = false;
+#pragma unroll
+        for (int j = 0; j < QPT; ++j) small |= Q[j].q * rmin < 1.f;
+        if (__any_sync(0xffffffffu, small)) {
+#pragma unroll
+            for (int j = 0; j < QPT; ++j) {
+                float gn = sph_g<true>(Q[j], cn.c[0]), go = sph_g<true>(Q[j], co.c[0]);
+                d[j] = fmaf(gn * gn, cn.c[1], -(go * go) * co.c[1]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < QPT; ++j) {
+                float gn = sph_g<false>(Q[j], cn.c[0]), go = sph_g<false>(Q[j], co.c[0]);
+                d[j] = fmaf(gn * gn, cn.c[1], -(go * go) * co.c[1]);
+            }
+        }
+    }
+};
+
+struct FastDec {
+    int kstar;
+    int wd;
+    double a, b, conval;
+};
+
+// Minimum of the exact quadratic chi^2 of the proposal with delta sums (s1..s4) around the
+// centre (a0,b0) of a state with base sums S, Sm, Smm, E0, E1, E2 (see file header).
+struct FastBase { double S, Sm, Smm, E0, E1, E2, a0, b0; };
+__device__ __forceinline__ void fast_solve(const FastBase &B, int find_bg, int pos_bg, double s1, double s2,
+                                           double s3, double s4, double &rss, double &an, double &bn)
+{
+    const double Smp = B.Sm + s4, Smmp = B.Smm + 2. * s3 + s2;
+    const double f0 = B.E0 - 2. * B.a0 * s1 + B.a0 * B.a0 * s2;
+    const double ga = -2. * (B.E1 + s1 - B.a0 * (s3 + s2));
+    const double gb = -2. * (B.E2 - B.a0 * s4);
+    const double Haa = 2. * Smmp, Hab = 2. * Smp, Hbb = 2. * B.S;
+    double da, db = 0.;
+    if (find_bg) {
+        const double inv = 1. / (Haa * Hbb - Hab * Hab);
+        da = -(Hbb * ga - Hab * gb) * inv;
+        db = -(Haa * gb - Hab * ga) * inv;
+        rss = f0 + .5 * (ga * da + gb * db);
+        if (pos_bg && B.b0 + db < 0.) {                          // |b| residual -> b = 0 (:60-63)
+            db = -B.b0;
+            da = -(ga + Hab * db) / Haa;
+            rss = f0 + ga * da + gb * db + .5 * (Haa * da * da + 2. * Hab * da * db + Hbb * db * db);
+        }
+    } else {                                                     // chiNoBg (:66-70), b0 == 0
+        da = -ga / Haa;
+        rss = f0 + .5 * ga * da;
+    }
+    an = B.a0 + da;
+    bn = B.b0 + db;
+}
+
+template <int NG> __device__ __forceinline__ int grp_perm(int lane)
+{
+    return NG == 8 ? ((lane >> 2) & 7) : ((lane >> 3) & 3);
+}
+
+template <int MODEL, int QPT>
+__global__ void __launch_bounds__(QPT == 1 ? 1024 : (QPT == 2 ? 544 : 288), 1)
+chain_fast_kernel(const __grid_constant__ ChainArgs a)
+{
+    using FO = FastOps<MODEL>;
+    using O = Ops<MODEL, float>;
+    constexpr int NARR = O::NARR;
+    constexpr int FGRP = QPT == 1 ? 4 : 8;         // proposals per reduce-scatter chunk
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T = blockDim.x - 32;                 // eval threads; the last warp produces
+    const int W = T >> 5;
+    const bool producer = tid >= T;
+    const int WQ = a.warps_q;                      // warps that cover this CTA's q slice once
+    const int PS = W / WQ;                         // proposal groups
+    const int grp = producer ? PS : warp / WQ, wq = warp % WQ;
+    const int TQ = WQ * 32, qtid = wq * 32 + lane;
+    const int C = a.cluster;
+    const int rank = C > 1 ? (int)cluster_ctarank() : 0;
+    const int slot = blockIdx.x / C;
+    const int chain = a.chain_ids ? a.chain_ids[slot] : slot;
+    const uint32_t gchain = (uint32_t)(a.first_chain + chain);
+    const int set = chain / a.n_reps;
+    const DatasetDesc ds = a.sets[set];
+    const int nq = ds.nq, N = a.n_contribs, P = a.mp.n_active;
+    const int D = NARR ? a.mp.quad_nodes : 0;
+    const int RING = a.ring;
+    const int kmax = a.spec_max;
+
+    // ---- shared memory carve-up (keep in sync with fast_smem_bytes) -----------------------
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned char *sp = smem_raw;
+    auto carve = [&](size_t bytes) { unsigned char *p = sp; sp += (bytes + 15) & ~size_t(15); return p; };
+    uint64_t *s_bar = (uint64_t *)carve(16);
+    double *s_data = (double *)carve(sizeof(double) * 3 * ds.nq_pad);
+    double *s_rset = (double *)carve(sizeof(double) * N * (P > 0 ? P : 1));
+    ChainCtrl *s_ctrl = (ChainCtrl *)carve(64);
+    RingEntry<float> *s_ring = (RingEntry<float> *)carve((size_t)RING * sizeof(RingEntry<float>));
+    float4 *s_wsum = (float4 *)carve(16 * (size_t)FAST_MAX_WARPS * KCAP);
+    double *s_bsum = (double *)carve(8 * (size_t)(FAST_MAX_WARPS + 1) * 6);
+    constexpr int XU = 2 * KCAP + 8;               // b64 units per rank in an exchange buffer
+    double *s_part = (double *)carve(8 * 2 * (size_t)MAX_CLUSTER * XU);
+    uint64_t *s_xbar = (uint64_t *)carve(16);
+    double *s_chi = (double *)carve(8 * (size_t)KCAP + 128);
+    FastDec *s_dec = (FastDec *)(s_chi + KCAP);
+    double *s_asum = (double *)carve(8 * (size_t)(FAST_MAX_WARPS + 2) * 3 + 8 * 2 * MAX_CLUSTER * 3);
+    double *s_apart = s_asum + (FAST_MAX_WARPS + 2) * 3;
+    double *s_ft = (double *)carve(8 * 2 * FAST_QCAP);            // model intensity, double buffered
+    double *s_In = (double *)carve(8 * FAST_QCAP);                // I / i_scale
+    double *s_sw = (double *)carve(8 * FAST_QCAP);                // i_scale / sigma (0: padding)
+    float *s_qs = (float *)carve(4 * FAST_QCAP);                  // (q_ref/q)^QS_POW
+    float *s_qx = (float *)carve(sizeof(float) * (D + 1));
+    float *s_qw = (float *)carve(sizeof(float) * (D + 1));
+    float *s_nodes = (float *)sp;                  // [RING][2][NARR][D]
+    const size_t NSTR = (size_t)NARR * D;
+
+    // ---- stage the dataset once: TMA bulk copy global -> shared ---------------------------
+    if (tid == 0) { mbar_init(s_bar, 1); mbar_init(s_xbar, 1); mbar_init(s_xbar + 1, 1); s_dec->wd = 0; }
+    unsigned xphase = 0;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t bytes = (uint32_t)(sizeof(double) * 3 * ds.nq_pad);
+        mbar_expect_tx(s_bar, bytes);
+        tma_bulk_g2s(s_data, a.data + ds.offset, bytes, s_bar);
+    }
+    for (int j = tid; j < D; j += blockDim.x) {
+        s_qx[j] = (float)a.quad_x[j];
+        s_qw[j] = (float)a.quad_w[j];
+    }
+    mbar_wait(s_bar, 0);
+    __syncthreads();
+    const QuadTab<float> qt = { D, a.mp.quad_rule, s_qx, s_qw };
+    const float qref = (float)(ds.q_ref * 1e-9);   // 1/nm
+
+    // ---- per-thread resident state of q point (j*C + rank)*TQ + qtid ----------------------
+    // intensities are normalised by i_scale; sw = 1/sigma, In = I (normalised), ft = model (fp64)
+    QRep<float> Q[QPT];
+    float cq[QPT], rho[QPT], mu[QPT], om[QPT];
+    int cur = 0;                                   // s_ft buffer holding the current state
+    const double inorm = 1. / ds.i_scale;
+    double v3[3] = {0., 0., 0.};
+#pragma unroll
+    for (int j = 0; j < QPT; ++j) {
+        int i = (j * C + rank) * TQ + qtid;
+        bool valid = !producer && i < nq;
+        int ii = (i < nq) ? i : nq - 1;
+        double qv = s_data[ii], Iv = s_data[ds.nq_pad + ii] * inorm, ev = s_data[2 * ds.nq_pad + ii] * inorm;
+        if (ev == 0.0) ev = 1. * inorm;                          // backgroundscalingfit.py:117
+        Q[j].set(qv);
+        double qsd = 1.;
+        if (FO::QS_POW > 0) {
+            double t = (double)qref / (qv * 1e-9);
+            double t2 = t * t;
+            qsd = FO::QS_POW == 6 ? t2 * t2 * t2 : (FO::QS_POW == 4 ? t2 * t2 : t2);
+        }
+        const float qsf = (float)qsd;
+        const double swd = valid ? 1. / ev : 0.;
+        cq[j] = (float)(swd * (double)qsf);
+        om[j] = (float)swd;
+        rho[j] = 0.f; mu[j] = 0.f;
+        if (grp == 0) {
+            const int ql = j * TQ + qtid;
+            s_qs[ql] = qsf; s_sw[ql] = swd; s_In[ql] = Iv;
+            double w = swd * swd;
+            v3[0] += w; v3[1] += w * Iv; v3[2] += w * Iv * Iv;
+        }
+    }
+
+    // Sum three per-thread partials over the whole cluster (fixed order; all threads call it)
+    int abuf = 0;
+    auto cluster_allsum3 = [&](double (&v)[3]) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) v[i] = warp_sum(v[i]);
+        if (lane == 0) { s_asum[warp * 3] = v[0]; s_asum[warp * 3 + 1] = v[1]; s_asum[warp * 3 + 2] = v[2]; }
+        __syncthreads();
+        double *part = s_apart + (size_t)abuf * MAX_CLUSTER * 3;
+        if (tid < 3) {
+            double x = 0.;
+            for (int wv = 0; wv <= W; ++wv) x += s_asum[wv * 3 + tid];
+            if (C > 1) { for (int r = 0; r < C; ++r) dsmem_store(part + rank * 3 + tid, (uint32_t)r, x); }
+            else part[tid] = x;
+        }
+        if (C > 1) cluster_sync_all(); else __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            double x = 0.;
+            for (int r = 0; r < C; ++r) x += part[r * 3 + i];
+            v[i] = x;
+        }
+        abuf ^= 1;
+    };
+
+    cluster_allsum3(v3);
+    LsqConst L;
+    L.S = v3[0]; L.Si = v3[1]; L.Sii = v3[2];
+    L.inv_nq = 1. / (double)nq;
+    L.find_bg = a.find_bg; L.pos_bg = a.pos_bg;
+
+    // ---- fp32 amplitude scale G: 1 / amplitude at the upper end of the active ranges ------
+    double G = 1.;
+    {
+        if (tid == 0) {
+            PVec p(a.mp, a.mp.hi);
+            Contrib<float> tmp;
+            VWS o = O::template prep<false>(p, a.comp_exp, 1., qt, tmp, s_nodes);
+            double g = 1. / o.amp_raw;
+            if (!(g > 0.) || isinf(g)) g = 1.;
+            s_chi[0] = g;
+        }
+        __syncthreads();
+        G = s_chi[0];
+        __syncthreads();
+    }
+
+    // exact fp64 fit of the resident ft over the cluster (initial and final fit)
+    auto lsq_all = [&](double &sa, double &sb, double &chi) {
+        double v[3] = {0., 0., 0.};
+        if (grp == 0) {
+#pragma unroll
+            for (int j = 0; j < QPT; ++j) {
+                const int ql = j * TQ + qtid;
+                const double f = s_ft[cur * FAST_QCAP + ql], sq = s_sw[ql];
+                double w = sq * sq, t = w * f;
+                v[0] += t; v[1] = fma(t, f, v[1]); v[2] = fma(t, s_In[ql], v[2]);
+            }
+        }
+        cluster_allsum3(v);
+        lsq_solve(L, v[0], v[1], v[2], sa, sb, chi);
+        double r2[3] = {0., 0., 0.};                             // residual form (:73-77,:135)
+        if (grp == 0) {
+#pragma unroll
+            for (int j = 0; j < QPT; ++j) {
+                const int ql = j * TQ + qtid;
+                double r = s_sw[ql] * (s_In[ql] - (s_ft[cur * FAST_QCAP + ql] * sa + sb));
+                r2[0] = fma(r, r, r2[0]);
+            }
+        }
+        cluster_allsum3(r2);
+        chi = r2[0] * L.inv_nq;
+    };
+
+    auto fill_entry = [&](long long t, int attempt, long long sbase) {
+        const int e = (int)t & (RING - 1);                       // RING is a power of two
+        RingEntry<float> &E = s_ring[e];
+        uint32_t o4[4];
+        if (!a.stream) philox4x32_10(a.seed, (uint64_t)t, gchain, 2u * attempt, o4);
+#pragma unroll
+        for (int k = 0; k < MCSAS_MAX_ACTIVE; ++k) {
+            if (k < P) {
+                double u = a.stream ? a.stream[sbase + t * P + k]
+                                    : generator_output(o4[k], a.mp.gen_kind[k]);
+                E.prop[k] = u * (a.mp.hi[k] - a.mp.lo[k]) + a.mp.lo[k];  // mcsas.py:358
+            }
+        }
+        PVec pn(a.mp, E.prop);
+        FO::prep(pn, a.comp_exp, G, qref, qt, E.cn, s_nodes + (size_t)(e * 2) * NSTR);
+        PVec po(a.mp, s_rset + (int)((uint32_t)t % (uint32_t)N) * P);   // max_iter < 2^31 (host)
+        FO::prep(po, a.comp_exp, G, qref, qt, E.co, s_nodes + (size_t)(e * 2 + 1) * NSTR);
+    };
+
+    const unsigned long long t_start = globaltimer_ns();
+    long long step = 0, moves = 0, evals = 0, steps_all = 0;
+    double conval = 0., conval0 = 0., sc_a = 1., sc_b = 0.;
+    int attempt = 0, status = 1;
+    bool resume = a.resume != 0 && a.status[chain] == 0;
+    if (a.resume) {
+        evals = a.evals[chain]; steps_all = a.steps_all[chain];
+        attempt = a.attempts[chain] - 1;
+        if (resume) { step = a.num_iter[chain]; moves = a.num_moves[chain]; conval0 = a.conval0[chain]; }
+    }
+    const long long slice_end = a.slice_steps > 0 ? step + a.slice_steps : (1LL << 62);
+
+    for (;; ++attempt) {
+        // ---- contribution set: fresh draws (mcsas.py:310-317) or saved state ---------------
+        for (int i = tid; i < N; i += blockDim.x) {
+            uint32_t o4[4];
+            if (!resume && !a.start_min && !a.stream)
+                philox4x32_10(a.seed, (uint64_t)i, gchain, 2u * attempt + 1u, o4);
+            for (int k = 0; k < P; ++k) {
+                double lo = a.mp.lo[k], hi = a.mp.hi[k], val;
+                if (resume) {
+                    val = a.rset[((long long)chain * N + i) * P + k];
+                } else if (a.start_min) {
+                    double mb = lo < hi ? lo : hi;
+                    if (mb == 0.) mb = M_PI / ds.q_max;
+                    val = 1. * mb * .5;
+                } else {
+                    double u = a.stream ? a.stream[(long long)chain * a.stream_stride + (long long)k * N + i]
+                                        : generator_output(o4[k], a.mp.gen_kind[k]);
+                    val = u * (hi - lo) + lo;                    // parameter.py:83-84
+                }
+                s_rset[i * P + k] = val;
+            }
+        }
+        double ft0[QPT];
+#pragma unroll
+        for (int j = 0; j < QPT; ++j) ft0[j] = 0.;
+        cur = 0;
+        __syncthreads();
+        // ---- ft = sum of all contributions, in contribution order (mcsas.py:319) -----------
+        for (int i0 = 0; i0 < N; i0 += RING) {
+            int nb = min(RING, N - i0);
+            for (int e = tid; e < nb; e += blockDim.x) {
+                PVec p(a.mp, s_rset + (i0 + e) * P);
+                FO::prep(p, a.comp_exp, G, qref, qt, s_ring[e].co, s_nodes + (size_t)(e * 2 + 1) * NSTR);
+            }
+            __syncthreads();
+            if (!producer) {
+                for (int e = 0; e < nb; ++e) {
+                    const Contrib<float> cc = s_ring[e].co;
+                    const float *nd = s_nodes + (size_t)(e * 2 + 1) * NSTR;
+#pragma unroll
+                    for (int j = 0; j < QPT; ++j)
+                        ft0[j] += (double)FO::evalS(cc, nd, qt, Q[j]) * (double)s_qs[j * TQ + qtid];
+                }
+            }
+            __syncthreads();
+        }
+        evals += N;
+        if (grp == 0) {
+#pragma unroll
+            for (int j = 0; j < QPT; ++j) s_ft[j * TQ + qtid] = ft0[j];
+        }
+        lsq_all(sc_a, sc_b, conval);                             // mcsas.py:339-344
+        if (!resume) { conval0 = conval; step = 0; moves = 0; }
+        resume = false;
+        // centre of the quadratic expansion = this fit; residual / model in units of sigma
+        double a0 = sc_a, b0 = sc_b;
+#pragma unroll
+        for (int j = 0; j < QPT; ++j) {
+            const int ql = j * TQ + qtid;
+            const double sq = producer ? 0. : s_sw[ql];
+            rho[j] = (float)(sq * (s_In[ql] - (a0 * ft0[j] + b0)));
+            mu[j] = (float)(sq * ft0[j]);
+        }
+        bool dirty = true;                                       // base sums not yet accumulated
+        const long long sbase = (long long)chain * a.stream_stride + (a.start_min ? 0 : (long long)N * P);
+        // ---- first ring fill: steps [step, step + RING) -------------------------------------
+        {
+            long long target = min(step + (long long)RING, a.max_iter);
+            for (long long t = step + tid; t < target; t += blockDim.x) fill_entry(t, attempt, sbase);
+            if (tid == 0) {
+                s_ctrl->step = step; s_ctrl->filled = target; s_ctrl->batch = 0;
+                s_ctrl->done = !(N > 1 && conval > a.conv_crit && step < a.max_iter && step < slice_end);
+            }
+        }
+        __syncthreads();
+        int K = max(1, kmax / 2);
+        int batch = 0;
+        const int wd_batches = (int)min((long long)0x3fffffff, 2 * (min(a.max_iter, slice_end) - step) + 64);
+
+        if (producer) {
+            long long filled = s_ctrl->filled;
+            for (;;) {
+                const long long pstep = ld_volatile(&s_ctrl->step);
+                const int pdone = ld_volatile_i(&s_ctrl->done);
+                __threadfence_block();
+                if (pdone) { step = ld_volatile(&s_ctrl->step); if (pdone == 2) status = -2; break; }
+                const long long target = min(pstep + (long long)RING, a.max_iter);
+                if (filled < target) {
+                    for (long long t = filled + lane; t < target; t += 32) fill_entry(t, attempt, sbase);
+                    __syncwarp();
+                    __threadfence_block();
+                    filled = target;
+                    if (lane == 0) st_volatile(&s_ctrl->filled, filled);
+                } else {
+                    __nanosleep(64);
+                }
+            }
+        } else {
+        // ---- the MC loop (mcsas.py:354-404), Kb speculative steps per batch ------------------
+        FastBase B;                                              // meaningful in warp 0 only
+        B.S = L.S; B.Sm = 0.; B.Smm = 0.; B.E0 = 0.; B.E1 = 0.; B.E2 = 0.; B.a0 = a0; B.b0 = b0;
+        for (;;) {
+            if (ld_volatile_i(&s_ctrl->done)) {
+                if (s_ctrl->done == 2) status = -2;
+                break;
+            }
+            int Kb = min(K, kmax);
+            {
+                long long rem = a.max_iter - step;
+                if (rem < Kb) Kb = rem >= 1 ? (1 << (31 - __clz((int)rem))) : 0;   // power of two
+            }
+            ++batch;
+            bool wd = Kb < 1 || batch > wd_batches;
+            if (!wd) {
+                int spins = 0;
+                while (ld_volatile(&s_ctrl->filled) < step + Kb) {
+                    if (++spins > (1 << 24)) { wd = true; break; }
+                    __nanosleep(32);
+                }
+                __threadfence_block();
+            }
+            wd = __any_sync(0xffffffffu, wd);
+            // ---- exact base sums of the current state (after an accepted move) ---------------
+            if (dirty && grp == 0) {
+                double b5[5] = {0., 0., 0., 0., 0.};
+#pragma unroll
+                for (int j = 0; j < QPT; ++j) {
+                    const int ql = j * TQ + qtid;
+                    const double sq = s_sw[ql];
+                    double m = sq * s_ft[cur * FAST_QCAP + ql];
+                    double r = sq * s_In[ql] - (a0 * m + b0 * sq);
+                    b5[0] = fma(r, r, b5[0]);                    // E0 = sum w e^2
+                    b5[1] = fma(r, m, b5[1]);                    // E1 = sum w e ft
+                    b5[2] = fma(r, sq, b5[2]);                   // E2 = sum w e
+                    b5[3] = fma(m, sq, b5[3]);                   // Sm
+                    b5[4] = fma(m, m, b5[4]);                    // Smm
+                }
+#pragma unroll
+                for (int i = 0; i < 5; ++i) b5[i] = warp_sum(b5[i]);
+                if (lane < 5) {
+                    double x = b5[0];
+                    if (lane == 1) x = b5[1];
+                    if (lane == 2) x = b5[2];
+                    if (lane == 3) x = b5[3];
+                    if (lane == 4) x = b5[4];
+                    s_bsum[wq * 6 + lane] = x;
+                }
+            }
+            // ---- evaluate the batch ---------------------------------------------------------
+            if (!wd) {
+                if (Kb >= FGRP) {
+                    const int perm = grp_perm<FGRP>(lane);
+                    const int e0 = (int)step & (RING - 1);
+                    for (int k0 = grp * FGRP; k0 < Kb; k0 += PS * FGRP) {
+                        float acc[FGRP][4];
+#pragma unroll
+                        for (int s = 0; s < FGRP; ++s) {
+                            acc[s][0] = 0.f; acc[s][1] = 0.f; acc[s][2] = 0.f; acc[s][3] = 0.f;
+                            const int k = k0 + (s ^ perm);
+                            const int e = (e0 + k) & (RING - 1);
+                            const Contrib<float> cn = s_ring[e].cn, co = s_ring[e].co;
+                            const float *nn = s_nodes + (size_t)(e * 2) * NSTR, *no = nn + NSTR;
+                            float dd[QPT];
+                            FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd);  // mcsas.py:360-362
+#pragma unroll
+                            for (int j = 0; j < QPT; ++j) {
+                                float u = cq[j] * dd[j];                     // (new - old)/sigma, :366
+                                acc[s][0] = fmaf(rho[j], u, acc[s][0]);
+                                acc[s][1] = fmaf(u, u, acc[s][1]);
+                                acc[s][2] = fmaf(mu[j], u, acc[s][2]);
+                                acc[s][3] = fmaf(om[j], u, acc[s][3]);
+                            }
+                        }
+                        // select-free reduce-scatter: slot s of lane l holds proposal s ^ perm(l)
+#pragma unroll
+                        for (int h = FGRP / 2, off = 16; h >= 1; h >>= 1, off >>= 1) {
+#pragma unroll
+                            for (int s = 0; s < h; ++s)
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+                                    acc[s][i] += __shfl_xor_sync(0xffffffffu, acc[s + h][i], off);
+                        }
+#pragma unroll
+                        for (int off = 32 / FGRP / 2; off >= 1; off >>= 1)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                acc[0][i] += __shfl_xor_sync(0xffffffffu, acc[0][i], off);
+                        if ((lane & (32 / FGRP - 1)) == 0)
+                            s_wsum[wq * KCAP + k0 + perm] = make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
+                    }
+                } else if (grp == 0) {
+                    for (int k = 0; k < Kb; ++k) {
+                        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                        const int e = ((int)step + k) & (RING - 1);
+                        const Contrib<float> cn = s_ring[e].cn, co = s_ring[e].co;
+                        const float *nn = s_nodes + (size_t)(e * 2) * NSTR, *no = nn + NSTR;
+                        float dd[QPT];
+                        FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd);
+#pragma unroll
+                        for (int j = 0; j < QPT; ++j) {
+                            float u = cq[j] * dd[j];
+                            acc[0] = fmaf(rho[j], u, acc[0]);
+                            acc[1] = fmaf(u, u, acc[1]);
+                            acc[2] = fmaf(mu[j], u, acc[2]);
+                            acc[3] = fmaf(om[j], u, acc[3]);
+                        }
+#pragma unroll
+                        for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+                        if (lane == 0) s_wsum[wq * KCAP + k] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                    }
+                }
+            }
+            if (wd && lane == 0) s_dec->wd = 1;                  // any warp may raise it
+            named_bar_sync(1, T);                                // B1: eval warps only
+            if (tid == 0) { __threadfence_block(); st_volatile(&s_ctrl->step, step); }
+            wd = s_dec->wd != 0;
+            // ---- exchange the partial sums over the cluster (st.async + mbarrier) -------------
+            double *part = s_part + (size_t)abuf * MAX_CLUSTER * XU;
+            const int nb5 = dirty ? 5 : 0;
+            if (C > 1) {
+                const int nprop = 2 * Kb, nval = nprop + nb5 + 1;
+                if (tid == 0) mbar_expect_tx(s_xbar + abuf, (uint32_t)(C * nval * 8));
+                for (int i = tid; i < nval; i += T) {
+                    double x;
+                    if (i < nprop) {                             // two floats of proposal i/2
+                        const float *src = (const float *)s_wsum + (size_t)(i >> 1) * 4 + (i & 1) * 2;
+                        float x0 = 0.f, x1 = 0.f;
+                        for (int wv = 0; wv < WQ; ++wv) { x0 += src[(size_t)wv * KCAP * 4]; x1 += src[(size_t)wv * KCAP * 4 + 1]; }
+                        x = __hiloint2double(__float_as_int(x1), __float_as_int(x0));
+                    } else if (i < nprop + nb5) {
+                        x = 0.;
+                        for (int wv = 0; wv < WQ; ++wv) x += s_bsum[wv * 6 + (i - nprop)];
+                    } else x = wd ? 1. : 0.;
+                    double *dst = part + (size_t)rank * XU + (i < nprop ? i : 2 * KCAP + (i - nprop));
+                    for (int r = 0; r < C; ++r) dsmem_store_async(dst, s_xbar + abuf, (uint32_t)r, x);
+                }
+                if (warp == 0) {
+                    mbar_wait(s_xbar + abuf, (xphase >> abuf) & 1);
+                    bool anywd = false;
+                    for (int r = 0; r < C; ++r) anywd |= part[(size_t)r * XU + 2 * KCAP + nb5] != 0.;
+                    wd = anywd;
+                }
+                xphase ^= 1u << abuf;
+            }
+            if (warp == 0) {
+                if (dirty) {                                     // fresh base sums (identical in all lanes)
+                    double b5[5] = {0., 0., 0., 0., 0.};
+                    if (C > 1) {
+                        for (int r = 0; r < C; ++r)
+#pragma unroll
+                            for (int i = 0; i < 5; ++i) b5[i] += part[(size_t)r * XU + 2 * KCAP + i];
+                    } else {
+                        for (int wv = 0; wv < WQ; ++wv)
+#pragma unroll
+                            for (int i = 0; i < 5; ++i) b5[i] += s_bsum[wv * 6 + i];
+                    }
+                    B.E0 = b5[0]; B.E1 = b5[1]; B.E2 = b5[2]; B.Sm = b5[3]; B.Smm = b5[4];
+                    B.a0 = a0; B.b0 = b0;
+                    double rss, an, bn;
+                    fast_solve(B, L.find_bg, L.pos_bg, 0., 0., 0., 0., rss, an, bn);
+                    conval = rss * L.inv_nq;                     // exact chi2 of the current state
+                    sc_a = an; sc_b = bn;
+                }
+                double chi = 0., an = 0., bn = 0.;
+                bool better = false;
+                if (lane < Kb && !wd) {
+                    double s1 = 0., s2 = 0., s3 = 0., s4 = 0.;
+                    if (C > 1) {
+                        for (int r = 0; r < C; ++r) {
+                            const float4 x = *(const float4 *)(part + (size_t)r * XU + 2 * lane);
+                            s1 += (double)x.x; s2 += (double)x.y; s3 += (double)x.z; s4 += (double)x.w;
+                        }
+                    } else {
+                        float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int wv = 0; wv < WQ; ++wv) {
+                            const float4 x = s_wsum[wv * KCAP + lane];
+                            t4.x += x.x; t4.y += x.y; t4.z += x.z; t4.w += x.w;
+                        }
+                        s1 = t4.x; s2 = t4.y; s3 = t4.z; s4 = t4.w;
+                    }
+                    double rss;
+                    fast_solve(B, L.find_bg, L.pos_bg, s1, s2, s3, s4, rss, an, bn);   // mcsas.py:376
+                    chi = rss * L.inv_nq;
+                    better = chi < conval;                       // :379 strict
+                    s_chi[lane] = chi;
+                }
+                unsigned mask = __ballot_sync(0xffffffffu, better);
+                const int ks = mask ? (__ffs(mask) - 1) : -1;
+                const int src = ks >= 0 ? ks : 0;
+                const double ca = __shfl_sync(0xffffffffu, an, src), cb = __shfl_sync(0xffffffffu, bn, src);
+                const double cc = __shfl_sync(0xffffffffu, chi, src);
+                if (lane == 0) {
+                    s_dec->kstar = ks;
+                    s_dec->wd = wd ? 2 : 0;
+                    s_dec->a = ks >= 0 ? ca : sc_a;              // accepted: new centre; else the exact fit
+                    s_dec->b = ks >= 0 ? cb : sc_b;
+                    s_dec->conval = ks >= 0 ? cc : conval;
+                }
+            }
+            abuf ^= 1;
+            named_bar_sync(1, T);                                // B2
+            if (s_dec->wd == 2) {
+                if (tid == 0) { st_volatile(&s_ctrl->step, step); __threadfence_block(); st_volatile_i(&s_ctrl->done, 2); }
+                status = -2;
+                break;
+            }
+            const int kstar = s_dec->kstar;
+            const int used = kstar >= 0 ? kstar + 1 : Kb;
+            conval = s_dec->conval;
+            if (a.trace_accept && rank == 0) {
+                for (int k = tid; k < used; k += T) {
+                    a.trace_accept[(long long)chain * a.max_iter + step + k] = (k == kstar);
+                    a.trace_chi[(long long)chain * a.max_iter + step + k] = s_chi[k];
+                }
+            }
+            dirty = false;
+            if (kstar >= 0) {                                    // mcsas.py:381-384
+                a0 = s_dec->a; b0 = s_dec->b;
+                sc_a = a0; sc_b = b0;
+                const int e = ((int)step + kstar) & (RING - 1);
+                const Contrib<float> cn = s_ring[e].cn, co = s_ring[e].co;
+                const float *nn = s_nodes + (size_t)(e * 2) * NSTR, *no = nn + NSTR;
+                float dd[QPT];
+                FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd);
+#pragma unroll
+                for (int j = 0; j < QPT; ++j) {
+                    const int ql = j * TQ + qtid;
+                    const double f = s_ft[cur * FAST_QCAP + ql] + (double)dd[j] * (double)s_qs[ql];
+                    const double sq = s_sw[ql];
+                    if (grp == 0) s_ft[(cur ^ 1) * FAST_QCAP + ql] = f;      // other groups still read `cur`
+                    rho[j] = (float)(sq * (s_In[ql] - (a0 * f + b0)));
+                    mu[j] = (float)(sq * f);
+                }
+                cur ^= 1;
+                const int rix = (int)((uint32_t)(step + kstar) % (uint32_t)N);
+                if (tid < P) s_rset[rix * P + tid] = s_ring[e].prop[tid];
+                ++moves;
+                evals += 2;
+                dirty = true;
+                K = max(1, min(kmax, 1 << (31 - __clz(kstar + 1))));
+            } else {
+                sc_a = s_dec->a; sc_b = s_dec->b;
+                K = min(kmax, K * 2);
+            }
+            evals += 2 * Kb;
+            step += used;                                        // :403-404 (ri = step % N)
+            steps_all += used;
+            if (!(conval > a.conv_crit && step < a.max_iter && step < slice_end)) {
+                if (tid == 0) {
+                    st_volatile(&s_ctrl->step, step);
+                    __threadfence_block();
+                    st_volatile_i(&s_ctrl->done, 1);
+                }
+                break;
+            }
+        }
+        }
+        __syncthreads();                                         // eval warps and producer rejoin
+        step = s_ctrl->step;
+        if (producer) { conval = 0.; }
+        // ---- final fit of the accepted state (mcsas.py:424-425) --------------------------------
+        lsq_all(sc_a, sc_b, conval);
+        if (status == -2) break;
+        const bool running = (N > 1 && conval > a.conv_crit && step < a.max_iter);
+        if (running) { status = 0; break; }                      // slice ended: resume later
+        status = 1;
+        if (conval <= a.conv_crit || a.stream || attempt + 1 >= a.max_attempts || N <= 1)
+            break;
+        if (a.slice_steps > 0) {                                 // retry (mcsas.py:220-246) in a later slice
+            status = 2; ++attempt; step = 0; moves = 0;
+            break;
+        }
+        __syncthreads();
+    }
+
+    // ---- results / saved state ---------------------------------------------------------------
+    if (rank == 0)
+        for (int i = tid; i < N * P; i += blockDim.x) a.rset[(long long)chain * N * P + i] = s_rset[i];
+    if (grp == 0) {
+#pragma unroll
+        for (int j = 0; j < QPT; ++j) {
+            int i = (j * C + rank) * TQ + qtid;
+            if (i < nq)
+                a.fit_meas[(long long)chain * a.nq_stride + i] =
+                    (s_ft[cur * FAST_QCAP + j * TQ + qtid] * sc_a + sc_b) * ds.i_scale;                 // mcsas.py:429
+        }
+    }
+    if (tid == 0 && rank == 0) {
+        // internal model = (reference model) * G / i_scale-normalised data: undo both
+        a.scaling[chain] = sc_a * G * ds.i_scale;
+        a.background[chain] = sc_b * ds.i_scale;
+        a.conval[chain] = conval;
+        a.conval0[chain] = conval0;
+        a.num_iter[chain] = step;
+        a.num_moves[chain] = moves;
+        a.evals[chain] = evals;
+        a.steps_all[chain] = steps_all;
+        a.attempts[chain] = attempt + 1;
+        a.elapsed_s[chain] = (a.resume ? a.elapsed_s[chain] : 0.) + 1e-9 * (double)(globaltimer_ns() - t_start);
+        a.status[chain] = status;
+    }
+    if (C > 1) cluster_sync_all();
+}

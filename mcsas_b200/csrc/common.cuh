@@ -30,6 +30,8 @@ struct DatasetDesc {
     int nq;
     int nq_pad;
     double q_max;       // data.x0.limit[1] (mcsas.py:313)
+    double q_ref;       // sqrt(q_min q_max): centre of the fp32 kernel's per-q scale factors
+    double i_scale;     // max |I|: the fp32 kernel normalises I and sigma by it
 };
 
 struct ChainArgs {
@@ -46,6 +48,7 @@ struct ChainArgs {
     int spec_max;                // max speculative proposals per batch (<= ring / 4)
     int ring;                    // ring entries = min(RING_MAX, n_contribs)
     int cluster;                 // CTAs per chain (q split)
+    int warps_q;                 // fp32 kernel: warps covering one CTA's q slice (eval warps = warps_q * groups)
     int resume;                  // 1: continue from the saved state (rset, counters)
     long long slice_steps;       // MC steps per chain in this launch, 0 = run to the end
     const int *chain_ids;        // chains of this launch (grid = n * cluster) or NULL
@@ -116,5 +119,29 @@ __host__ __device__ inline size_t chain_smem_bytes(int nq_pad, int N, int P, int
     s += MCSAS_AL16(real * (size_t)ring * 2 * narr * D) + 16;            // node arrays
     return s;
 #undef MCSAS_AL16
+}
+
+// ---- shared-memory footprint of chain_fast_kernel (mirrors its carve-up) -----------------------------
+#define FAST_MAX_WARPS 31
+#define FAST_QCAP 1024            // q points per CTA (QPT * 32 * warps_q)
+__host__ __device__ inline size_t fast_smem_bytes(int nq_pad, int N, int P, int D, int narr, int ring)
+{
+#define AL16(b) ((((size_t)(b)) + 15) & ~size_t(15))
+    size_t s = 16;                                               // mbarrier
+    s += AL16(8 * 3 * (size_t)nq_pad);                           // data staging
+    s += AL16(8 * (size_t)N * (P > 0 ? P : 1));                  // rset
+    s += AL16(64);                                               // ctrl
+    s += AL16((size_t)ring * (8 * MCSAS_MAX_ACTIVE + 2 * 4 * 8));// ring entries
+    s += AL16(16 * (size_t)FAST_MAX_WARPS * KCAP);               // per-warp proposal sums (float4)
+    s += AL16(8 * (size_t)(FAST_MAX_WARPS + 1) * 6);             // per-warp base sums
+    s += AL16(8 * 2 * (size_t)MAX_CLUSTER * (2 * KCAP + 8));     // cluster exchange, 2 buffers
+    s += 16;                                                     // exchange mbarriers
+    s += AL16(8 * (size_t)KCAP + 128);                           // chi per proposal + decision
+    s += AL16(8 * (size_t)(FAST_MAX_WARPS + 2) * 3 + 8 * 2 * MAX_CLUSTER * 3);   // full-LSQ all-sum
+    s += AL16(8 * 2 * FAST_QCAP) + 2 * AL16(8 * FAST_QCAP) + AL16(4 * FAST_QCAP);   // ft (x2), I, 1/sigma, q scale
+    s += 2 * AL16(4 * (size_t)(D + 1));                          // quadrature table
+    s += AL16(4 * (size_t)ring * 2 * narr * D) + 16;             // node arrays
+    return s;
+#undef AL16
 }
 

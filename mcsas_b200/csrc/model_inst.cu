@@ -1,6 +1,6 @@
 // model_inst.cu -- compiled once per model with -DMODEL_ID=<n>: instantiates the chain
 // and eval kernels of that model for both precisions and all thread layouts.
-#include "chain_kernel.cuh"
+#include "chain_fast.cuh"
 #include "launch.cuh"
 
 #ifndef MODEL_ID
@@ -9,11 +9,19 @@
 #define CAT2(a, b) a##b
 #define CAT(a, b) CAT2(a, b)
 
+// kernel of one (precision, layout): fp64 -> parity kernel, fp32 -> production kernel
+template <class Real, int QPT> struct KernelOf {
+    static auto get() { return chain_kernel<MODEL_ID, Real, QPT>; }
+};
+template <int QPT> struct KernelOf<float, QPT> {
+    static auto get() { return chain_fast_kernel<MODEL_ID, QPT>; }
+};
+
 template <class Real, int QPT>
 static cudaError_t launch_one(int grid, int threads, size_t smem, cudaStream_t st,
                               const ChainArgs &a)
 {
-    auto k = chain_kernel<MODEL_ID, Real, QPT>;
+    auto k = KernelOf<Real, QPT>::get();
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
@@ -34,7 +42,7 @@ static cudaError_t launch_one(int grid, int threads, size_t smem, cudaStream_t s
 template <class Real, int QPT>
 static cudaError_t query_one(int threads, size_t smem, int cluster, int *max_clusters, int *regs)
 {
-    auto k = chain_kernel<MODEL_ID, Real, QPT>;
+    auto k = KernelOf<Real, QPT>::get();
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaFuncAttributes fa;

@@ -10,7 +10,7 @@ eng = Engine(0)
 eng.upload_datasets([(q, I, sig)])
 eng.set_model(0, [10e-9, 1e14], [0], [1e-9], [100e-9], [0])
 cfg = Engine.make_config(n_contribs=300, n_reps=reps, precision=FP32, seed=5, max_iter=int(os.environ.get("TUNE_MAXIT", "4096")),
-                         conv_crit=0.0, max_retries=-1, slice_steps=-1)
+                         conv_crit=0.0, max_retries=-1, slice_steps=int(os.environ.get("TUNE_SLICE", "-1")))
 ms = eng.run(cfg)
 r = eng.fetch()
 print("kernel ms", ms, "steps", int(r["num_iter"].sum()), "steps/s %.3e" % (r["num_iter"].sum() / ms * 1e3), eng.run_info())

@@ -57,6 +57,12 @@ if __name__ == "__main__":
     if "slice" in which:
         for sl in (2048, 4096, 16384, 65536, 1000000):
             run("auto slice=%d" % sl, {"MCSAS_B200_SLICE": str(sl)})
+    if "fast" in which:
+        for c in (1, 2, 4, 8):
+            for qpt in (1, 2, 4):
+                for ps in (1, 2, 4):
+                    run("cluster=%d qpt=%d ps=%d" % (c, qpt, ps), {"MCSAS_B200_CLUSTER": str(c), "MCSAS_B200_QPT": str(qpt),
+                                                               "MCSAS_B200_PS": str(ps)}, seeds=(1,))
     if "ct" in which:
         for c in (1, 2, 4, 8):
             for t in (64, 128, 256):
