@@ -66,6 +66,9 @@ struct mcsas_ctx {
     int forced_cluster = 0;
     std::vector<int> h_ids;
     int *d_ids = nullptr;
+    long long *d_prof = nullptr;
+    float *d_cache = nullptr;
+    size_t cache_cap = 0;
     int n_live = 0, n_launches = 0, last_cluster = 1, last_threads = 0, last_qpt = 0, last_resident = 0;
     float kernel_ms = 0.f;
     volatile int *stop_flag = nullptr;
@@ -128,7 +131,7 @@ extern "C" void mcsas_ctx_destroy(mcsas_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_sets); cudaFree(ctx->d_data); cudaFree(ctx->d_quad); cudaFree(ctx->d_stream);
     cudaFree(ctx->d_rset); cudaFree(ctx->d_fit); cudaFree(ctx->d_scal); cudaFree(ctx->d_cnt);
-    cudaFree(ctx->d_att); cudaFree(ctx->d_tacc); cudaFree(ctx->d_tchi); cudaFree(ctx->d_ids);
+    cudaFree(ctx->d_att); cudaFree(ctx->d_tacc); cudaFree(ctx->d_tchi); cudaFree(ctx->d_ids); cudaFree(ctx->d_prof); cudaFree(ctx->d_cache);
     cudaFreeHost(ctx->h_stop);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -444,7 +447,7 @@ static int plan_chain_fp32(mcsas_ctx *ctx, int nq, int n_live, ChainPlan *out)
             const int threads = wq * ps * 32;
             if (threads > FAST_MAX_EVAL_THREADS[l] || threads / 32 > FAST_MAX_WARPS) continue;
             int resident = 0;
-            query_resident(ctx, c, l, threads + 32, &resident);
+            query_resident(ctx, c, l, threads, &resident);
             if (resident < 1) continue;
             if (resident < n_live && forced_c <= 0 && oi + 1 < no) continue;       // prefer one wave
             best.cluster = c; best.layout = l; best.threads = threads; best.resident = resident; best.warps_q = wq;
@@ -478,7 +481,8 @@ static int launch_slice(mcsas_ctx *ctx, int n_live, bool resume)
         a.chain_ids = ctx->d_ids;
     }
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    cudaError_t e = CHAIN_FN[a.mp.model_id](ctx->precision, pl.layout, n_live * pl.cluster, pl.threads + 32,
+    cudaError_t e = CHAIN_FN[a.mp.model_id](ctx->precision, pl.layout, n_live * pl.cluster,
+                                            pl.threads + (ctx->precision == MCSAS_FP64 ? 32 : 0),   // fp64: + producer warp
                                             ctx->smem, ctx->stream, a);
     if (e != cudaSuccess) return fail(ctx, MCSAS_ERR_CUDA, "chain kernel launch: %s", cudaGetErrorString(e));
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -574,6 +578,10 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     a.find_bg = cfg->find_background != 0; a.pos_bg = cfg->positive_background != 0;
     a.start_min = cfg->start_from_minimum != 0;
     a.spec_max = kcap; a.ring = ring;
+    {
+        const char *ge = getenv("MCSAS_B200_GRAM");
+        a.gram = ge ? atoi(ge) != 0 : 1;
+    }
     a.first_chain = cfg->first_chain; a.record_trace = cfg->record_trace;
     a.seed = cfg->seed;
     // time slicing: deterministic (uploaded stream / traced) runs are one launch
@@ -593,6 +601,24 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     a.attempts = ctx->d_att; a.status = ctx->d_att + n_chains;
     a.trace_accept = cfg->record_trace ? ctx->d_tacc : nullptr;
     a.trace_chi = cfg->record_trace ? ctx->d_tchi : nullptr;
+    a.cache = nullptr;
+    if (cfg->precision == MCSAS_FP32 && !(getenv("MCSAS_B200_CACHE") && atoi(getenv("MCSAS_B200_CACHE")) == 0)) {
+        // contribution-row cache: one row of padded q points per contribution and chain slot
+        const size_t stride = (size_t)N * ((size_t)ctx->nq_max + 128 * MAX_CLUSTER);
+        const size_t need = stride * (size_t)n_chains;
+        if (need * sizeof(float) <= ((size_t)8 << 30)) {        // beyond 8 GB: recompute instead
+            if (need > ctx->cache_cap) { CK(regrow(&ctx->d_cache, need)); ctx->cache_cap = need; }
+            a.cache = ctx->d_cache;
+            a.cache_stride = (long long)stride;
+        }
+    }
+    if (getenv("MCSAS_B200_PROF") && cfg->precision == MCSAS_FP32) {
+        cudaFree(ctx->d_prof);
+        ctx->d_prof = nullptr;
+        CK(cudaMalloc(&ctx->d_prof, sizeof(long long) * 32 * n_chains));
+        CK(cudaMemset(ctx->d_prof, 0, sizeof(long long) * 32 * n_chains));
+        a.prof = ctx->d_prof;
+    }
     ctx->args = a;
     ctx->precision = cfg->precision;
     ctx->smem = smem;
@@ -653,6 +679,25 @@ extern "C" int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms)
         if (n == 0 || stop) break;
         int rc = launch_slice(ctx, n, true);
         if (rc) return rc;
+    }
+    if (ctx->args.prof) {                                 // phase profile (experiments only)
+        std::vector<long long> h((size_t)32 * ctx->n_chains);
+        CK(cudaMemcpy(h.data(), ctx->args.prof, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+        static const char *nm[6] = {"ring-wait", "refresh+eval", "B1", "exchange+decide", "B2", "update"};
+        for (int m = 0; m < 2; ++m) {
+            long long tot[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int c = 0; c < ctx->n_chains; ++c)
+                for (int i = 0; i < 16; ++i) tot[i] += h[((size_t)c * 2 + m) * 16 + i];
+            if (!tot[6]) continue;
+            fprintf(stderr, "[mcsas_b200 prof] %s batches %lld steps %lld (%.1f steps/batch), cycles/batch:",
+                    m ? "GRAM" : "SPEC", tot[6], tot[7], (double)tot[7] / tot[6]);
+            double sum = 0.;
+            for (int i = 0; i < 6; ++i) { fprintf(stderr, " %s %.0f", nm[i], (double)tot[i] / tot[6]); sum += (double)tot[i] / tot[6]; }
+            fprintf(stderr, " | total %.0f = %.0f cycles/step\n", sum, sum * tot[6] / tot[7]);
+            fprintf(stderr, "[mcsas_b200 prof]    refresh %.0f/batch, first chunk %.0f (n %lld), later chunks %.0f each (n %lld)\n",
+                    (double)tot[8] / tot[6], tot[11] ? (double)tot[9] / tot[11] : 0., tot[11],
+                    tot[12] ? (double)tot[10] / tot[12] : 0., tot[12]);
+        }
     }
     if (kernel_ms) *kernel_ms = ctx->kernel_ms;
     ctx->have_run = true;

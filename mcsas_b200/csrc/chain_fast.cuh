@@ -37,6 +37,15 @@ template <int MODEL> struct FastOps {
     {
         return O::eval(cc, nodes, qt, Q);
     }
+    // scaled intensity of one contribution for the thread's q points
+    template <int QPT>
+    __device__ __forceinline__ static void evalN(const Contrib<float> &cc, const float *nodes,
+                                                 const QuadTab<float> &qt, const QRep<float> (&Q)[QPT],
+                                                 float (&d)[QPT])
+    {
+#pragma unroll
+        for (int j = 0; j < QPT; ++j) d[j] = evalS(cc, nodes, qt, Q[j]);
+    }
     // scaled intensity change of a proposal: D(new) - D(old) for the thread's q points
     template <int QPT>
     __device__ __forceinline__ static void diffS(const Contrib<float> &cn, const Contrib<float> &co,
@@ -48,20 +57,49 @@ template <int MODEL> struct FastOps {
     }
 };
 
-// g(x) = sin x - x cos x = x^3 F(x)/3   (sphere.py:62); SER: series below x = 1, where
-// s - x c cancels
-template <bool SER> __device__ __forceinline__ float sph_g(const QRep<float> &Q, float r)
+// g(x) = sin x - x cos x = x^3 F(x)/3 (sphere.py:62) for the M (q, radius) pairs of a
+// thread at once; SER: series below x = 1, where s - x c cancels.  Written stage by stage
+// over the M independent chains: ptxas keeps that order, which gives M-way instruction
+// level parallelism (an eval-by-eval formulation is scheduled serially, one dependent
+// instruction every ~5 cycles).
+template <int M, bool SER>
+__device__ __forceinline__ void sph_g_vec(const float (&q)[M], const float (&th)[M], const float (&tl)[M],
+                                          const float (&r)[M], float (&g)[M])
 {
-    float s, c, x;
-    sincos_qr(Q, r, s, c, x);
-    float g = fmaf(-x, c, s);
+    float x[M], t[M], fr[M], sn[M], cs[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) t[i] = fmaf(th[i], r[i], 12582912.f);     // rint(th r) for |t| < 2^22
+#pragma unroll
+    for (int i = 0; i < M; ++i) x[i] = q[i] * r[i];
+#pragma unroll
+    for (int i = 0; i < M; ++i) t[i] = t[i] - 12582912.f;
+#pragma unroll
+    for (int i = 0; i < M; ++i) fr[i] = fmaf(th[i], r[i], -t[i]);         // exact up to one rounding
+#pragma unroll
+    for (int i = 0; i < M; ++i) fr[i] = fmaf(tl[i], r[i], fr[i]);         // low part of q / (2 pi)
+#pragma unroll
+    for (int i = 0; i < M; ++i) fr[i] = fr[i] * 6.2831853071795865f;
+#pragma unroll
+    for (int i = 0; i < M; ++i) sn[i] = __sinf(fr[i]);
+#pragma unroll
+    for (int i = 0; i < M; ++i) cs[i] = __cosf(fr[i]);
+#pragma unroll
+    for (int i = 0; i < M; ++i) g[i] = fmaf(-x[i], cs[i], sn[i]);
     if (SER) {
-        float x2 = x * x;
-        float ser = (x * x2) * (0.33333333f + x2 * (-0.033333333f + x2 * (1.1904762e-3f
-                    + x2 * (-2.2045855e-5f + x2 * 2.5052108e-7f))));
-        g = x < 1.f ? ser : g;
+        float x2[M], p[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) x2[i] = x[i] * x[i];
+#pragma unroll
+        for (int i = 0; i < M; ++i) p[i] = fmaf(x2[i], 2.5052108e-7f, -2.2045855e-5f);
+#pragma unroll
+        for (int i = 0; i < M; ++i) p[i] = fmaf(x2[i], p[i], 1.1904762e-3f);
+#pragma unroll
+        for (int i = 0; i < M; ++i) p[i] = fmaf(x2[i], p[i], -0.033333333f);
+#pragma unroll
+        for (int i = 0; i < M; ++i) p[i] = fmaf(x2[i], p[i], 0.33333333f);
+#pragma unroll
+        for (int i = 0; i < M; ++i) g[i] = x[i] < 1.f ? (x[i] * x2[i]) * p[i] : g[i];
     }
-    return g;
 }
 
 template <> struct FastOps<MCSAS_SPHERE> {
@@ -79,48 +117,81 @@ template <> struct FastOps<MCSAS_SPHERE> {
     __device__ __forceinline__ static float evalS(const Contrib<float> &cc, const float *,
                                                   const QuadTab<float> &, const QRep<float> &Q)
     {
-        float g = sph_g<true>(Q, cc.c[0]);
-        return (g * g) * cc.c[1];
+        const float q[1] = {Q.q}, th[1] = {Q.th}, tl[1] = {Q.tl}, r[1] = {cc.c[0]};
+        float g[1];
+        sph_g_vec<1, true>(q, th, tl, r, g);
+        return (g[0] * g[0]) * cc.c[1];
     }
     // q ascends along the lanes, so "some x < 1" is warp-uniform for all but one warp per
     // radius: one vote per proposal selects the variant without the series.  Callers are
     // warp-convergent.
     template <int QPT>
+    __device__ __forceinline__ static void evalN(const Contrib<float> &cc, const float *, const QuadTab<float> &,
+                                                 const QRep<float> (&Q)[QPT], float (&d)[QPT])
+    {
+        float q[QPT], th[QPT], tl[QPT], r[QPT], g[QPT];
+        bool small = false;
+#pragma unroll
+        for (int j = 0; j < QPT; ++j) {
+            q[j] = Q[j].q; th[j] = Q[j].th; tl[j] = Q[j].tl; r[j] = cc.c[0];
+            small |= Q[j].q * cc.c[0] < 1.f;
+        }
+        if (__any_sync(0xffffffffu, small)) sph_g_vec<QPT, true>(q, th, tl, r, g);
+        else sph_g_vec<QPT, false>(q, th, tl, r, g);
+#pragma unroll
+        for (int j = 0; j < QPT; ++j) g[j] = g[j] * g[j];
+#pragma unroll
+        for (int j = 0; j < QPT; ++j) d[j] = g[j] * cc.c[1];
+    }
+    template <int QPT>
     __device__ __forceinline__ static void diffS(const Contrib<float> &cn, const Contrib<float> &co,
                                                  const float *, const float *, const QuadTab<float> &,
                                                  const QRep<float> (&Q)[QPT], float (&d)[QPT])
     {
+        float q[2 * QPT], th[2 * QPT], tl[2 * QPT], r[2 * QPT], g[2 * QPT];
         const float rmin = fminf(cn.c[0], co.c[0]);
         bool small = false;
 #pragma unroll
-        for (int j = 0; j < QPT; ++j) small |= Q[j].q * rmin < 1.f;
-        if (__any_sync(0xffffffffu, small)) {
-#pragma unroll
-            for (int j = 0; j < QPT; ++j) {
-                float gn = sph_g<true>(Q[j], cn.c[0]), go = sph_g<true>(Q[j], co.c[0]);
-                d[j] = fmaf(gn * gn, cn.c[1], -(go * go) * co.c[1]);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < QPT; ++j) {
-                float gn = sph_g<false>(Q[j], cn.c[0]), go = sph_g<false>(Q[j], co.c[0]);
-                d[j] = fmaf(gn * gn, cn.c[1], -(go * go) * co.c[1]);
-            }
+        for (int j = 0; j < QPT; ++j) {
+            q[j] = Q[j].q; th[j] = Q[j].th; tl[j] = Q[j].tl; r[j] = cn.c[0];
+            q[QPT + j] = Q[j].q; th[QPT + j] = Q[j].th; tl[QPT + j] = Q[j].tl; r[QPT + j] = co.c[0];
+            small |= Q[j].q * rmin < 1.f;
         }
+        if (__any_sync(0xffffffffu, small)) sph_g_vec<2 * QPT, true>(q, th, tl, r, g);
+        else sph_g_vec<2 * QPT, false>(q, th, tl, r, g);
+#pragma unroll
+        for (int j = 0; j < 2 * QPT; ++j) g[j] = g[j] * g[j];
+#pragma unroll
+        for (int j = 0; j < QPT; ++j) g[QPT + j] = g[QPT + j] * co.c[1];
+#pragma unroll
+        for (int j = 0; j < QPT; ++j) d[j] = fmaf(g[j], cn.c[1], -g[QPT + j]);
     }
 };
 
 struct FastDec {
     int kstar;
     int wd;
+    int accmask;
+    int pad_;
     double a, b, conval;
 };
+
+// index of the pair (t, s), t < s, in the packed upper triangle of an n x n matrix
+template <int NN> __host__ __device__ constexpr int tri_idx(int t, int s)
+{
+    return t < s ? t * NN - t * (t + 1) / 2 + (s - t - 1) : s * NN - s * (s + 1) / 2 + (t - s - 1);
+}
+__device__ __forceinline__ int tri_idx_rt(int n, int t, int s)
+{
+    return t * n - t * (t + 1) / 2 + (s - t - 1);
+}
 
 // Minimum of the exact quadratic chi^2 of the proposal with delta sums (s1..s4) around the
 // centre (a0,b0) of a state with base sums S, Sm, Smm, E0, E1, E2 (see file header).
 struct FastBase { double S, Sm, Smm, E0, E1, E2, a0, b0; };
 __device__ __forceinline__ void fast_solve(const FastBase &B, int find_bg, int pos_bg, double s1, double s2,
-                                           double s3, double s4, double &rss, double &an, double &bn)
+                                           double s3, double s4, double &rss, double &an, double &bn,
+                                           double &e1n, double &e2n)
 {
     const double Smp = B.Sm + s4, Smmp = B.Smm + 2. * s3 + s2;
     const double f0 = B.E0 - 2. * B.a0 * s1 + B.a0 * B.a0 * s2;
@@ -144,6 +215,9 @@ __device__ __forceinline__ void fast_solve(const FastBase &B, int find_bg, int p
     }
     an = B.a0 + da;
     bn = B.b0 + db;
+    // sum w e M and sum w e at the new centre (zero at an unconstrained minimum)
+    e1n = -.5 * (ga + Haa * da + Hab * db);
+    e2n = -.5 * (gb + Hab * da + Hbb * db);
 }
 
 template <int NG> __device__ __forceinline__ int grp_perm(int lane)
@@ -151,21 +225,26 @@ template <int NG> __device__ __forceinline__ int grp_perm(int lane)
     return NG == 8 ? ((lane >> 2) & 7) : ((lane >> 3) & 3);
 }
 
-template <int MODEL, int QPT>
-__global__ void __launch_bounds__(QPT == 1 ? 1024 : (QPT == 2 ? 544 : 288), 1)
+// CACHE: the scaled intensity rows D_i(q) of the N current contributions live in global
+// memory (L2 resident: N x nq floats per chain), so the "old" half of every evaluation
+// (mcsas.py:362 recomputes it) is one coalesced load; rows are rebuilt with the initial sum
+// of every launch and rewritten when a move is accepted.
+template <int MODEL, int QPT, bool CACHE>
+__global__ void __launch_bounds__(QPT == 1 ? 1024 : (QPT == 2 ? 512 : 256), 1)
 chain_fast_kernel(const __grid_constant__ ChainArgs a)
 {
     using FO = FastOps<MODEL>;
     using O = Ops<MODEL, float>;
     constexpr int NARR = O::NARR;
     constexpr int FGRP = QPT == 1 ? 4 : 8;         // proposals per reduce-scatter chunk
+    constexpr int NGP = FGRP * (FGRP - 1) / 2;     // pairs of a chunk (Gram matrix, off diagonal)
+    constexpr int NGU = (NGP + 1) / 2;             // ... in 64-bit exchange units
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int T = blockDim.x - 32;                 // eval threads; the last warp produces
+    const int T = blockDim.x;                      // all warps evaluate; the last one also fills the ring
     const int W = T >> 5;
-    const bool producer = tid >= T;
     const int WQ = a.warps_q;                      // warps that cover this CTA's q slice once
     const int PS = W / WQ;                         // proposal groups
-    const int grp = producer ? PS : warp / WQ, wq = warp % WQ;
+    const int grp = warp / WQ, wq = warp % WQ;
     const int TQ = WQ * 32, qtid = wq * 32 + lane;
     const int C = a.cluster;
     const int rank = C > 1 ? (int)cluster_ctarank() : 0;
@@ -178,6 +257,8 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     const int D = NARR ? a.mp.quad_nodes : 0;
     const int RING = a.ring;
     const int kmax = a.spec_max;
+    const int RL = QPT * TQ;                       // cached row length of this CTA
+    float *const crow = CACHE ? a.cache + (size_t)slot * a.cache_stride + (size_t)rank * N * RL + qtid : nullptr;
 
     // ---- shared memory carve-up (keep in sync with fast_smem_bytes) -----------------------
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -186,13 +267,15 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     uint64_t *s_bar = (uint64_t *)carve(16);
     double *s_data = (double *)carve(sizeof(double) * 3 * ds.nq_pad);
     double *s_rset = (double *)carve(sizeof(double) * N * (P > 0 ? P : 1));
-    ChainCtrl *s_ctrl = (ChainCtrl *)carve(64);
+    carve(64);
     RingEntry<float> *s_ring = (RingEntry<float> *)carve((size_t)RING * sizeof(RingEntry<float>));
     float4 *s_wsum = (float4 *)carve(16 * (size_t)FAST_MAX_WARPS * KCAP);
     double *s_bsum = (double *)carve(8 * (size_t)(FAST_MAX_WARPS + 1) * 6);
-    constexpr int XU = 2 * KCAP + 8;               // b64 units per rank in an exchange buffer
+    constexpr int XU = FAST_XU;                    // b64 units per rank in an exchange buffer
     double *s_part = (double *)carve(8 * 2 * (size_t)MAX_CLUSTER * XU);
     uint64_t *s_xbar = (uint64_t *)carve(16);
+    float *s_gram = (float *)carve(4 * (size_t)FAST_MAX_WARPS * 28);  // per-warp Gram pairs
+    float *s_gtot = (float *)carve(4 * 32);
     double *s_chi = (double *)carve(8 * (size_t)KCAP + 128);
     FastDec *s_dec = (FastDec *)(s_chi + KCAP);
     double *s_asum = (double *)carve(8 * (size_t)(FAST_MAX_WARPS + 2) * 3 + 8 * 2 * MAX_CLUSTER * 3);
@@ -234,7 +317,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
 #pragma unroll
     for (int j = 0; j < QPT; ++j) {
         int i = (j * C + rank) * TQ + qtid;
-        bool valid = !producer && i < nq;
+        bool valid = i < nq;
         int ii = (i < nq) ? i : nq - 1;
         double qv = s_data[ii], Iv = s_data[ds.nq_pad + ii] * inorm, ev = s_data[2 * ds.nq_pad + ii] * inorm;
         if (ev == 0.0) ev = 1. * inorm;                          // backgroundscalingfit.py:117
@@ -268,7 +351,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         double *part = s_apart + (size_t)abuf * MAX_CLUSTER * 3;
         if (tid < 3) {
             double x = 0.;
-            for (int wv = 0; wv <= W; ++wv) x += s_asum[wv * 3 + tid];
+            for (int wv = 0; wv < W; ++wv) x += s_asum[wv * 3 + tid];
             if (C > 1) { for (int r = 0; r < C; ++r) dsmem_store(part + rank * 3 + tid, (uint32_t)r, x); }
             else part[tid] = x;
         }
@@ -346,8 +429,10 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         }
         PVec pn(a.mp, E.prop);
         FO::prep(pn, a.comp_exp, G, qref, qt, E.cn, s_nodes + (size_t)(e * 2) * NSTR);
-        PVec po(a.mp, s_rset + (int)((uint32_t)t % (uint32_t)N) * P);   // max_iter < 2^31 (host)
-        FO::prep(po, a.comp_exp, G, qref, qt, E.co, s_nodes + (size_t)(e * 2 + 1) * NSTR);
+        if (!CACHE) {                                            // cached rows replace the old contribution
+            PVec po(a.mp, s_rset + (int)((uint32_t)t % (uint32_t)N) * P);   // max_iter < 2^31 (host)
+            FO::prep(po, a.comp_exp, G, qref, qt, E.co, s_nodes + (size_t)(e * 2 + 1) * NSTR);
+        }
     };
 
     const unsigned long long t_start = globaltimer_ns();
@@ -397,13 +482,17 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                 FO::prep(p, a.comp_exp, G, qref, qt, s_ring[e].co, s_nodes + (size_t)(e * 2 + 1) * NSTR);
             }
             __syncthreads();
-            if (!producer) {
+            {
                 for (int e = 0; e < nb; ++e) {
                     const Contrib<float> cc = s_ring[e].co;
                     const float *nd = s_nodes + (size_t)(e * 2 + 1) * NSTR;
+                    float dv[QPT];
+                    FO::template evalN<QPT>(cc, nd, qt, Q, dv);
 #pragma unroll
-                    for (int j = 0; j < QPT; ++j)
-                        ft0[j] += (double)FO::evalS(cc, nd, qt, Q[j]) * (double)s_qs[j * TQ + qtid];
+                    for (int j = 0; j < QPT; ++j) {
+                        ft0[j] += (double)dv[j] * (double)s_qs[j * TQ + qtid];
+                        if (CACHE && grp == 0) __stcg(crow + (size_t)(i0 + e) * RL + j * TQ, dv[j]);
+                    }
                 }
             }
             __syncthreads();
@@ -421,69 +510,41 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
 #pragma unroll
         for (int j = 0; j < QPT; ++j) {
             const int ql = j * TQ + qtid;
-            const double sq = producer ? 0. : s_sw[ql];
+            const double sq = s_sw[ql];
             rho[j] = (float)(sq * (s_In[ql] - (a0 * ft0[j] + b0)));
             mu[j] = (float)(sq * ft0[j]);
         }
         bool dirty = true;                                       // base sums not yet accumulated
         const long long sbase = (long long)chain * a.stream_stride + (a.start_min ? 0 : (long long)N * P);
-        // ---- first ring fill: steps [step, step + RING) -------------------------------------
-        {
-            long long target = min(step + (long long)RING, a.max_iter);
-            for (long long t = step + tid; t < target; t += blockDim.x) fill_entry(t, attempt, sbase);
-            if (tid == 0) {
-                s_ctrl->step = step; s_ctrl->filled = target; s_ctrl->batch = 0;
-                s_ctrl->done = !(N > 1 && conval > a.conv_crit && step < a.max_iter && step < slice_end);
-            }
-        }
+        // ---- first ring fill: the next two batches' worth of steps ------------------------------
+        long long filled = min(step + 2LL * kmax, a.max_iter);   // ring holds steps [.., filled)
+        for (long long t = step + tid; t < filled; t += blockDim.x) fill_entry(t, attempt, sbase);
         __syncthreads();
         int K = max(1, kmax / 2);
         int batch = 0;
         const int wd_batches = (int)min((long long)0x3fffffff, 2 * (min(a.max_iter, slice_end) - step) + 64);
+        bool live = N > 1 && conval > a.conv_crit && step < a.max_iter && step < slice_end;
 
-        if (producer) {
-            long long filled = s_ctrl->filled;
-            for (;;) {
-                const long long pstep = ld_volatile(&s_ctrl->step);
-                const int pdone = ld_volatile_i(&s_ctrl->done);
-                __threadfence_block();
-                if (pdone) { step = ld_volatile(&s_ctrl->step); if (pdone == 2) status = -2; break; }
-                const long long target = min(pstep + (long long)RING, a.max_iter);
-                if (filled < target) {
-                    for (long long t = filled + lane; t < target; t += 32) fill_entry(t, attempt, sbase);
-                    __syncwarp();
-                    __threadfence_block();
-                    filled = target;
-                    if (lane == 0) st_volatile(&s_ctrl->filled, filled);
-                } else {
-                    __nanosleep(64);
-                }
-            }
-        } else {
-        // ---- the MC loop (mcsas.py:354-404), Kb speculative steps per batch ------------------
+        {
+        // ---- the MC loop (mcsas.py:354-404) ---------------------------------------------------
+        // Two kinds of batches: SPECULATIVE (Kb <= 32 steps evaluated against the current state,
+        // committed up to the first accepted one) when moves are rare, and GRAM (exactly FGRP
+        // steps, all of them consumed: the Gram matrix of the proposals' changes lets warp 0
+        // re-derive the sums of later proposals after each accepted one) when moves are frequent.
         FastBase B;                                              // meaningful in warp 0 only
         B.S = L.S; B.Sm = 0.; B.Smm = 0.; B.E0 = 0.; B.E1 = 0.; B.E2 = 0.; B.a0 = a0; B.b0 = b0;
-        for (;;) {
-            if (ld_volatile_i(&s_ctrl->done)) {
-                if (s_ctrl->done == 2) status = -2;
-                break;
-            }
+        while (live) {
+            const long long pt0 = a.prof ? clock64() : 0;
             int Kb = min(K, kmax);
+            bool gram = a.gram && Kb <= FGRP && kmax >= FGRP;
+            if (gram) Kb = FGRP;
             {
                 long long rem = a.max_iter - step;
-                if (rem < Kb) Kb = rem >= 1 ? (1 << (31 - __clz((int)rem))) : 0;   // power of two
+                if (rem < Kb) { Kb = rem >= 1 ? (1 << (31 - __clz((int)rem))) : 0; gram = false; }   // power of two
             }
             ++batch;
-            bool wd = Kb < 1 || batch > wd_batches;
-            if (!wd) {
-                int spins = 0;
-                while (ld_volatile(&s_ctrl->filled) < step + Kb) {
-                    if (++spins > (1 << 24)) { wd = true; break; }
-                    __nanosleep(32);
-                }
-                __threadfence_block();
-            }
-            wd = __any_sync(0xffffffffu, wd);
+            bool wd = Kb < 1 || batch > wd_batches;               // watchdog: never loop forever
+            const long long pt1 = a.prof ? clock64() : 0;
             // ---- exact base sums of the current state (after an accepted move) ---------------
             if (dirty && grp == 0) {
                 double b5[5] = {0., 0., 0., 0., 0.};
@@ -510,22 +571,128 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     s_bsum[wq * 6 + lane] = x;
                 }
             }
+            const long long pt1a = a.prof ? clock64() : 0;
+            long long ptc[4] = {0, 0, 0, 0};
             // ---- evaluate the batch ---------------------------------------------------------
+            // pinned in a register: ptxas otherwise re-reads %tid (S2R) for every proposal slot
+            int perm = grp_perm<FGRP>(lane);
+            asm volatile("mov.b32 %0, %0;" : "+r"(perm));
+            const int ri0 = (int)((uint32_t)step % (uint32_t)N);  // contribution replaced by the batch's first step
+            float uu[FGRP][QPT];                                 // GRAM: (new - old)/sigma of slot s
             if (!wd) {
-                if (Kb >= FGRP) {
-                    const int perm = grp_perm<FGRP>(lane);
+                if (gram) {
+                    // every group evaluates the chunk (all need uu for the update); group 0 reports
+                    const int e0 = (int)step & (RING - 1);
+                    float acc[FGRP][4], gq[NGP];
+                    float od[CACHE ? FGRP : 1][QPT];
+                    if (CACHE) {
+#pragma unroll
+                        for (int s = 0; s < FGRP; ++s) {
+                            int ri = ri0 + (s ^ perm);
+                            if (ri >= N) ri -= N;
+#pragma unroll
+                            for (int j = 0; j < QPT; ++j) od[CACHE ? s : 0][j] = __ldcg(crow + (size_t)ri * RL + j * TQ);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < NGP; ++i) gq[i] = 0.f;
+#pragma unroll
+                    for (int s = 0; s < FGRP; ++s) {
+                        acc[s][0] = 0.f; acc[s][1] = 0.f; acc[s][2] = 0.f; acc[s][3] = 0.f;
+                        const int e = (e0 + (s ^ perm)) & (RING - 1);
+                        const Contrib<float> cn = s_ring[e].cn, co = s_ring[e].co;
+                        const float *nn = s_nodes + (size_t)(e * 2) * NSTR, *no = nn + NSTR;
+                        float dd[QPT];
+                        if (CACHE) {
+                            FO::template evalN<QPT>(cn, nn, qt, Q, dd);
+#pragma unroll
+                            for (int j = 0; j < QPT; ++j) dd[j] -= od[CACHE ? s : 0][j];
+                        } else {
+                            FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd);
+                        }
+#pragma unroll
+                        for (int j = 0; j < QPT; ++j) {
+                            const float u = cq[j] * dd[j];
+                            uu[s][j] = u;
+                            acc[s][0] = fmaf(rho[j], u, acc[s][0]);
+                            acc[s][1] = fmaf(u, u, acc[s][1]);
+                            acc[s][2] = fmaf(mu[j], u, acc[s][2]);
+                            acc[s][3] = fmaf(om[j], u, acc[s][3]);
+#pragma unroll
+                            for (int t = 0; t < s; ++t)
+                                gq[tri_idx<FGRP>(t, s)] = fmaf(uu[t][j], u, gq[tri_idx<FGRP>(t, s)]);
+                        }
+                    }
+                    if (grp == 0) {
+#pragma unroll
+                        for (int h = FGRP / 2, off = 16; h >= 1; h >>= 1, off >>= 1) {
+#pragma unroll
+                            for (int s = 0; s < h; ++s)
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+                                    acc[s][i] += __shfl_xor_sync(0xffffffffu, acc[s + h][i], off);
+                            // Gram: all-reduce with the slot permutation of the partner lane
+                            float tmp[NGP];
+#pragma unroll
+                            for (int t = 0; t < FGRP; ++t)
+#pragma unroll
+                                for (int s2 = t + 1; s2 < FGRP; ++s2)
+                                    tmp[tri_idx<FGRP>(t, s2)] =
+                                        __shfl_xor_sync(0xffffffffu, gq[tri_idx<FGRP>(t ^ h, s2 ^ h)], off);
+#pragma unroll
+                            for (int i = 0; i < NGP; ++i) gq[i] += tmp[i];
+                        }
+#pragma unroll
+                        for (int off = 32 / FGRP / 2; off >= 1; off >>= 1) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                acc[0][i] += __shfl_xor_sync(0xffffffffu, acc[0][i], off);
+#pragma unroll
+                            for (int i = 0; i < NGP; ++i) gq[i] += __shfl_xor_sync(0xffffffffu, gq[i], off);
+                        }
+                        if ((lane & (32 / FGRP - 1)) == 0)
+                            s_wsum[wq * KCAP + perm] = make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
+                        if (lane == 0) {                          // perm == 0: natural proposal order
+#pragma unroll
+                            for (int i = 0; i < NGP; ++i) s_gram[wq * NGP + i] = gq[i];
+                        }
+                    }
+                } else if (Kb >= FGRP) {
                     const int e0 = (int)step & (RING - 1);
                     for (int k0 = grp * FGRP; k0 < Kb; k0 += PS * FGRP) {
+                        const long long ptk = a.prof ? clock64() : 0;
                         float acc[FGRP][4];
+                        float dn[CACHE ? FGRP : 1][QPT], od[CACHE ? FGRP : 1][QPT];
+                        if (CACHE) {
+                            // old rows first (L2 latency hides behind the new evaluations)
+#pragma unroll
+                            for (int s = 0; s < FGRP; ++s) {
+                                int ri = ri0 + k0 + (s ^ perm);
+                                if (ri >= N) ri -= N;
+#pragma unroll
+                                for (int j = 0; j < QPT; ++j) od[CACHE ? s : 0][j] = __ldcg(crow + (size_t)ri * RL + j * TQ);
+                            }
+#pragma unroll
+                            for (int s = 0; s < FGRP; ++s) {
+                                const int e = (e0 + k0 + (s ^ perm)) & (RING - 1);
+                                const Contrib<float> cn = s_ring[e].cn;
+                                FO::template evalN<QPT>(cn, s_nodes + (size_t)(e * 2) * NSTR, qt, Q, dn[CACHE ? s : 0]);
+                            }
+                        }
 #pragma unroll
                         for (int s = 0; s < FGRP; ++s) {
                             acc[s][0] = 0.f; acc[s][1] = 0.f; acc[s][2] = 0.f; acc[s][3] = 0.f;
-                            const int k = k0 + (s ^ perm);
-                            const int e = (e0 + k) & (RING - 1);
-                            const Contrib<float> cn = s_ring[e].cn, co = s_ring[e].co;
-                            const float *nn = s_nodes + (size_t)(e * 2) * NSTR, *no = nn + NSTR;
                             float dd[QPT];
-                            FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd);  // mcsas.py:360-362
+                            if (CACHE) {
+#pragma unroll
+                                for (int j = 0; j < QPT; ++j) dd[j] = dn[CACHE ? s : 0][j] - od[CACHE ? s : 0][j];
+                            } else {
+                                const int k = k0 + (s ^ perm);
+                                const int e = (e0 + k) & (RING - 1);
+                                const Contrib<float> cn = s_ring[e].cn, co = s_ring[e].co;
+                                const float *nn = s_nodes + (size_t)(e * 2) * NSTR, *no = nn + NSTR;
+                                FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd);  // mcsas.py:360-362
+                            }
 #pragma unroll
                             for (int j = 0; j < QPT; ++j) {
                                 float u = cq[j] * dd[j];                     // (new - old)/sigma, :366
@@ -551,6 +718,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                                 acc[0][i] += __shfl_xor_sync(0xffffffffu, acc[0][i], off);
                         if ((lane & (32 / FGRP - 1)) == 0)
                             s_wsum[wq * KCAP + k0 + perm] = make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
+                        if (a.prof) { ptc[k0 == 0 ? 0 : 1] += clock64() - ptk; ptc[k0 == 0 ? 2 : 3] += 1; }
                     }
                 } else if (grp == 0) {
                     for (int k = 0; k < Kb; ++k) {
@@ -559,7 +727,15 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                         const Contrib<float> cn = s_ring[e].cn, co = s_ring[e].co;
                         const float *nn = s_nodes + (size_t)(e * 2) * NSTR, *no = nn + NSTR;
                         float dd[QPT];
-                        FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd);
+                        if (CACHE) {
+                            int ri = ri0 + k;
+                            if (ri >= N) ri -= N;
+                            FO::template evalN<QPT>(cn, nn, qt, Q, dd);
+#pragma unroll
+                            for (int j = 0; j < QPT; ++j) dd[j] -= __ldcg(crow + (size_t)ri * RL + j * TQ);
+                        } else {
+                            FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd);
+                        }
 #pragma unroll
                         for (int j = 0; j < QPT; ++j) {
                             float u = cq[j] * dd[j];
@@ -577,33 +753,58 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                 }
             }
             if (wd && lane == 0) s_dec->wd = 1;                  // any warp may raise it
+            const long long pt2 = a.prof ? clock64() : 0;
             named_bar_sync(1, T);                                // B1: eval warps only
-            if (tid == 0) { __threadfence_block(); st_volatile(&s_ctrl->step, step); }
+            const long long pt3 = a.prof ? clock64() : 0;
             wd = s_dec->wd != 0;
+            // ---- the last warp prepares the ring entries of the NEXT batch while warp 0 decides:
+            // steps [filled, step + Kb + kmax); their slots held steps <= step - RING/2 (consumed),
+            // and the contributions they replace are not touched by this batch (Kb + kmax < N)
+            const long long fill_from = filled, fill_to = min(step + Kb + (long long)kmax, a.max_iter);
+            if (warp == W - 1 && W > 1)
+                for (long long t = fill_from + lane; t < fill_to; t += 32) fill_entry(t, attempt, sbase);
+            filled = max(filled, fill_to);
             // ---- exchange the partial sums over the cluster (st.async + mbarrier) -------------
+            // units of a rank's exchange row: [0, 2K) two floats each of the proposal sums,
+            // [2 KCAP, +5) base sums, [2 KCAP + 5] watchdog flag, [2 KCAP + 8, +NGU) Gram pairs
             double *part = s_part + (size_t)abuf * MAX_CLUSTER * XU;
             const int nb5 = dirty ? 5 : 0;
             if (C > 1) {
-                const int nprop = 2 * Kb, nval = nprop + nb5 + 1;
+                const int nprop = 2 * Kb, ngu = gram ? NGU : 0, nval = nprop + nb5 + 1 + ngu;
                 if (tid == 0) mbar_expect_tx(s_xbar + abuf, (uint32_t)(C * nval * 8));
                 for (int i = tid; i < nval; i += T) {
                     double x;
+                    int du;
                     if (i < nprop) {                             // two floats of proposal i/2
                         const float *src = (const float *)s_wsum + (size_t)(i >> 1) * 4 + (i & 1) * 2;
                         float x0 = 0.f, x1 = 0.f;
                         for (int wv = 0; wv < WQ; ++wv) { x0 += src[(size_t)wv * KCAP * 4]; x1 += src[(size_t)wv * KCAP * 4 + 1]; }
                         x = __hiloint2double(__float_as_int(x1), __float_as_int(x0));
+                        du = i;
                     } else if (i < nprop + nb5) {
                         x = 0.;
                         for (int wv = 0; wv < WQ; ++wv) x += s_bsum[wv * 6 + (i - nprop)];
-                    } else x = wd ? 1. : 0.;
-                    double *dst = part + (size_t)rank * XU + (i < nprop ? i : 2 * KCAP + (i - nprop));
+                        du = 2 * KCAP + (i - nprop);
+                    } else if (i == nprop + nb5) {
+                        x = wd ? 1. : 0.;
+                        du = 2 * KCAP + 5;
+                    } else {                                     // two Gram pairs
+                        const int g = 2 * (i - nprop - nb5 - 1);
+                        float x0 = 0.f, x1 = 0.f;
+                        for (int wv = 0; wv < WQ; ++wv) {
+                            x0 += s_gram[wv * NGP + g];
+                            if (g + 1 < NGP) x1 += s_gram[wv * NGP + g + 1];
+                        }
+                        x = __hiloint2double(__float_as_int(x1), __float_as_int(x0));
+                        du = 2 * KCAP + 8 + (g >> 1);
+                    }
+                    double *dst = part + (size_t)rank * XU + du;
                     for (int r = 0; r < C; ++r) dsmem_store_async(dst, s_xbar + abuf, (uint32_t)r, x);
                 }
                 if (warp == 0) {
                     mbar_wait(s_xbar + abuf, (xphase >> abuf) & 1);
                     bool anywd = false;
-                    for (int r = 0; r < C; ++r) anywd |= part[(size_t)r * XU + 2 * KCAP + nb5] != 0.;
+                    for (int r = 0; r < C; ++r) anywd |= part[(size_t)r * XU + 2 * KCAP + 5] != 0.;
                     wd = anywd;
                 }
                 xphase ^= 1u << abuf;
@@ -622,15 +823,13 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     }
                     B.E0 = b5[0]; B.E1 = b5[1]; B.E2 = b5[2]; B.Sm = b5[3]; B.Smm = b5[4];
                     B.a0 = a0; B.b0 = b0;
-                    double rss, an, bn;
-                    fast_solve(B, L.find_bg, L.pos_bg, 0., 0., 0., 0., rss, an, bn);
-                    conval = rss * L.inv_nq;                     // exact chi2 of the current state
-                    sc_a = an; sc_b = bn;
+                    // the centre is the fit of this state up to the fp32 error of the delta sums:
+                    // chi2 at the centre exceeds the minimum by O(1e-14) relative
+                    conval = B.E0 * L.inv_nq;
                 }
-                double chi = 0., an = 0., bn = 0.;
-                bool better = false;
-                if (lane < Kb && !wd) {
-                    double s1 = 0., s2 = 0., s3 = 0., s4 = 0.;
+                double s1 = 0., s2 = 0., s3 = 0., s4 = 0.;
+                const bool mine = lane < Kb && !wd;
+                if (mine) {
                     if (C > 1) {
                         for (int r = 0; r < C; ++r) {
                             const float4 x = *(const float4 *)(part + (size_t)r * XU + 2 * lane);
@@ -644,50 +843,162 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                         }
                         s1 = t4.x; s2 = t4.y; s3 = t4.z; s4 = t4.w;
                     }
-                    double rss;
-                    fast_solve(B, L.find_bg, L.pos_bg, s1, s2, s3, s4, rss, an, bn);   // mcsas.py:376
-                    chi = rss * L.inv_nq;
-                    better = chi < conval;                       // :379 strict
-                    s_chi[lane] = chi;
                 }
-                unsigned mask = __ballot_sync(0xffffffffu, better);
-                const int ks = mask ? (__ffs(mask) - 1) : -1;
-                const int src = ks >= 0 ? ks : 0;
-                const double ca = __shfl_sync(0xffffffffu, an, src), cb = __shfl_sync(0xffffffffu, bn, src);
-                const double cc = __shfl_sync(0xffffffffu, chi, src);
+                int ks = -1, accmask = 0;
+                double ca = a0, cb = b0, cc = conval;
+                if (!gram) {
+                    double chi = 0., an = 0., bn = 0., e1, e2;
+                    bool better = false;
+                    if (mine) {
+                        double rss;
+                        fast_solve(B, L.find_bg, L.pos_bg, s1, s2, s3, s4, rss, an, bn, e1, e2);   // mcsas.py:376
+                        chi = rss * L.inv_nq;
+                        better = chi < conval;                   // :379 strict
+                        s_chi[lane] = chi;
+                    }
+                    const unsigned mask = __ballot_sync(0xffffffffu, better);
+                    ks = mask ? (__ffs(mask) - 1) : -1;
+                    if (ks >= 0) {
+                        ca = __shfl_sync(0xffffffffu, an, ks); cb = __shfl_sync(0xffffffffu, bn, ks);
+                        cc = __shfl_sync(0xffffffffu, chi, ks);
+                    }
+                } else {
+                    // Gram totals over warps / ranks
+                    for (int i = lane; i < NGP; i += 32) {
+                        float x = 0.f;
+                        if (C > 1) {
+                            for (int r = 0; r < C; ++r) x += ((const float *)(part + (size_t)r * XU + 2 * KCAP + 8))[i];
+                        } else {
+                            for (int wv = 0; wv < WQ; ++wv) x += s_gram[wv * NGP + i];
+                        }
+                        s_gtot[i] = x;
+                    }
+                    __syncwarp();
+                    int pos = 0;
+                    for (int it = 0; it <= FGRP && !wd; ++it) {
+                        double rss = 0., an = 0., bn = 0., e1 = 0., e2 = 0.;
+                        bool better = false;
+                        if (mine && lane >= pos) {
+                            fast_solve(B, L.find_bg, L.pos_bg, s1, s2, s3, s4, rss, an, bn, e1, e2);
+                            const double chi = rss * L.inv_nq;
+                            better = chi < cc;                   // :379 against the state reached so far
+                            s_chi[lane] = chi;
+                        }
+                        const unsigned mask = __ballot_sync(0xffffffffu, better);
+                        if (!mask) break;
+                        const int i = __ffs(mask) - 1;
+                        const double ai = __shfl_sync(0xffffffffu, an, i), bi = __shfl_sync(0xffffffffu, bn, i);
+                        const double ri = __shfl_sync(0xffffffffu, rss, i);
+                        const double e1i = __shfl_sync(0xffffffffu, e1, i), e2i = __shfl_sync(0xffffffffu, e2, i);
+                        const double s2i = __shfl_sync(0xffffffffu, s2, i), s3i = __shfl_sync(0xffffffffu, s3, i);
+                        const double s4i = __shfl_sync(0xffffffffu, s4, i);
+                        const double da = ai - B.a0, db = bi - B.b0;
+                        if (mine && lane > i) {                  // sums of later proposals w.r.t. the new state
+                            const double G = (double)s_gtot[tri_idx_rt(FGRP, i, lane)];
+                            s1 = s1 - da * s3 - ai * G - db * s4;
+                            s3 += G;
+                        }
+                        B.Sm += s4i; B.Smm += 2. * s3i + s2i;
+                        B.E0 = ri; B.E1 = e1i; B.E2 = e2i; B.a0 = ai; B.b0 = bi;
+                        ca = ai; cb = bi; cc = ri * L.inv_nq;
+                        accmask |= 1 << i;
+                        pos = i + 1;
+                    }
+                    ks = accmask ? 0 : -1;
+                }
                 if (lane == 0) {
                     s_dec->kstar = ks;
+                    s_dec->accmask = accmask;
                     s_dec->wd = wd ? 2 : 0;
-                    s_dec->a = ks >= 0 ? ca : sc_a;              // accepted: new centre; else the exact fit
-                    s_dec->b = ks >= 0 ? cb : sc_b;
-                    s_dec->conval = ks >= 0 ? cc : conval;
+                    s_dec->a = ca;                               // centre of the state after this batch
+                    s_dec->b = cb;
+                    s_dec->conval = cc;
                 }
             }
+            if (W == 1)                                          // one-warp CTA: fill after deciding
+                for (long long t = fill_from + lane; t < fill_to; t += 32) fill_entry(t, attempt, sbase);
             abuf ^= 1;
+            const long long pt4 = a.prof ? clock64() : 0;
             named_bar_sync(1, T);                                // B2
-            if (s_dec->wd == 2) {
-                if (tid == 0) { st_volatile(&s_ctrl->step, step); __threadfence_block(); st_volatile_i(&s_ctrl->done, 2); }
-                status = -2;
-                break;
-            }
+            const long long pt5 = a.prof ? clock64() : 0;
+            if (s_dec->wd == 2) { status = -2; break; }
             const int kstar = s_dec->kstar;
-            const int used = kstar >= 0 ? kstar + 1 : Kb;
+            const int accmask = s_dec->accmask;
+            const int used = gram ? Kb : (kstar >= 0 ? kstar + 1 : Kb);
             conval = s_dec->conval;
             if (a.trace_accept && rank == 0) {
                 for (int k = tid; k < used; k += T) {
-                    a.trace_accept[(long long)chain * a.max_iter + step + k] = (k == kstar);
+                    a.trace_accept[(long long)chain * a.max_iter + step + k] = gram ? ((accmask >> k) & 1) : (k == kstar);
                     a.trace_chi[(long long)chain * a.max_iter + step + k] = s_chi[k];
                 }
             }
             dirty = false;
-            if (kstar >= 0) {                                    // mcsas.py:381-384
+            if (gram) {
+                if (accmask) {                                   // mcsas.py:381-384 for every accepted step
+                    a0 = s_dec->a; b0 = s_dec->b;
+                    sc_a = a0; sc_b = b0;
+#pragma unroll
+                    for (int j = 0; j < QPT; ++j) {
+                        const int ql = j * TQ + qtid;
+                        const double sq = s_sw[ql];
+                        double du = 0.;
+#pragma unroll
+                        for (int s = 0; s < FGRP; ++s)
+                            if ((accmask >> (s ^ perm)) & 1) du += (double)uu[s][j];
+                        // uu = (new - old)/sigma in the model's units: undo the 1/sigma
+                        const double f = s_ft[cur * FAST_QCAP + ql] + (sq > 0. ? du / sq : 0.);
+                        if (grp == 0) s_ft[(cur ^ 1) * FAST_QCAP + ql] = f;
+                        rho[j] = (float)(sq * (s_In[ql] - (a0 * f + b0)));
+                        mu[j] = (float)(sq * f);
+                    }
+                    cur ^= 1;
+                    if (CACHE && grp == 0) {                     // rows of the accepted contributions
+                        for (int k = 0; k < FGRP; ++k) {
+                            if (!((accmask >> k) & 1)) continue;
+                            const int e = ((int)step + k) & (RING - 1);
+                            int ri = ri0 + k;
+                            if (ri >= N) ri -= N;
+                            float dv[QPT];
+                            FO::template evalN<QPT>(s_ring[e].cn, s_nodes + (size_t)(e * 2) * NSTR, qt, Q, dv);
+#pragma unroll
+                            for (int j = 0; j < QPT; ++j) __stcg(crow + (size_t)ri * RL + j * TQ, dv[j]);
+                        }
+                    }
+                    if (tid < FGRP * P) {
+                        const int k = tid / P, p = tid - k * P;
+                        if ((accmask >> k) & 1) {
+                            const int e = ((int)step + k) & (RING - 1);
+                            const int rix = (int)((uint32_t)(step + k) % (uint32_t)N);
+                            s_rset[rix * P + p] = s_ring[e].prop[p];
+                        }
+                    }
+                    moves += __popc(accmask);
+                    dirty = true;
+                    K = FGRP;
+                } else {
+                    K = min(kmax, 2 * FGRP);                     // no move in a whole chunk: speculate
+                }
+            } else if (kstar >= 0) {                             // mcsas.py:381-384
                 a0 = s_dec->a; b0 = s_dec->b;
                 sc_a = a0; sc_b = b0;
                 const int e = ((int)step + kstar) & (RING - 1);
                 const Contrib<float> cn = s_ring[e].cn, co = s_ring[e].co;
                 const float *nn = s_nodes + (size_t)(e * 2) * NSTR, *no = nn + NSTR;
+                const int rix = (int)((uint32_t)(step + kstar) % (uint32_t)N);
                 float dd[QPT];
-                FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd);
+                if (CACHE) {
+                    float dv[QPT];
+                    FO::template evalN<QPT>(cn, nn, qt, Q, dv);
+#pragma unroll
+                    for (int j = 0; j < QPT; ++j) dd[j] = dv[j] - __ldcg(crow + (size_t)rix * RL + j * TQ);
+                    if (PS > 1) named_bar_sync(1, T);            // every group has read the old row
+                    if (grp == 0) {
+#pragma unroll
+                        for (int j = 0; j < QPT; ++j) __stcg(crow + (size_t)rix * RL + j * TQ, dv[j]);
+                    }
+                } else {
+                    FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd);
+                }
 #pragma unroll
                 for (int j = 0; j < QPT; ++j) {
                     const int ql = j * TQ + qtid;
@@ -698,32 +1009,27 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     mu[j] = (float)(sq * f);
                 }
                 cur ^= 1;
-                const int rix = (int)((uint32_t)(step + kstar) % (uint32_t)N);
                 if (tid < P) s_rset[rix * P + tid] = s_ring[e].prop[tid];
                 ++moves;
                 evals += 2;
                 dirty = true;
                 K = max(1, min(kmax, 1 << (31 - __clz(kstar + 1))));
             } else {
-                sc_a = s_dec->a; sc_b = s_dec->b;
                 K = min(kmax, K * 2);
             }
             evals += 2 * Kb;
             step += used;                                        // :403-404 (ri = step % N)
             steps_all += used;
-            if (!(conval > a.conv_crit && step < a.max_iter && step < slice_end)) {
-                if (tid == 0) {
-                    st_volatile(&s_ctrl->step, step);
-                    __threadfence_block();
-                    st_volatile_i(&s_ctrl->done, 1);
-                }
-                break;
+            if (a.prof && tid == 0 && rank == 0) {               // phase cycles of warp 0 (tools/prof)
+                long long *pp = a.prof + ((long long)chain * 2 + (gram ? 1 : 0)) * 16;
+                pp[8] += pt1a - pt1; pp[9] += ptc[0]; pp[10] += ptc[1]; pp[11] += ptc[2]; pp[12] += ptc[3];
+                pp[0] += pt1 - pt0; pp[1] += pt2 - pt1; pp[2] += pt3 - pt2; pp[3] += pt4 - pt3;
+                pp[4] += pt5 - pt4; pp[5] += clock64() - pt5; pp[6] += 1; pp[7] += used;
             }
+            live = conval > a.conv_crit && step < a.max_iter && step < slice_end;
         }
         }
-        __syncthreads();                                         // eval warps and producer rejoin
-        step = s_ctrl->step;
-        if (producer) { conval = 0.; }
+        __syncthreads();
         // ---- final fit of the accepted state (mcsas.py:424-425) --------------------------------
         lsq_all(sc_a, sc_b, conval);
         if (status == -2) break;

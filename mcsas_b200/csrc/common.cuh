@@ -48,6 +48,7 @@ struct ChainArgs {
     int spec_max;                // max speculative proposals per batch (<= ring / 4)
     int ring;                    // ring entries = min(RING_MAX, n_contribs)
     int cluster;                 // CTAs per chain (q split)
+    int gram;                    // fp32 kernel: 1 = Gram batches (multi-accept chunks) when moves are frequent
     int warps_q;                 // fp32 kernel: warps covering one CTA's q slice (eval warps = warps_q * groups)
     int resume;                  // 1: continue from the saved state (rset, counters)
     long long slice_steps;       // MC steps per chain in this launch, 0 = run to the end
@@ -72,6 +73,9 @@ struct ChainArgs {
     int *attempts;
     unsigned char *trace_accept; // [chain][max_iter] or NULL
     double *trace_chi;           // [chain][max_iter] or NULL
+    float *cache;                // fp32 kernel: NULL or [launch slot][cache_stride] contribution rows
+    long long cache_stride;      // floats per launch slot (>= n_contribs * padded nq)
+    long long *prof;             // NULL or [chain][2][8] phase cycle counters (MCSAS_B200_PROF)
 };
 
 struct EvalArgs {
@@ -122,7 +126,8 @@ __host__ __device__ inline size_t chain_smem_bytes(int nq_pad, int N, int P, int
 }
 
 // ---- shared-memory footprint of chain_fast_kernel (mirrors its carve-up) -----------------------------
-#define FAST_MAX_WARPS 31
+#define FAST_MAX_WARPS 32
+#define FAST_XU (2 * KCAP + 8 + 16) // 64-bit units per rank in a cluster exchange buffer
 #define FAST_QCAP 1024            // q points per CTA (QPT * 32 * warps_q)
 __host__ __device__ inline size_t fast_smem_bytes(int nq_pad, int N, int P, int D, int narr, int ring)
 {
@@ -134,7 +139,8 @@ __host__ __device__ inline size_t fast_smem_bytes(int nq_pad, int N, int P, int 
     s += AL16((size_t)ring * (8 * MCSAS_MAX_ACTIVE + 2 * 4 * 8));// ring entries
     s += AL16(16 * (size_t)FAST_MAX_WARPS * KCAP);               // per-warp proposal sums (float4)
     s += AL16(8 * (size_t)(FAST_MAX_WARPS + 1) * 6);             // per-warp base sums
-    s += AL16(8 * 2 * (size_t)MAX_CLUSTER * (2 * KCAP + 8));     // cluster exchange, 2 buffers
+    s += AL16(8 * 2 * (size_t)MAX_CLUSTER * FAST_XU);            // cluster exchange, 2 buffers
+    s += AL16(4 * (size_t)FAST_MAX_WARPS * 28) + AL16(4 * 32);   // Gram pairs per warp + totals
     s += 16;                                                     // exchange mbarriers
     s += AL16(8 * (size_t)KCAP + 128);                           // chi per proposal + decision
     s += AL16(8 * (size_t)(FAST_MAX_WARPS + 2) * 3 + 8 * 2 * MAX_CLUSTER * 3);   // full-LSQ all-sum

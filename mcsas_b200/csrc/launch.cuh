@@ -8,7 +8,7 @@ static const int CHAIN_QPT[] = {1, 2, 4};
 static const int N_CHAIN_LAYOUTS = 3;
 #define CHAIN_MAX_EVAL_THREADS 256
 // fp32 production kernel (chain_fast.cuh): max eval threads per CTA of layout QPT = 1, 2, 4
-static const int FAST_MAX_EVAL_THREADS[] = {992, 512, 256};
+static const int FAST_MAX_EVAL_THREADS[] = {1024, 512, 256};
 
 // node arrays kept per contribution (Ops<MODEL>::NARR)
 static const int MODEL_NARR[MCSAS_N_MODELS] = {0, 0, 0, 2, 1, 2, 0, 0};

@@ -14,7 +14,11 @@ template <class Real, int QPT> struct KernelOf {
     static auto get() { return chain_kernel<MODEL_ID, Real, QPT>; }
 };
 template <int QPT> struct KernelOf<float, QPT> {
-    static auto get() { return chain_fast_kernel<MODEL_ID, QPT>; }
+    static auto get() { return chain_fast_kernel<MODEL_ID, QPT, false>; }
+};
+struct CachedF {};            // tag: fp32 production kernel with the contribution-row cache
+template <int QPT> struct KernelOf<CachedF, QPT> {
+    static auto get() { return chain_fast_kernel<MODEL_ID, QPT, true>; }
 };
 
 template <class Real, int QPT>
@@ -79,7 +83,7 @@ cudaError_t CAT(mcsas_query_chain_, MODEL_ID)(int prec, int layout, int threads,
                                               int cluster, int *max_clusters, int *regs)
 {
     return prec == MCSAS_FP64 ? query_prec<double>(layout, threads, smem, cluster, max_clusters, regs)
-                              : query_prec<float>(layout, threads, smem, cluster, max_clusters, regs);
+                              : query_prec<CachedF>(layout, threads, smem, cluster, max_clusters, regs);
 }
 
 template <class Real>
@@ -97,8 +101,9 @@ static cudaError_t launch_prec(int layout, int grid, int threads, size_t smem, c
 cudaError_t CAT(mcsas_launch_chain_, MODEL_ID)(int prec, int layout, int grid, int threads,
                                                size_t smem, cudaStream_t st, const ChainArgs &a)
 {
-    return prec == MCSAS_FP64 ? launch_prec<double>(layout, grid, threads, smem, st, a)
-                              : launch_prec<float>(layout, grid, threads, smem, st, a);
+    if (prec == MCSAS_FP64) return launch_prec<double>(layout, grid, threads, smem, st, a);
+    return a.cache ? launch_prec<CachedF>(layout, grid, threads, smem, st, a)
+                   : launch_prec<float>(layout, grid, threads, smem, st, a);
 }
 
 cudaError_t CAT(mcsas_launch_eval_, MODEL_ID)(int prec, int grid, size_t smem, cudaStream_t st,
