@@ -604,7 +604,7 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     a.cache = nullptr;
     if (cfg->precision == MCSAS_FP32 && !(getenv("MCSAS_B200_CACHE") && atoi(getenv("MCSAS_B200_CACHE")) == 0)) {
         // contribution-row cache: one row of padded q points per contribution and chain slot
-        const size_t stride = (size_t)N * ((size_t)ctx->nq_max + 128 * MAX_CLUSTER);
+        const size_t stride = (size_t)N * (((size_t)ctx->nq_max + 128 * MAX_CLUSTER + 3) & ~(size_t)3);   // 16-byte aligned rows
         const size_t need = stride * (size_t)n_chains;
         if (need * sizeof(float) <= ((size_t)8 << 30)) {        // beyond 8 GB: recompute instead
             if (need > ctx->cache_cap) { CK(regrow(&ctx->d_cache, need)); ctx->cache_cap = need; }

@@ -55,6 +55,18 @@ template <int MODEL> struct FastOps {
 #pragma unroll
         for (int j = 0; j < QPT; ++j) d[j] = evalS(cn, nn, qt, Q[j]) - evalS(co, no, qt, Q[j]);
     }
+    // NS contributions (ring entries ent[s]) at once
+    template <int QPT, int NS>
+    __device__ __forceinline__ static void evalChunk(const RingEntry<float> *ring, const int (&ent)[NS],
+                                                     const float *nodes, size_t nstr, const QuadTab<float> &qt,
+                                                     const QRep<float> (&Q)[QPT], float (&d)[NS][QPT])
+    {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const Contrib<float> cn = ring[ent[s]].cn;
+            evalN<QPT>(cn, nodes + (size_t)(ent[s] * 2) * nstr, qt, Q, d[s]);
+        }
+    }
 };
 
 // g(x) = sin x - x cos x = x^3 F(x)/3 (sphere.py:62) for the M (q, radius) pairs of a
@@ -112,7 +124,8 @@ template <> struct FastOps<MCSAS_SPHERE> {
         O::template prep<true>(p, ce, G, qt, cc, nodes);
         double xr = (double)cc.c[0] * (double)qref;          // r * q_ref
         double x3 = xr * xr * xr;
-        cc.c[1] = (float)((double)cc.amp / (x3 * x3));       // amp / (r q_ref)^6
+        cc.c[2] = (float)((double)cc.amp / (x3 * x3));       // amp / (r q_ref)^6
+        cc.c[1] = cc.c[0];                                   // (r, A) = one aligned 8-byte load
     }
     __device__ __forceinline__ static float evalS(const Contrib<float> &cc, const float *,
                                                   const QuadTab<float> &, const QRep<float> &Q)
@@ -120,7 +133,7 @@ template <> struct FastOps<MCSAS_SPHERE> {
         const float q[1] = {Q.q}, th[1] = {Q.th}, tl[1] = {Q.tl}, r[1] = {cc.c[0]};
         float g[1];
         sph_g_vec<1, true>(q, th, tl, r, g);
-        return (g[0] * g[0]) * cc.c[1];
+        return (g[0] * g[0]) * cc.c[2];
     }
     // q ascends along the lanes, so "some x < 1" is warp-uniform for all but one warp per
     // radius: one vote per proposal selects the variant without the series.  Callers are
@@ -141,7 +154,51 @@ template <> struct FastOps<MCSAS_SPHERE> {
 #pragma unroll
         for (int j = 0; j < QPT; ++j) g[j] = g[j] * g[j];
 #pragma unroll
-        for (int j = 0; j < QPT; ++j) d[j] = g[j] * cc.c[1];
+        for (int j = 0; j < QPT; ++j) d[j] = g[j] * cc.c[2];
+    }
+    // NS contributions at once: ONE vote selects the series variant for the whole chunk, so
+    // the NS x QPT evaluations form a single basic block that ptxas can interleave freely
+    template <int QPT, int NS>
+    __device__ __forceinline__ static void evalChunk(const RingEntry<float> *ring, const int (&ent)[NS],
+                                                     const float *, size_t, const QuadTab<float> &,
+                                                     const QRep<float> (&Q)[QPT], float (&d)[NS][QPT])
+    {
+        float rr[NS], aa[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const float2 ra = *(const float2 *)&ring[ent[s]].cn.c[1];
+            rr[s] = ra.x; aa[s] = ra.y;
+        }
+        float rmin = rr[0];
+#pragma unroll
+        for (int s = 1; s < NS; ++s) rmin = fminf(rmin, rr[s]);
+        float qmin = Q[0].q;
+#pragma unroll
+        for (int j = 1; j < QPT; ++j) qmin = fminf(qmin, Q[j].q);
+        float q[QPT], th[QPT], tl[QPT];
+#pragma unroll
+        for (int j = 0; j < QPT; ++j) { q[j] = Q[j].q; th[j] = Q[j].th; tl[j] = Q[j].tl; }
+        if (__any_sync(0xffffffffu, qmin * rmin < 1.f)) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                float r[QPT], g[QPT];
+#pragma unroll
+                for (int j = 0; j < QPT; ++j) r[j] = rr[s];
+                sph_g_vec<QPT, true>(q, th, tl, r, g);
+#pragma unroll
+                for (int j = 0; j < QPT; ++j) d[s][j] = (g[j] * g[j]) * aa[s];
+            }
+        } else {
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                float r[QPT], g[QPT];
+#pragma unroll
+                for (int j = 0; j < QPT; ++j) r[j] = rr[s];
+                sph_g_vec<QPT, false>(q, th, tl, r, g);
+#pragma unroll
+                for (int j = 0; j < QPT; ++j) d[s][j] = (g[j] * g[j]) * aa[s];
+            }
+        }
     }
     template <int QPT>
     __device__ __forceinline__ static void diffS(const Contrib<float> &cn, const Contrib<float> &co,
@@ -162,11 +219,31 @@ template <> struct FastOps<MCSAS_SPHERE> {
 #pragma unroll
         for (int j = 0; j < 2 * QPT; ++j) g[j] = g[j] * g[j];
 #pragma unroll
-        for (int j = 0; j < QPT; ++j) g[QPT + j] = g[QPT + j] * co.c[1];
+        for (int j = 0; j < QPT; ++j) g[QPT + j] = g[QPT + j] * co.c[2];
 #pragma unroll
-        for (int j = 0; j < QPT; ++j) d[j] = fmaf(g[j], cn.c[1], -g[QPT + j]);
+        for (int j = 0; j < QPT; ++j) d[j] = fmaf(g[j], cn.c[2], -g[QPT + j]);
     }
 };
+
+// one thread's slice of a cached contribution row: QPT contiguous floats, one vector access
+template <int QPT> __device__ __forceinline__ void row_load(const float *p, float (&v)[QPT])
+{
+    if (QPT == 4) { const float4 x = __ldcg((const float4 *)p); v[0] = x.x; v[1] = x.y; v[2 % QPT] = x.z; v[3 % QPT] = x.w; }
+    else if (QPT == 2) { const float2 x = __ldcg((const float2 *)p); v[0] = x.x; v[1 % QPT] = x.y; }
+    else {
+#pragma unroll
+        for (int j = 0; j < QPT; ++j) v[j] = __ldcg(p + j);
+    }
+}
+template <int QPT> __device__ __forceinline__ void row_store(float *p, const float (&v)[QPT])
+{
+    if (QPT == 4) __stcg((float4 *)p, make_float4(v[0], v[1], v[2 % QPT], v[3 % QPT]));
+    else if (QPT == 2) __stcg((float2 *)p, make_float2(v[0], v[1 % QPT]));
+    else {
+#pragma unroll
+        for (int j = 0; j < QPT; ++j) __stcg(p + j, v[j]);
+    }
+}
 
 struct FastDec {
     int kstar;
@@ -258,7 +335,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     const int RING = a.ring;
     const int kmax = a.spec_max;
     const int RL = QPT * TQ;                       // cached row length of this CTA
-    float *const crow = CACHE ? a.cache + (size_t)slot * a.cache_stride + (size_t)rank * N * RL + qtid : nullptr;
+    float *const crow = CACHE ? a.cache + (size_t)slot * a.cache_stride + (size_t)rank * N * RL + qtid * QPT : nullptr;
 
     // ---- shared memory carve-up (keep in sync with fast_smem_bytes) -----------------------
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -307,7 +384,8 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     const QuadTab<float> qt = { D, a.mp.quad_rule, s_qx, s_qw };
     const float qref = (float)(ds.q_ref * 1e-9);   // 1/nm
 
-    // ---- per-thread resident state of q point (j*C + rank)*TQ + qtid ----------------------
+    // ---- per-thread resident state of q points (rank*TQ + qtid)*QPT + j, j < QPT (contiguous:
+    //      a thread's row slice is one 4/8/16-byte load) --------------------------------------
     // intensities are normalised by i_scale; sw = 1/sigma, In = I (normalised), ft = model (fp64)
     QRep<float> Q[QPT];
     float cq[QPT], rho[QPT], mu[QPT], om[QPT];
@@ -316,7 +394,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     double v3[3] = {0., 0., 0.};
 #pragma unroll
     for (int j = 0; j < QPT; ++j) {
-        int i = (j * C + rank) * TQ + qtid;
+        int i = (rank * TQ + qtid) * QPT + j;
         bool valid = i < nq;
         int ii = (i < nq) ? i : nq - 1;
         double qv = s_data[ii], Iv = s_data[ds.nq_pad + ii] * inorm, ev = s_data[2 * ds.nq_pad + ii] * inorm;
@@ -334,7 +412,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         om[j] = (float)swd;
         rho[j] = 0.f; mu[j] = 0.f;
         if (grp == 0) {
-            const int ql = j * TQ + qtid;
+            const int ql = qtid * QPT + j;
             s_qs[ql] = qsf; s_sw[ql] = swd; s_In[ql] = Iv;
             double w = swd * swd;
             v3[0] += w; v3[1] += w * Iv; v3[2] += w * Iv * Iv;
@@ -393,7 +471,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         if (grp == 0) {
 #pragma unroll
             for (int j = 0; j < QPT; ++j) {
-                const int ql = j * TQ + qtid;
+                const int ql = qtid * QPT + j;
                 const double f = s_ft[cur * FAST_QCAP + ql], sq = s_sw[ql];
                 double w = sq * sq, t = w * f;
                 v[0] += t; v[1] = fma(t, f, v[1]); v[2] = fma(t, s_In[ql], v[2]);
@@ -405,7 +483,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         if (grp == 0) {
 #pragma unroll
             for (int j = 0; j < QPT; ++j) {
-                const int ql = j * TQ + qtid;
+                const int ql = qtid * QPT + j;
                 double r = s_sw[ql] * (s_In[ql] - (s_ft[cur * FAST_QCAP + ql] * sa + sb));
                 r2[0] = fma(r, r, r2[0]);
             }
@@ -489,10 +567,8 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     float dv[QPT];
                     FO::template evalN<QPT>(cc, nd, qt, Q, dv);
 #pragma unroll
-                    for (int j = 0; j < QPT; ++j) {
-                        ft0[j] += (double)dv[j] * (double)s_qs[j * TQ + qtid];
-                        if (CACHE && grp == 0) __stcg(crow + (size_t)(i0 + e) * RL + j * TQ, dv[j]);
-                    }
+                    for (int j = 0; j < QPT; ++j) ft0[j] += (double)dv[j] * (double)s_qs[qtid * QPT + j];
+                    if (CACHE && grp == 0) row_store<QPT>(crow + (size_t)(i0 + e) * RL, dv);
                 }
             }
             __syncthreads();
@@ -500,7 +576,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         evals += N;
         if (grp == 0) {
 #pragma unroll
-            for (int j = 0; j < QPT; ++j) s_ft[j * TQ + qtid] = ft0[j];
+            for (int j = 0; j < QPT; ++j) s_ft[qtid * QPT + j] = ft0[j];
         }
         lsq_all(sc_a, sc_b, conval);                             // mcsas.py:339-344
         if (!resume) { conval0 = conval; step = 0; moves = 0; }
@@ -509,7 +585,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         double a0 = sc_a, b0 = sc_b;
 #pragma unroll
         for (int j = 0; j < QPT; ++j) {
-            const int ql = j * TQ + qtid;
+            const int ql = qtid * QPT + j;
             const double sq = s_sw[ql];
             rho[j] = (float)(sq * (s_In[ql] - (a0 * ft0[j] + b0)));
             mu[j] = (float)(sq * ft0[j]);
@@ -544,13 +620,14 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             }
             ++batch;
             bool wd = Kb < 1 || batch > wd_batches;               // watchdog: never loop forever
+            const int ri0 = (int)((uint32_t)step % (uint32_t)N);  // contribution replaced by the batch's first step
             const long long pt1 = a.prof ? clock64() : 0;
             // ---- exact base sums of the current state (after an accepted move) ---------------
             if (dirty && grp == 0) {
                 double b5[5] = {0., 0., 0., 0., 0.};
 #pragma unroll
                 for (int j = 0; j < QPT; ++j) {
-                    const int ql = j * TQ + qtid;
+                    const int ql = qtid * QPT + j;
                     const double sq = s_sw[ql];
                     double m = sq * s_ft[cur * FAST_QCAP + ql];
                     double r = sq * s_In[ql] - (a0 * m + b0 * sq);
@@ -577,7 +654,6 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             // pinned in a register: ptxas otherwise re-reads %tid (S2R) for every proposal slot
             int perm = grp_perm<FGRP>(lane);
             asm volatile("mov.b32 %0, %0;" : "+r"(perm));
-            const int ri0 = (int)((uint32_t)step % (uint32_t)N);  // contribution replaced by the batch's first step
             float uu[FGRP][QPT];                                 // GRAM: (new - old)/sigma of slot s
             if (!wd) {
                 if (gram) {
@@ -590,8 +666,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                         for (int s = 0; s < FGRP; ++s) {
                             int ri = ri0 + (s ^ perm);
                             if (ri >= N) ri -= N;
-#pragma unroll
-                            for (int j = 0; j < QPT; ++j) od[CACHE ? s : 0][j] = __ldcg(crow + (size_t)ri * RL + j * TQ);
+                            row_load<QPT>(crow + (size_t)ri * RL, od[CACHE ? s : 0]);
                         }
                     }
 #pragma unroll
@@ -669,15 +744,13 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                             for (int s = 0; s < FGRP; ++s) {
                                 int ri = ri0 + k0 + (s ^ perm);
                                 if (ri >= N) ri -= N;
-#pragma unroll
-                                for (int j = 0; j < QPT; ++j) od[CACHE ? s : 0][j] = __ldcg(crow + (size_t)ri * RL + j * TQ);
+                                row_load<QPT>(crow + (size_t)ri * RL, od[CACHE ? s : 0]);
                             }
+                            int ent[FGRP];
 #pragma unroll
-                            for (int s = 0; s < FGRP; ++s) {
-                                const int e = (e0 + k0 + (s ^ perm)) & (RING - 1);
-                                const Contrib<float> cn = s_ring[e].cn;
-                                FO::template evalN<QPT>(cn, s_nodes + (size_t)(e * 2) * NSTR, qt, Q, dn[CACHE ? s : 0]);
-                            }
+                            for (int s = 0; s < FGRP; ++s) ent[s] = (e0 + k0 + (s ^ perm)) & (RING - 1);
+                            FO::template evalChunk<QPT, CACHE ? FGRP : 1>(s_ring, (const int (&)[CACHE ? FGRP : 1])ent,
+                                                                          s_nodes, NSTR, qt, Q, dn);
                         }
 #pragma unroll
                         for (int s = 0; s < FGRP; ++s) {
@@ -731,8 +804,10 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                             int ri = ri0 + k;
                             if (ri >= N) ri -= N;
                             FO::template evalN<QPT>(cn, nn, qt, Q, dd);
+                            float ov[QPT];
+                            row_load<QPT>(crow + (size_t)ri * RL, ov);
 #pragma unroll
-                            for (int j = 0; j < QPT; ++j) dd[j] -= __ldcg(crow + (size_t)ri * RL + j * TQ);
+                            for (int j = 0; j < QPT; ++j) dd[j] -= ov[j];
                         } else {
                             FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd);
                         }
@@ -939,7 +1014,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     sc_a = a0; sc_b = b0;
 #pragma unroll
                     for (int j = 0; j < QPT; ++j) {
-                        const int ql = j * TQ + qtid;
+                        const int ql = qtid * QPT + j;
                         const double sq = s_sw[ql];
                         double du = 0.;
 #pragma unroll
@@ -960,8 +1035,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                             if (ri >= N) ri -= N;
                             float dv[QPT];
                             FO::template evalN<QPT>(s_ring[e].cn, s_nodes + (size_t)(e * 2) * NSTR, qt, Q, dv);
-#pragma unroll
-                            for (int j = 0; j < QPT; ++j) __stcg(crow + (size_t)ri * RL + j * TQ, dv[j]);
+                            row_store<QPT>(crow + (size_t)ri * RL, dv);
                         }
                     }
                     if (tid < FGRP * P) {
@@ -987,21 +1061,19 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                 const int rix = (int)((uint32_t)(step + kstar) % (uint32_t)N);
                 float dd[QPT];
                 if (CACHE) {
-                    float dv[QPT];
+                    float dv[QPT], ov[QPT];
+                    row_load<QPT>(crow + (size_t)rix * RL, ov);   // in flight during the evaluation
                     FO::template evalN<QPT>(cn, nn, qt, Q, dv);
 #pragma unroll
-                    for (int j = 0; j < QPT; ++j) dd[j] = dv[j] - __ldcg(crow + (size_t)rix * RL + j * TQ);
+                    for (int j = 0; j < QPT; ++j) dd[j] = dv[j] - ov[j];
                     if (PS > 1) named_bar_sync(1, T);            // every group has read the old row
-                    if (grp == 0) {
-#pragma unroll
-                        for (int j = 0; j < QPT; ++j) __stcg(crow + (size_t)rix * RL + j * TQ, dv[j]);
-                    }
+                    if (grp == 0) row_store<QPT>(crow + (size_t)rix * RL, dv);
                 } else {
                     FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd);
                 }
 #pragma unroll
                 for (int j = 0; j < QPT; ++j) {
-                    const int ql = j * TQ + qtid;
+                    const int ql = qtid * QPT + j;
                     const double f = s_ft[cur * FAST_QCAP + ql] + (double)dd[j] * (double)s_qs[ql];
                     const double sq = s_sw[ql];
                     if (grp == 0) s_ft[(cur ^ 1) * FAST_QCAP + ql] = f;      // other groups still read `cur`
@@ -1051,10 +1123,10 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     if (grp == 0) {
 #pragma unroll
         for (int j = 0; j < QPT; ++j) {
-            int i = (j * C + rank) * TQ + qtid;
+            int i = (rank * TQ + qtid) * QPT + j;
             if (i < nq)
                 a.fit_meas[(long long)chain * a.nq_stride + i] =
-                    (s_ft[cur * FAST_QCAP + j * TQ + qtid] * sc_a + sc_b) * ds.i_scale;                 // mcsas.py:429
+                    (s_ft[cur * FAST_QCAP + qtid * QPT + j] * sc_a + sc_b) * ds.i_scale;                 // mcsas.py:429
         }
     }
     if (tid == 0 && rank == 0) {

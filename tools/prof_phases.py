@@ -7,8 +7,8 @@ from mcsas_b200 import Engine, synth, FP32
 os.environ["MCSAS_B200_PROF"] = "1"
 q, I, sig = synth.sphere_curve(nq=1000)
 runs = []
-for qpt in ("4", "2", "1"):
-    for cache in ("1", "0"):
+for qpt in ("4", "2"):
+    for cache in ("1",):
         runs.append(("qpt %s cache %s" % (qpt, cache), {"MCSAS_B200_QPT": qpt, "MCSAS_B200_CACHE": cache, "MCSAS_B200_CLUSTER": "1"}))
 if len(sys.argv) > 1:
     runs = [("default", {})]
