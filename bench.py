@@ -3,8 +3,8 @@
 """bench.py -- MC steps/s of the McSAS fitting core on B200 (BASELINE.json metric).
 
 Workload (configs[1]): Sphere model, synthetic 1000-point q curve, nContribs=300,
-nRep=100 per GPU, convergenceCriterion=1, production mode (fp32 form factors, fp64 LSQ,
-in-kernel Philox).  One bench "step" = one complete McSAS.analyse of the 100
+nRep=100 per GPU, convergenceCriterion=1, production mode (fp32 form factors and delta
+sums, fp64 base sums / fit, in-kernel Philox).  One bench "step" = one complete McSAS.analyse of the 100
 repetitions (a fresh seed per step); MC steps = sum of numIter over all chains.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
@@ -27,7 +27,8 @@ sys.path.insert(0, ROOT)
 
 NQ, N_CONTRIBS, N_REPS = 1000, 300, 100
 RADIUS_RANGE = (1e-9, 100e-9)
-MUFU_PER_STEP = 6 * NQ          # 2 evaluations x (sin, cos, rcp) per q point
+MUFU_PER_STEP = 6 * NQ          # 2 evaluations x (sin, cos, rcp) per q point (algorithmic)
+MUFU_EXECUTED_PER_STEP = 2 * NQ # what the kernel issues: 1 evaluation x (sin, cos); the old row is cached
 FLOP_PER_STEP = 44 * NQ         # ~14 flop per evaluation + 16 flop LSQ per q point
 METRIC = "MC steps/s (nRep=100 sphere fit, 1000 q, 300 contributions)"
 
@@ -110,7 +111,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = host_threads()
-    per_chain = 4000
+    per_chain = 20000
     vals, tot_t = [], 0.0
     for i in range(args.warmup + args.steps):
         v, el = oracle_cpu_steps_per_s(per_chain, threads)
@@ -190,13 +191,16 @@ def main():
         t0 = time.perf_counter()
         algo.analyse()                       # upload (H2D) + chains + fetch (D2H)
         res = algo.result[0]
+        launches[0] += algo.engine.run_info()["launches"]
         if gather and world > 1:
             algo.gatherResults()             # NCCL all_gather of the contribution sets
         t1 = time.perf_counter()
         return res, algo.lastKernelMs, t1 - t0
 
+    launches = [0]
     for i in range(args.warmup):
         one_step(i, True)
+    launches[0] = 0
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -238,7 +242,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "MC steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": kern_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 form factors / f64 LSQ sums", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "configs[1]: Sphere, synthetic 1000-point q curve, nContribs=300, "
                                    "nRep=100 per GPU, convergenceCriterion=1",
                        "nq": NQ, "n_contribs": N_CONTRIBS, "n_reps_per_gpu": N_REPS,
@@ -252,23 +256,25 @@ def main():
             "e2e": {"value": e2e_value, "unit": "MC steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps},
             "wall_s": wall,
-            "gpu_launches": args.steps,      # one persistent chain kernel per analyse()
+            "gpu_launches": launches[0],     # chain-kernel time slices launched in the timed region (rank 0)
             "clocks": clocks,
             "roofline": {"bound": "sfu", "achieved": mufu_ach, "peak": peaks["mufu_gops"],
                          "unit": "GMUFU/s", "frac": mufu_ach / peaks["mufu_gops"],
-                         "traffic": None,
+                         "traffic": 2.9e9,    # ncu dram read+write bytes of one time-slice launch (profiles/)
+                         "executed_mufu_frac": per_gpu * MUFU_EXECUTED_PER_STEP * 1e-9 / peaks["mufu_gops"],
                          "peak_source": "measured live: mcsas_measure_peaks (sin+cos+rcp MUFU mix)",
                          "fp32": {"achieved": fp32_ach, "peak": peaks["ffma_tflops"],
                                   "unit": "TFLOP/s", "frac": fp32_ach / peaks["ffma_tflops"]},
-                         "hbm_note": "HBM traffic ~0: 24 KB in, 1.1 MB out per launch",
+                         "hbm_note": "not HBM bound: the contribution-row cache streams ~0.75 TB/s of "
+                                     "6.55 TB/s measured (MEASURED_PEAKS.json); inputs/outputs are 24 KB / 1.1 MB per fit",
                          "sm_count": info["sm_count"], "ctas": N_REPS},
         }
         if not args.no_cpu_baseline and world == 1:
             threads = host_threads()
-            v, el = oracle_cpu_steps_per_s(4000, threads)
+            v, el = oracle_cpu_steps_per_s(150000, threads)
             line["cpu_baseline"] = {
                 "value": v, "unit": "MC steps/s", "cores": threads, "kind": "port",
-                "sample": "%d threads x 1 chain x 4000 MC steps of the same workload (%.1f s); "
+                "sample": "%d threads x 1 chain x 150000 MC steps of the same workload (%.1f s); "
                           "oracle/mcsas_oracle.c" % (threads, el)}
         print(json.dumps(line))
     if world > 1:

@@ -655,6 +655,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             int perm = grp_perm<FGRP>(lane);
             asm volatile("mov.b32 %0, %0;" : "+r"(perm));
             float uu[FGRP][QPT];                                 // GRAM: (new - old)/sigma of slot s
+            float dnk[CACHE ? FGRP : 1][QPT];                    // GRAM + CACHE: new row of slot s
             if (!wd) {
                 if (gram) {
                     // every group evaluates the chunk (all need uu for the update); group 0 reports
@@ -668,6 +669,11 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                             if (ri >= N) ri -= N;
                             row_load<QPT>(crow + (size_t)ri * RL, od[CACHE ? s : 0]);
                         }
+                        int ent[FGRP];
+#pragma unroll
+                        for (int s = 0; s < FGRP; ++s) ent[s] = (e0 + (s ^ perm)) & (RING - 1);
+                        FO::template evalChunk<QPT, CACHE ? FGRP : 1>(s_ring, (const int (&)[CACHE ? FGRP : 1])ent,
+                                                                      s_nodes, NSTR, qt, Q, dnk);
                     }
 #pragma unroll
                     for (int i = 0; i < NGP; ++i) gq[i] = 0.f;
@@ -679,9 +685,8 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                         const float *nn = s_nodes + (size_t)(e * 2) * NSTR, *no = nn + NSTR;
                         float dd[QPT];
                         if (CACHE) {
-                            FO::template evalN<QPT>(cn, nn, qt, Q, dd);
 #pragma unroll
-                            for (int j = 0; j < QPT; ++j) dd[j] -= od[CACHE ? s : 0][j];
+                            for (int j = 0; j < QPT; ++j) dd[j] = dnk[CACHE ? s : 0][j] - od[CACHE ? s : 0][j];
                         } else {
                             FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd);
                         }
@@ -1028,14 +1033,12 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     }
                     cur ^= 1;
                     if (CACHE && grp == 0) {                     // rows of the accepted contributions
-                        for (int k = 0; k < FGRP; ++k) {
-                            if (!((accmask >> k) & 1)) continue;
-                            const int e = ((int)step + k) & (RING - 1);
-                            int ri = ri0 + k;
+#pragma unroll
+                        for (int s = 0; s < FGRP; ++s) {
+                            if (!((accmask >> (s ^ perm)) & 1)) continue;
+                            int ri = ri0 + (s ^ perm);
                             if (ri >= N) ri -= N;
-                            float dv[QPT];
-                            FO::template evalN<QPT>(s_ring[e].cn, s_nodes + (size_t)(e * 2) * NSTR, qt, Q, dv);
-                            row_store<QPT>(crow + (size_t)ri * RL, dv);
+                            row_store<QPT>(crow + (size_t)ri * RL, dnk[CACHE ? s : 0]);
                         }
                     }
                     if (tid < FGRP * P) {
