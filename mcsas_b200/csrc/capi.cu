@@ -68,6 +68,7 @@ struct mcsas_ctx {
     int *d_ids = nullptr;
     long long *d_prof = nullptr;
     float *d_cache = nullptr;
+    int *d_cache_lock = nullptr;
     size_t cache_cap = 0;
     int n_live = 0, n_launches = 0, last_cluster = 1, last_threads = 0, last_qpt = 0, last_resident = 0;
     float kernel_ms = 0.f;
@@ -131,7 +132,7 @@ extern "C" void mcsas_ctx_destroy(mcsas_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_sets); cudaFree(ctx->d_data); cudaFree(ctx->d_quad); cudaFree(ctx->d_stream);
     cudaFree(ctx->d_rset); cudaFree(ctx->d_fit); cudaFree(ctx->d_scal); cudaFree(ctx->d_cnt);
-    cudaFree(ctx->d_att); cudaFree(ctx->d_tacc); cudaFree(ctx->d_tchi); cudaFree(ctx->d_ids); cudaFree(ctx->d_prof); cudaFree(ctx->d_cache);
+    cudaFree(ctx->d_att); cudaFree(ctx->d_tacc); cudaFree(ctx->d_tchi); cudaFree(ctx->d_ids); cudaFree(ctx->d_prof); cudaFree(ctx->d_cache); cudaFree(ctx->d_cache_lock);
     cudaFreeHost(ctx->h_stop);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
@@ -448,8 +449,7 @@ static int plan_chain_fp32(mcsas_ctx *ctx, int nq, int n_live, ChainPlan *out)
             if (threads > FAST_MAX_EVAL_THREADS[l] || threads / 32 > FAST_MAX_WARPS) continue;
             int resident = 0;
             query_resident(ctx, c, l, threads, &resident);
-            if (resident < 1) continue;
-            if (resident < n_live && forced_c <= 0 && oi + 1 < no) continue;       // prefer one wave
+            if (resident < 1) continue;                                            // more chains than fit: waves
             best.cluster = c; best.layout = l; best.threads = threads; best.resident = resident; best.warps_q = wq;
         }
     }
@@ -523,6 +523,10 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     };
     while (ring > 4 && smem_of(ring) > smem_limit) ring /= 2;
     size_t smem = smem_of(ring);
+    // fp32 kernel: one CTA per SM (its contribution-row cache region is indexed by the SM id):
+    // ask for more than half of an SM's shared memory
+    if (cfg->precision == MCSAS_FP32 && smem < (size_t)120 * 1024 && smem_limit >= (size_t)120 * 1024)
+        smem = (size_t)120 * 1024;
     if (smem > smem_limit)
         return fail(ctx, MCSAS_ERR_ARG, "run: configuration needs %zu B shared memory (> %zu)", smem, smem_limit);
     int kcap = cfg->spec_max <= 0 ? MCSAS_MAX_SPEC : (cfg->spec_max > MCSAS_MAX_SPEC ? MCSAS_MAX_SPEC : cfg->spec_max);
@@ -603,20 +607,21 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     a.trace_chi = cfg->record_trace ? ctx->d_tchi : nullptr;
     a.cache = nullptr;
     if (cfg->precision == MCSAS_FP32 && !(getenv("MCSAS_B200_CACHE") && atoi(getenv("MCSAS_B200_CACHE")) == 0)) {
-        // contribution-row cache: one row of padded q points per contribution and chain slot
-        const size_t stride = (size_t)N * (((size_t)ctx->nq_max + 128 * MAX_CLUSTER + 3) & ~(size_t)3);   // 16-byte aligned rows
-        const size_t need = stride * (size_t)n_chains;
-        if (need * sizeof(float) <= ((size_t)8 << 30)) {        // beyond 8 GB: recompute instead
-            if (need > ctx->cache_cap) { CK(regrow(&ctx->d_cache, need)); ctx->cache_cap = need; }
-            a.cache = ctx->d_cache;
-            a.cache_stride = (long long)stride;
-        }
+        // contribution-row cache: n_contribs rows of FAST_QCAP floats per SM (a CTA owns its SM)
+        const size_t stride = (size_t)N * FAST_QCAP;
+        const size_t need = stride * FAST_CACHE_SMS;
+        if (need > ctx->cache_cap) { CK(regrow(&ctx->d_cache, need)); ctx->cache_cap = need; }
+        if (!ctx->d_cache_lock) CK(cudaMalloc(&ctx->d_cache_lock, sizeof(int) * FAST_CACHE_SMS));
+        CK(cudaMemsetAsync(ctx->d_cache_lock, 0, sizeof(int) * FAST_CACHE_SMS, ctx->stream));
+        a.cache = ctx->d_cache;
+        a.cache_stride = (long long)stride;
+        a.cache_lock = ctx->d_cache_lock;
     }
     if (getenv("MCSAS_B200_PROF") && cfg->precision == MCSAS_FP32) {
         cudaFree(ctx->d_prof);
         ctx->d_prof = nullptr;
-        CK(cudaMalloc(&ctx->d_prof, sizeof(long long) * 32 * n_chains));
-        CK(cudaMemset(ctx->d_prof, 0, sizeof(long long) * 32 * n_chains));
+        CK(cudaMalloc(&ctx->d_prof, sizeof(long long) * 48 * n_chains));
+        CK(cudaMemset(ctx->d_prof, 0, sizeof(long long) * 48 * n_chains));
         a.prof = ctx->d_prof;
     }
     ctx->args = a;
@@ -681,13 +686,13 @@ extern "C" int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms)
         if (rc) return rc;
     }
     if (ctx->args.prof) {                                 // phase profile (experiments only)
-        std::vector<long long> h((size_t)32 * ctx->n_chains);
+        std::vector<long long> h((size_t)48 * ctx->n_chains);
         CK(cudaMemcpy(h.data(), ctx->args.prof, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
         static const char *nm[6] = {"ring-wait", "refresh+eval", "B1", "exchange+decide", "B2", "update"};
         for (int m = 0; m < 2; ++m) {
-            long long tot[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+            long long tot[24] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
             for (int c = 0; c < ctx->n_chains; ++c)
-                for (int i = 0; i < 16; ++i) tot[i] += h[((size_t)c * 2 + m) * 16 + i];
+                for (int i = 0; i < 24; ++i) tot[i] += h[((size_t)c * 2 + m) * 24 + i];
             if (!tot[6]) continue;
             fprintf(stderr, "[mcsas_b200 prof] %s batches %lld steps %lld (%.1f steps/batch), cycles/batch:",
                     m ? "GRAM" : "SPEC", tot[6], tot[7], (double)tot[7] / tot[6]);
@@ -697,6 +702,9 @@ extern "C" int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms)
             fprintf(stderr, "[mcsas_b200 prof]    refresh %.0f/batch, first chunk %.0f (n %lld), later chunks %.0f each (n %lld)\n",
                     (double)tot[8] / tot[6], tot[11] ? (double)tot[9] / tot[11] : 0., tot[11],
                     tot[12] ? (double)tot[10] / tot[12] : 0., tot[12]);
+            fprintf(stderr, "[mcsas_b200 prof]    decide: pre %.0f, base sums %.0f, proposal sums %.0f, solve+select %.0f, publish %.0f\n",
+                    (double)tot[13] / tot[6], (double)tot[14] / tot[6], (double)tot[15] / tot[6], (double)tot[16] / tot[6],
+                    (double)tot[17] / tot[6]);
         }
     }
     if (kernel_ms) *kernel_ms = ctx->kernel_ms;

@@ -335,7 +335,11 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     const int RING = a.ring;
     const int kmax = a.spec_max;
     const int RL = QPT * TQ;                       // cached row length of this CTA
-    float *const crow = CACHE ? a.cache + (size_t)slot * a.cache_stride + (size_t)rank * N * RL + qtid * QPT : nullptr;
+    // one row region per SM: every layout of this kernel fills the register file of an SM, so
+    // a CTA has its SM to itself; the lock word only guards that assumption
+    unsigned smid = 0;
+    if (CACHE) asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    float *const crow = CACHE ? a.cache + (size_t)smid * a.cache_stride + qtid * QPT : nullptr;
 
     // ---- shared memory carve-up (keep in sync with fast_smem_bytes) -----------------------
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -366,6 +370,10 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     float *s_nodes = (float *)sp;                  // [RING][2][NARR][D]
     const size_t NSTR = (size_t)NARR * D;
 
+    if (CACHE && tid == 0) {
+        while (atomicCAS(a.cache_lock + smid, 0, 1) != 0) __nanosleep(200);
+        __threadfence();
+    }
     // ---- stage the dataset once: TMA bulk copy global -> shared ---------------------------
     if (tid == 0) { mbar_init(s_bar, 1); mbar_init(s_xbar, 1); mbar_init(s_xbar + 1, 1); s_dec->wd = 0; }
     unsigned xphase = 0;
@@ -889,7 +897,9 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                 }
                 xphase ^= 1u << abuf;
             }
+            long long pd[4] = {0, 0, 0, 0};
             if (warp == 0) {
+                if (a.prof) pd[0] = clock64();
                 if (dirty) {                                     // fresh base sums (identical in all lanes)
                     double b5[5] = {0., 0., 0., 0., 0.};
                     if (C > 1) {
@@ -907,6 +917,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     // chi2 at the centre exceeds the minimum by O(1e-14) relative
                     conval = B.E0 * L.inv_nq;
                 }
+                if (a.prof) pd[1] = clock64();
                 double s1 = 0., s2 = 0., s3 = 0., s4 = 0.;
                 const bool mine = lane < Kb && !wd;
                 if (mine) {
@@ -924,6 +935,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                         s1 = t4.x; s2 = t4.y; s3 = t4.z; s4 = t4.w;
                     }
                 }
+                if (a.prof) pd[2] = clock64();
                 int ks = -1, accmask = 0;
                 double ca = a0, cb = b0, cc = conval;
                 if (!gram) {
@@ -986,6 +998,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     }
                     ks = accmask ? 0 : -1;
                 }
+                if (a.prof) pd[3] = clock64();
                 if (lane == 0) {
                     s_dec->kstar = ks;
                     s_dec->accmask = accmask;
@@ -1096,7 +1109,9 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             step += used;                                        // :403-404 (ri = step % N)
             steps_all += used;
             if (a.prof && tid == 0 && rank == 0) {               // phase cycles of warp 0 (tools/prof)
-                long long *pp = a.prof + ((long long)chain * 2 + (gram ? 1 : 0)) * 16;
+                long long *pp = a.prof + ((long long)chain * 2 + (gram ? 1 : 0)) * 24;
+                pp[16] += pd[3] - pd[2]; pp[17] += pt4 - pd[3];
+                pp[13] += pd[0] - pt3; pp[14] += pd[1] - pd[0]; pp[15] += pd[2] - pd[1]; pp[5] += 0;
                 pp[8] += pt1a - pt1; pp[9] += ptc[0]; pp[10] += ptc[1]; pp[11] += ptc[2]; pp[12] += ptc[3];
                 pp[0] += pt1 - pt0; pp[1] += pt2 - pt1; pp[2] += pt3 - pt2; pp[3] += pt4 - pt3;
                 pp[4] += pt5 - pt4; pp[5] += clock64() - pt5; pp[6] += 1; pp[7] += used;
@@ -1145,6 +1160,10 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         a.attempts[chain] = attempt + 1;
         a.elapsed_s[chain] = (a.resume ? a.elapsed_s[chain] : 0.) + 1e-9 * (double)(globaltimer_ns() - t_start);
         a.status[chain] = status;
+    }
+    if (CACHE) {
+        __syncthreads();
+        if (tid == 0) { __threadfence(); atomicExch(a.cache_lock + smid, 0); }
     }
     if (C > 1) cluster_sync_all();
 }

@@ -73,8 +73,9 @@ struct ChainArgs {
     int *attempts;
     unsigned char *trace_accept; // [chain][max_iter] or NULL
     double *trace_chi;           // [chain][max_iter] or NULL
-    float *cache;                // fp32 kernel: NULL or [launch slot][cache_stride] contribution rows
-    long long cache_stride;      // floats per launch slot (>= n_contribs * padded nq)
+    float *cache;                // fp32 kernel: NULL or [SM id][cache_stride] contribution rows
+    long long cache_stride;      // floats per SM (n_contribs * FAST_QCAP)
+    int *cache_lock;             // [SM id] 0 = free
     long long *prof;             // NULL or [chain][2][8] phase cycle counters (MCSAS_B200_PROF)
 };
 
@@ -128,6 +129,7 @@ __host__ __device__ inline size_t chain_smem_bytes(int nq_pad, int N, int P, int
 // ---- shared-memory footprint of chain_fast_kernel (mirrors its carve-up) -----------------------------
 #define FAST_MAX_WARPS 32
 #define FAST_XU (2 * KCAP + 8 + 16) // 64-bit units per rank in a cluster exchange buffer
+#define FAST_CACHE_SMS 256         // row regions allocated (>= %nsmid of a B200)
 #define FAST_QCAP 1024            // q points per CTA (QPT * 32 * warps_q)
 __host__ __device__ inline size_t fast_smem_bytes(int nq_pad, int N, int P, int D, int narr, int ring)
 {
