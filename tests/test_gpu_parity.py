@@ -168,3 +168,70 @@ def test_missing_device_or_bad_args_fail_loudly():
     with pytest.raises(McSASB200Error):
         eng.run(Engine.make_config())          # no datasets / model
     eng.close()
+
+
+@pytest.mark.parametrize("name", ["sphere_small", "sphere_nobg", "sphere_posbg", "sphcs_small", "cyl_small"])
+@pytest.mark.parametrize("spec_max,cluster", [(1, 1), (32, 1), (32, 2), (8, 4)])
+def test_fp32_chain_tracks_fp64_chain(name, spec_max, cluster):
+    """Production kernel (fp32 residual-delta sums, Gram batches, cached rows) against the
+    fp64 parity kernel on the SAME Philox stream: identical accept/reject sequence over the
+    first steps and the chi-squared trace within 1e-4 (fp32 form factors)."""
+    from mcsas_b200 import Engine
+    g = common.load_chain(name)
+    om = common.oracle_model(g)
+    max_iter = min(int(g["max_iter"]), 1500)
+
+    def run(prec, spec, cl):
+        eng = gpu_common.engine_for(om, [(g["q"], g["I"], g["sigma"])])
+        cfg = Engine.make_config(n_contribs=g["N"], n_reps=2, conv_crit=float(g["conv_crit"]),
+                                 max_iter=max_iter, max_retries=-1, comp_exp=float(g["comp_exp"]),
+                                 find_background=g["find_background"],
+                                 positive_background=g["positive_background"],
+                                 precision=prec, seed=424242, record_trace=True, spec_max=spec,
+                                 cluster_size=cl)
+        eng.run(cfg)
+        out = eng.fetch()
+        tr = [eng.fetch_trace(r, max_iter) for r in range(2)]
+        eng.close()
+        return out, tr
+
+    ref, rtr = run(FP64, 32, 1)
+    out, tr = run(FP32, spec_max, cluster)
+    for r in range(2):
+        n = min(int(out["num_iter"][0, r]), int(ref["num_iter"][0, r]))
+        assert n >= 100
+        acc, chi = tr[r][0][:n], tr[r][1][:n]
+        racc, rchi = rtr[r][0][:n], rtr[r][1][:n]
+        differ = np.nonzero(acc != racc)[0]
+        first = int(differ[0]) if differ.size else n
+        assert first >= min(n, 300), (first, n)            # marginal flips may appear much later
+        np.testing.assert_allclose(chi[:first], rchi[:first], rtol=1e-4)
+        assert abs(out["conval0"][0, r] / ref["conval0"][0, r] - 1) < 1e-5
+
+
+def test_many_chains_run_in_waves_and_do_not_depend_on_packing():
+    """More chains than SMs (3 datasets x 100 repetitions): the launch runs in waves; with a
+    fixed layout every chain's result depends only on (seed, global chain id), not on which
+    other chains share the launch."""
+    from mcsas_b200 import Engine
+    g = common.load_chain("sphere_cfg1")
+    om = common.oracle_model(g)
+    sets = [(g["q"], g["I"] * s, g["sigma"] * s) for s in (1.0, 2.0, 0.5)]
+    kw = dict(n_contribs=100, conv_crit=1.0, max_iter=2000, max_retries=-1, precision=FP32,
+              seed=77, cluster_size=1)
+    eng = gpu_common.engine_for(om, sets)
+    eng.run(Engine.make_config(n_reps=100, **kw))
+    big = eng.fetch()
+    eng.close()
+    assert np.isfinite(big["conval"]).all() and (big["num_iter"] == 2000).all()
+    eng = gpu_common.engine_for(om, sets[:1])
+    eng.run(Engine.make_config(n_reps=100, **kw))
+    one = eng.fetch()
+    eng.close()
+    np.testing.assert_array_equal(big["contribs"][0], one["contribs"][0])
+    np.testing.assert_array_equal(big["conval"][0], one["conval"][0])
+    # the other datasets are the same curve scaled by 2 and 0.5: chi-squared is scale invariant,
+    # so their (different) chains reach the same quality of fit and proportional scalings
+    assert abs(np.median(big["conval"][1]) / np.median(big["conval"][0]) - 1) < 0.2
+    assert abs(np.median(big["scaling"][1]) / np.median(big["scaling"][0]) - 2.0) < 0.2
+    assert abs(np.median(big["scaling"][2]) / np.median(big["scaling"][0]) - 0.5) < 0.05
