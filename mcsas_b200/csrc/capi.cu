@@ -47,6 +47,13 @@ struct mcsas_ctx {
     double *d_quad = nullptr;     // [2][quad_nodes]
     // run state
     int n_chains = 0, n_contribs = 0, n_reps = 0, n_active = 0;
+    int n_slots = 0;              // state slots on the device: 2 per chain (current attempt + backup attempt)
+    bool backups = false;         // speculative next attempts of late chains on idle SMs
+    int max_attempts = 1;
+    std::vector<int> cur, bak, bak_state;          // per chain: slot of the current attempt, backup slot (-1), 1 running / 2 finished
+    std::vector<char> done;
+    std::vector<long long> carry_steps, carry_evals;   // work of the failed attempts left behind in the other slot
+    int n_backups_started = 0, n_backups_used = 0;
     long long max_iter = 0;
     bool have_run = false, have_trace = false, running = false;
     double *d_stream = nullptr;
@@ -553,16 +560,20 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
         d_stream = ctx->d_stream;
     }
     // outputs
-    size_t need_out = (size_t)n_chains * ((size_t)N * P + ctx->nq_max + 8);
+    const int n_slots = 2 * n_chains;
+    size_t need_out = (size_t)n_slots * ((size_t)N * P + ctx->nq_max + 8);
     if (need_out > ctx->out_cap || n_chains > ctx->n_chains || (size_t)N * P > (size_t)ctx->n_contribs * ctx->n_active) {
-        CK(regrow(&ctx->d_rset, (size_t)n_chains * N * P));
-        CK(regrow(&ctx->d_fit, (size_t)n_chains * ctx->nq_max));
-        CK(regrow(&ctx->d_scal, (size_t)n_chains * 5));
-        CK(regrow(&ctx->d_cnt, (size_t)n_chains * 4));
-        CK(regrow(&ctx->d_att, (size_t)n_chains * 2));
-        CK(regrow(&ctx->d_ids, (size_t)n_chains));
+        CK(regrow(&ctx->d_rset, (size_t)n_slots * N * P));
+        CK(regrow(&ctx->d_fit, (size_t)n_slots * ctx->nq_max));
+        CK(regrow(&ctx->d_scal, (size_t)n_slots * 5));
+        CK(regrow(&ctx->d_cnt, (size_t)n_slots * 4));
+        CK(regrow(&ctx->d_att, (size_t)n_slots * 2));
+        CK(regrow(&ctx->d_ids, (size_t)n_slots));
         ctx->out_cap = need_out;
     }
+    CK(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(long long) * (size_t)n_slots * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_scal, 0, sizeof(double) * (size_t)n_slots * 5, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_att, 0, sizeof(int) * (size_t)n_slots * 2, ctx->stream));
     ctx->have_trace = false;
     if (cfg->record_trace) {
         size_t n = (size_t)n_chains * (size_t)cfg->max_iter;
@@ -594,15 +605,22 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     const char *env = getenv("MCSAS_B200_SLICE");
     if (env && !(proposal_stream || cfg->record_trace)) slice = atoll(env);
     a.slice_steps = slice > 0 ? slice : 0;
+    a.slice_batches = 0;
+    if (cfg->precision == MCSAS_FP32 && cfg->slice_steps == 0 && !env && a.slice_steps > 0) {
+        // auto: a slice is a number of BATCHES (similar duration whether a chain is in its
+        // move-rich early phase or late), the step limit stays as an upper bound
+        a.slice_batches = 384;
+        a.slice_steps = 16384;
+    }
     a.sets = ctx->d_sets; a.data = ctx->d_data;
     a.quad_x = ctx->d_quad; a.quad_w = ctx->d_quad + D;
     a.stream = d_stream; a.stream_stride = stream_stride;
     a.rset = ctx->d_rset; a.fit_meas = ctx->d_fit; a.nq_stride = ctx->nq_max;
-    a.scaling = ctx->d_scal; a.background = ctx->d_scal + n_chains; a.conval = ctx->d_scal + 2 * n_chains;
-    a.conval0 = ctx->d_scal + 3 * n_chains; a.elapsed_s = ctx->d_scal + 4 * n_chains;
-    a.num_iter = ctx->d_cnt; a.num_moves = ctx->d_cnt + n_chains; a.evals = ctx->d_cnt + 2 * n_chains;
-    a.steps_all = ctx->d_cnt + 3 * (size_t)n_chains;
-    a.attempts = ctx->d_att; a.status = ctx->d_att + n_chains;
+    a.scaling = ctx->d_scal; a.background = ctx->d_scal + n_slots; a.conval = ctx->d_scal + 2 * n_slots;
+    a.conval0 = ctx->d_scal + 3 * n_slots; a.elapsed_s = ctx->d_scal + 4 * n_slots;
+    a.num_iter = ctx->d_cnt; a.num_moves = ctx->d_cnt + n_slots; a.evals = ctx->d_cnt + 2 * n_slots;
+    a.steps_all = ctx->d_cnt + 3 * (size_t)n_slots;
+    a.attempts = ctx->d_att; a.status = ctx->d_att + n_slots;
     a.trace_accept = cfg->record_trace ? ctx->d_tacc : nullptr;
     a.trace_chi = cfg->record_trace ? ctx->d_tchi : nullptr;
     a.cache = nullptr;
@@ -620,8 +638,8 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     if (getenv("MCSAS_B200_PROF") && cfg->precision == MCSAS_FP32) {
         cudaFree(ctx->d_prof);
         ctx->d_prof = nullptr;
-        CK(cudaMalloc(&ctx->d_prof, sizeof(long long) * 48 * n_chains));
-        CK(cudaMemset(ctx->d_prof, 0, sizeof(long long) * 48 * n_chains));
+        CK(cudaMalloc(&ctx->d_prof, sizeof(long long) * 48 * n_slots));
+        CK(cudaMemset(ctx->d_prof, 0, sizeof(long long) * 48 * n_slots));
         a.prof = ctx->d_prof;
     }
     ctx->args = a;
@@ -629,8 +647,23 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     ctx->smem = smem;
     ctx->forced_cluster = cfg->cluster_size;
     ctx->n_chains = n_chains; ctx->n_contribs = N; ctx->n_reps = cfg->n_reps; ctx->n_active = P;
+    ctx->n_slots = n_slots;
+    ctx->max_attempts = a.max_attempts;
+    {
+        const char *be = getenv("MCSAS_B200_BACKUP");
+        ctx->backups = cfg->precision == MCSAS_FP32 && !proposal_stream && !cfg->record_trace && a.slice_steps > 0
+                       && a.max_attempts > 1 && !(be && atoi(be) == 0);
+    }
+    ctx->cur.assign(n_chains, 0);
+    for (int i = 0; i < n_chains; ++i) ctx->cur[i] = i;
+    ctx->bak.assign(n_chains, -1);
+    ctx->bak_state.assign(n_chains, 0);
+    ctx->done.assign(n_chains, 0);
+    ctx->carry_steps.assign(n_chains, 0);
+    ctx->carry_evals.assign(n_chains, 0);
+    ctx->n_backups_started = ctx->n_backups_used = 0;
     ctx->max_iter = cfg->max_iter;
-    ctx->h_ids.resize(n_chains);
+    ctx->h_ids.resize(n_slots);
     for (int i = 0; i < n_chains; ++i) ctx->h_ids[i] = i;
     ctx->n_live = n_chains;
     ctx->n_launches = 0;
@@ -659,7 +692,9 @@ extern "C" int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms)
     if (!ctx) return MCSAS_ERR_ARG;
     if (!ctx->running) return fail(ctx, MCSAS_ERR_STATE, "wait: nothing running");
     ctx->running = false;
-    std::vector<int> status(ctx->n_chains);
+    const int NC = ctx->n_chains, NS = ctx->n_slots;
+    std::vector<int> att(2 * (size_t)NS);                 // attempts | status
+    std::vector<long long> cnt(4 * (size_t)NS);           // num_iter | num_moves | evals | steps_all
     for (;;) {
         CK(cudaStreamSynchronize(ctx->stream));
         float ms = 0.f;
@@ -670,28 +705,85 @@ extern "C" int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms)
                     ctx->n_launches, ctx->n_live, ctx->last_cluster, ctx->last_threads, ctx->last_qpt,
                     ctx->last_resident, ms);
         if (ctx->args.slice_steps <= 0) break;
-        CK(cudaMemcpy(status.data(), ctx->args.status, sizeof(int) * ctx->n_chains, cudaMemcpyDeviceToHost));
-        int n = 0;
+        CK(cudaMemcpy(att.data(), ctx->d_att, sizeof(int) * att.size(), cudaMemcpyDeviceToHost));
+        int *attempts = att.data(), *status = att.data() + NS;
         for (int i = 0; i < ctx->n_live; ++i) {
-            int c = ctx->h_ids[i];
-            if (status[c] < 0)
-                return fail(ctx, MCSAS_ERR_CUDA, "chain %d: kernel watchdog fired (status %d)", c, status[c]);
-            if (status[c] != 1) ctx->h_ids[n++] = c;       // 0: continue, 2: retry afresh
+            int s = ctx->h_ids[i];
+            if (status[s] < 0)
+                return fail(ctx, MCSAS_ERR_CUDA, "chain %d: kernel watchdog fired (status %d)", s % NC, status[s]);
+        }
+        if (ctx->backups) CK(cudaMemcpy(cnt.data(), ctx->d_cnt, sizeof(long long) * cnt.size(), cudaMemcpyDeviceToHost));
+        const long long *num_iter = cnt.data(), *evals = cnt.data() + 2 * (size_t)NS, *steps_all = cnt.data() + 3 * (size_t)NS;
+        // ---- per chain: current attempt finished / failed / continues; backup bookkeeping --------
+        int n = 0, n_primary = 0;
+        for (int c = 0; c < NC; ++c) {
+            if (ctx->done[c]) continue;
+            const int pslot = ctx->cur[c], sp = status[pslot];
+            int b = ctx->bak[c];
+            if (b >= 0 && ctx->bak_state[c] == 1 && status[b] == 1) ctx->bak_state[c] = 2;   // backup attempt ended
+            if (sp == 1) {                                   // converged, or out of attempts: final
+                ctx->done[c] = 1;
+                ctx->bak[c] = -1; ctx->bak_state[c] = 0;     // a running backup is dropped
+                continue;
+            }
+            if (sp == 2 && b >= 0) {
+                // this attempt failed and the NEXT attempt has been running in the backup slot:
+                // it becomes the chain's current attempt (identical to a retry started now --
+                // an attempt is a function of (seed, chain, attempt number) only)
+                ctx->carry_steps[c] += steps_all[pslot];
+                ctx->carry_evals[c] += evals[pslot];
+                ctx->cur[c] = b;
+                ctx->n_backups_used++;
+                const bool finished = ctx->bak_state[c] == 2;
+                ctx->bak[c] = -1; ctx->bak_state[c] = 0;
+                if (finished) { ctx->done[c] = 1; continue; }
+                ctx->h_ids[n++] = b;
+                ++n_primary;
+                continue;
+            }
+            ctx->h_ids[n++] = pslot;                         // 0: continue, 2: retry afresh in the same slot
+            ++n_primary;
+            if (b >= 0 && ctx->bak_state[c] == 1) ctx->h_ids[n++] = b;
+        }
+        // ---- start backups: few chains alive, SMs idle, chain is late in its attempt -------------
+        bool new_backups = false;
+        if (ctx->backups && n_primary > 0 && n_primary * 8 <= ctx->prop.multiProcessorCount) {
+            for (int c = 0; c < NC; ++c) {
+                if (ctx->done[c] || ctx->bak[c] >= 0) continue;
+                const int pslot = ctx->cur[c];
+                if (status[pslot] != 0 || attempts[pslot] >= ctx->max_attempts) continue;
+                if (2 * num_iter[pslot] < ctx->max_iter) continue;
+                const int b = pslot < NC ? pslot + NC : pslot - NC;
+                // fresh state of the backup slot, uploaded below with the host copies
+                att[b] = attempts[pslot] + 1; att[(size_t)NS + b] = 2;
+                for (int k = 0; k < 4; ++k) cnt[(size_t)k * NS + b] = 0;
+                new_backups = true;
+                CK(cudaMemsetAsync(ctx->d_scal + 4 * (size_t)NS + b, 0, sizeof(double), ctx->stream));   // elapsed
+                ctx->bak[c] = b; ctx->bak_state[c] = 1;
+                ctx->h_ids[n++] = b;
+                ctx->n_backups_started++;
+            }
+        }
+        if (new_backups) {                                  // nothing runs between slices: whole arrays
+            CK(cudaMemcpyAsync(ctx->d_att, att.data(), sizeof(int) * att.size(), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->d_cnt, cnt.data(), sizeof(long long) * cnt.size(), cudaMemcpyHostToDevice, ctx->stream));
         }
         if (ctx->n_launches > 100000) return fail(ctx, MCSAS_ERR_CUDA, "time-slice loop did not terminate");
         ctx->n_live = n;
         bool stop = *(volatile int *)ctx->h_stop != 0 || (ctx->stop_flag && *ctx->stop_flag);
-        if (n == 0 || stop) break;
+        if (n_primary == 0 || stop) break;
         int rc = launch_slice(ctx, n, true);
         if (rc) return rc;
     }
+    if (getenv("MCSAS_B200_DEBUG") && ctx->backups)
+        fprintf(stderr, "[mcsas_b200] backup attempts started %d, used %d\n", ctx->n_backups_started, ctx->n_backups_used);
     if (ctx->args.prof) {                                 // phase profile (experiments only)
-        std::vector<long long> h((size_t)48 * ctx->n_chains);
+        std::vector<long long> h((size_t)48 * ctx->n_slots);
         CK(cudaMemcpy(h.data(), ctx->args.prof, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
         static const char *nm[6] = {"ring-wait", "refresh+eval", "B1", "exchange+decide", "B2", "update"};
         for (int m = 0; m < 2; ++m) {
             long long tot[24] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-            for (int c = 0; c < ctx->n_chains; ++c)
+            for (int c = 0; c < ctx->n_slots; ++c)
                 for (int i = 0; i < 24; ++i) tot[i] += h[((size_t)c * 2 + m) * 24 + i];
             if (!tot[6]) continue;
             fprintf(stderr, "[mcsas_b200 prof] %s batches %lld steps %lld (%.1f steps/batch), cycles/batch:",
@@ -737,41 +829,49 @@ extern "C" int mcsas_fetch(mcsas_ctx *ctx, double *contribs, double *fit_meas, d
     if (!ctx) return MCSAS_ERR_ARG;
     if (!ctx->have_run) return fail(ctx, MCSAS_ERR_STATE, "fetch: no finished run");
     CK(cudaSetDevice(ctx->device));
-    const int C = ctx->n_chains, N = ctx->n_contribs, P = ctx->n_active, R = ctx->n_reps;
+    const int C = ctx->n_chains, N = ctx->n_contribs, P = ctx->n_active, R = ctx->n_reps, NS = ctx->n_slots;
+    const std::vector<int> &fs = ctx->cur;                // slot holding each chain's final attempt
     if (contribs) {
-        std::vector<double> h((size_t)C * N * P);
+        std::vector<double> h((size_t)NS * N * P);
         CK(cudaMemcpy(h.data(), ctx->d_rset, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
-        // [chain][N][P] -> [set][N][P][R]
+        // [slot][N][P] -> [set][N][P][R]
         for (int c = 0; c < C; ++c) {
             int s = c / R, r = c % R;
             for (int i = 0; i < N * P; ++i)
-                contribs[((size_t)s * N * P + i) * R + r] = h[(size_t)c * N * P + i];
+                contribs[((size_t)s * N * P + i) * R + r] = h[(size_t)fs[c] * N * P + i];
         }
     }
     if (fit_meas) {
-        std::vector<double> h((size_t)C * ctx->nq_max);
+        std::vector<double> h((size_t)NS * ctx->nq_max);
         CK(cudaMemcpy(h.data(), ctx->d_fit, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
         size_t base = 0;
         for (int s = 0; s < ctx->n_sets; ++s) {
             int nq = ctx->sets[s].nq;
             for (int r = 0; r < R; ++r)
                 for (int i = 0; i < nq; ++i)
-                    fit_meas[base + (size_t)i * R + r] = h[(size_t)(s * R + r) * ctx->nq_max + i];
+                    fit_meas[base + (size_t)i * R + r] = h[(size_t)fs[s * R + r] * ctx->nq_max + i];
             base += (size_t)nq * R;
         }
     }
-    std::vector<double> sc((size_t)C * 5);
+    std::vector<double> sc((size_t)NS * 5);
     CK(cudaMemcpy(sc.data(), ctx->d_scal, sizeof(double) * sc.size(), cudaMemcpyDeviceToHost));
-    if (scaling) memcpy(scaling, sc.data(), sizeof(double) * C);
-    if (background) memcpy(background, sc.data() + C, sizeof(double) * C);
-    if (conval) memcpy(conval, sc.data() + 2 * (size_t)C, sizeof(double) * C);
-    if (conval0) memcpy(conval0, sc.data() + 3 * (size_t)C, sizeof(double) * C);
-    if (elapsed_s) memcpy(elapsed_s, sc.data() + 4 * (size_t)C, sizeof(double) * C);
-    if (num_iter) CK(cudaMemcpy(num_iter, ctx->d_cnt, sizeof(long long) * C, cudaMemcpyDeviceToHost));
-    if (num_moves) CK(cudaMemcpy(num_moves, ctx->d_cnt + C, sizeof(long long) * C, cudaMemcpyDeviceToHost));
-    if (evals) CK(cudaMemcpy(evals, ctx->d_cnt + 2 * (size_t)C, sizeof(long long) * C, cudaMemcpyDeviceToHost));
-    if (steps_all) CK(cudaMemcpy(steps_all, ctx->d_cnt + 3 * (size_t)C, sizeof(long long) * C, cudaMemcpyDeviceToHost));
-    if (attempts) CK(cudaMemcpy(attempts, ctx->d_att, sizeof(int) * C, cudaMemcpyDeviceToHost));
+    std::vector<long long> cn((size_t)NS * 4);
+    CK(cudaMemcpy(cn.data(), ctx->d_cnt, sizeof(long long) * cn.size(), cudaMemcpyDeviceToHost));
+    std::vector<int> at((size_t)NS);
+    CK(cudaMemcpy(at.data(), ctx->d_att, sizeof(int) * at.size(), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < C; ++c) {
+        const size_t f = (size_t)fs[c];
+        if (scaling) scaling[c] = sc[f];
+        if (background) background[c] = sc[(size_t)NS + f];
+        if (conval) conval[c] = sc[2 * (size_t)NS + f];
+        if (conval0) conval0[c] = sc[3 * (size_t)NS + f];
+        if (elapsed_s) elapsed_s[c] = sc[4 * (size_t)NS + f];
+        if (num_iter) num_iter[c] = cn[f];
+        if (num_moves) num_moves[c] = cn[(size_t)NS + f];
+        if (evals) evals[c] = cn[2 * (size_t)NS + f] + ctx->carry_evals[c];
+        if (steps_all) steps_all[c] = cn[3 * (size_t)NS + f] + ctx->carry_steps[c];
+        if (attempts) attempts[c] = at[f];
+    }
     return MCSAS_OK;
 }
 

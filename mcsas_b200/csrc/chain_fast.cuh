@@ -327,8 +327,11 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     const int rank = C > 1 ? (int)cluster_ctarank() : 0;
     const int slot = blockIdx.x / C;
     const int chain = a.chain_ids ? a.chain_ids[slot] : slot;
-    const uint32_t gchain = (uint32_t)(a.first_chain + chain);
-    const int set = chain / a.n_reps;
+    // `chain` is a state slot: slots >= n_chains hold a chain's other attempt (retry prepared or
+    // run ahead of time by the host scheduler, capi.cu)
+    const int base_chain = chain % a.n_chains;
+    const uint32_t gchain = (uint32_t)(a.first_chain + base_chain);
+    const int set = base_chain / a.n_reps;
     const DatasetDesc ds = a.sets[set];
     const int nq = ds.nq, N = a.n_contribs, P = a.mp.n_active;
     const int D = NARR ? a.mp.quad_nodes : 0;
@@ -607,6 +610,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         int K = max(1, kmax / 2);
         int batch = 0;
         const int wd_batches = (int)min((long long)0x3fffffff, 2 * (min(a.max_iter, slice_end) - step) + 64);
+        const int batch_end = a.slice_batches > 0 ? a.slice_batches : 0x7fffffff;
         bool live = N > 1 && conval > a.conv_crit && step < a.max_iter && step < slice_end;
 
         {
@@ -1116,7 +1120,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                 pp[0] += pt1 - pt0; pp[1] += pt2 - pt1; pp[2] += pt3 - pt2; pp[3] += pt4 - pt3;
                 pp[4] += pt5 - pt4; pp[5] += clock64() - pt5; pp[6] += 1; pp[7] += used;
             }
-            live = conval > a.conv_crit && step < a.max_iter && step < slice_end;
+            live = conval > a.conv_crit && step < a.max_iter && step < slice_end && batch < batch_end;
         }
         }
         __syncthreads();

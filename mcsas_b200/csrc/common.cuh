@@ -52,6 +52,7 @@ struct ChainArgs {
     int warps_q;                 // fp32 kernel: warps covering one CTA's q slice (eval warps = warps_q * groups)
     int resume;                  // 1: continue from the saved state (rset, counters)
     long long slice_steps;       // MC steps per chain in this launch, 0 = run to the end
+    int slice_batches;           // fp32 kernel: batches per chain in this launch (0 = no limit)
     const int *chain_ids;        // chains of this launch (grid = n * cluster) or NULL
     int *status;                 // per chain: 1 finished, 0 needs another slice
     int first_chain;
