@@ -297,6 +297,42 @@ __device__ __forceinline__ void fast_solve(const FastBase &B, int find_bg, int p
     e2n = -.5 * (gb + Hab * da + Hbb * db);
 }
 
+// The same minimum in SCALED fp32 variables (decision latency: an fp64 chain of ~60
+// dependent operations per proposal is the critical path of a batch).  Unknowns
+// x = da sqrt(Smm), y = db sqrt(S); scaled Hessian 2 [[h11, h12], [h12, 1]] with entries of
+// order one for any data scale; every term is delta sized, the exact chi2 of the base state
+// enters only as  chi2' = chi2 + delta / nq.
+struct FastBaseF {
+    float rSmm, rS, c12, a0, b0, e1s, e2s;     // 1/sqrt(Smm), 1/sqrt(S), Sm rSmm rS, centre, E1 rSmm, E2 rS
+};
+__device__ __forceinline__ void fast_solve_f(const FastBaseF &F, int find_bg, int pos_bg, float s1, float s2,
+                                             float s3, float s4, float &delta, float &x, float &y,
+                                             float &h11, float &h12, float &e1n, float &e2n)
+{
+    const float gx = -2.f * (F.e1s + (s1 - F.a0 * (s3 + s2)) * F.rSmm);
+    const float gy = -2.f * (F.e2s - F.a0 * s4 * F.rS);
+    h11 = fmaf(2.f * s3 + s2, F.rSmm * F.rSmm, 1.f);
+    h12 = fmaf(s4, F.rSmm * F.rS, F.c12);
+    const float d0 = F.a0 * (F.a0 * s2 - 2.f * s1);
+    if (find_bg) {
+        const float inv = 0.5f / (h11 - h12 * h12);
+        x = -(gx - h12 * gy) * inv;
+        y = -(h11 * gy - h12 * gx) * inv;
+        delta = d0 + .5f * (gx * x + gy * y);
+        if (pos_bg && F.b0 + y * F.rS < 0.f) {                   // |b| residual -> b = 0 (:60-63)
+            y = -F.b0 / F.rS;
+            x = -(gx + 2.f * h12 * y) / (2.f * h11);
+            delta = d0 + gx * x + gy * y + (h11 * x * x + 2.f * h12 * x * y + y * y);
+        }
+    } else {                                                     // chiNoBg (:66-70), b0 == 0
+        y = 0.f;
+        x = -gx / (2.f * h11);
+        delta = d0 + .5f * gx * x;
+    }
+    e1n = -.5f * (gx + 2.f * h11 * x + 2.f * h12 * y);
+    e2n = -.5f * (gy + 2.f * h12 * x + 2.f * y);
+}
+
 template <int NG> __device__ __forceinline__ int grp_perm(int lane)
 {
     return NG == 8 ? ((lane >> 2) & 7) : ((lane >> 3) & 3);
@@ -619,8 +655,8 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         // committed up to the first accepted one) when moves are rare, and GRAM (exactly FGRP
         // steps, all of them consumed: the Gram matrix of the proposals' changes lets warp 0
         // re-derive the sums of later proposals after each accepted one) when moves are frequent.
-        FastBase B;                                              // meaningful in warp 0 only
-        B.S = L.S; B.Sm = 0.; B.Smm = 0.; B.E0 = 0.; B.E1 = 0.; B.E2 = 0.; B.a0 = a0; B.b0 = b0;
+        FastBaseF F;                                             // meaningful in warp 0 only
+        F.rSmm = 1.f; F.rS = 1.f; F.c12 = 0.f; F.a0 = (float)a0; F.b0 = (float)b0; F.e1s = 0.f; F.e2s = 0.f;
         while (live) {
             const long long pt0 = a.prof ? clock64() : 0;
             int Kb = min(K, kmax);
@@ -904,99 +940,99 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             long long pd[4] = {0, 0, 0, 0};
             if (warp == 0) {
                 if (a.prof) pd[0] = clock64();
-                if (dirty) {                                     // fresh base sums (identical in all lanes)
-                    double b5[5] = {0., 0., 0., 0., 0.};
-                    if (C > 1) {
-                        for (int r = 0; r < C; ++r)
-#pragma unroll
-                            for (int i = 0; i < 5; ++i) b5[i] += part[(size_t)r * XU + 2 * KCAP + i];
-                    } else {
-                        for (int wv = 0; wv < WQ; ++wv)
-#pragma unroll
-                            for (int i = 0; i < 5; ++i) b5[i] += s_bsum[wv * 6 + i];
+                if (dirty) {                                     // fresh base sums: lane i < 5 adds quantity i
+                    double x = 0.;
+                    if (lane < 5) {
+                        if (C > 1) { for (int r = 0; r < C; ++r) x += part[(size_t)r * XU + 2 * KCAP + lane]; }
+                        else { for (int wv = 0; wv < WQ; ++wv) x += s_bsum[wv * 6 + lane]; }
                     }
-                    B.E0 = b5[0]; B.E1 = b5[1]; B.E2 = b5[2]; B.Sm = b5[3]; B.Smm = b5[4];
-                    B.a0 = a0; B.b0 = b0;
+                    const double E0 = __shfl_sync(0xffffffffu, x, 0), E1 = __shfl_sync(0xffffffffu, x, 1);
+                    const double E2 = __shfl_sync(0xffffffffu, x, 2), Sm = __shfl_sync(0xffffffffu, x, 3);
+                    const double Smm = __shfl_sync(0xffffffffu, x, 4);
+                    const double rSmm = rsqrt(Smm), rS = rsqrt(L.S);
+                    F.rSmm = (float)rSmm; F.rS = (float)rS; F.c12 = (float)(Sm * rSmm * rS);
+                    F.a0 = (float)a0; F.b0 = (float)b0;
+                    F.e1s = (float)(E1 * rSmm); F.e2s = (float)(E2 * rS);
                     // the centre is the fit of this state up to the fp32 error of the delta sums:
                     // chi2 at the centre exceeds the minimum by O(1e-14) relative
-                    conval = B.E0 * L.inv_nq;
+                    conval = E0 * L.inv_nq;
                 }
                 if (a.prof) pd[1] = clock64();
-                double s1 = 0., s2 = 0., s3 = 0., s4 = 0.;
+                float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
                 const bool mine = lane < Kb && !wd;
                 if (mine) {
                     if (C > 1) {
                         for (int r = 0; r < C; ++r) {
-                            const float4 x = *(const float4 *)(part + (size_t)r * XU + 2 * lane);
-                            s1 += (double)x.x; s2 += (double)x.y; s3 += (double)x.z; s4 += (double)x.w;
+                            const float4 v = *(const float4 *)(part + (size_t)r * XU + 2 * lane);
+                            s1 += v.x; s2 += v.y; s3 += v.z; s4 += v.w;
                         }
                     } else {
-                        float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
                         for (int wv = 0; wv < WQ; ++wv) {
-                            const float4 x = s_wsum[wv * KCAP + lane];
-                            t4.x += x.x; t4.y += x.y; t4.z += x.z; t4.w += x.w;
+                            const float4 v = s_wsum[wv * KCAP + lane];
+                            s1 += v.x; s2 += v.y; s3 += v.z; s4 += v.w;
                         }
-                        s1 = t4.x; s2 = t4.y; s3 = t4.z; s4 = t4.w;
                     }
                 }
                 if (a.prof) pd[2] = clock64();
                 int ks = -1, accmask = 0;
                 double ca = a0, cb = b0, cc = conval;
                 if (!gram) {
-                    double chi = 0., an = 0., bn = 0., e1, e2;
+                    float delta = 0.f, x = 0.f, y = 0.f, h11, h12, e1, e2;
                     bool better = false;
                     if (mine) {
-                        double rss;
-                        fast_solve(B, L.find_bg, L.pos_bg, s1, s2, s3, s4, rss, an, bn, e1, e2);   // mcsas.py:376
-                        chi = rss * L.inv_nq;
-                        better = chi < conval;                   // :379 strict
-                        s_chi[lane] = chi;
+                        fast_solve_f(F, L.find_bg, L.pos_bg, s1, s2, s3, s4, delta, x, y, h11, h12, e1, e2);   // mcsas.py:376
+                        better = delta < 0.f;                    // :379 strict: chi2' < chi2
+                        s_chi[lane] = conval + (double)delta * L.inv_nq;
                     }
                     const unsigned mask = __ballot_sync(0xffffffffu, better);
                     ks = mask ? (__ffs(mask) - 1) : -1;
                     if (ks >= 0) {
-                        ca = __shfl_sync(0xffffffffu, an, ks); cb = __shfl_sync(0xffffffffu, bn, ks);
-                        cc = __shfl_sync(0xffffffffu, chi, ks);
+                        const float xs = __shfl_sync(0xffffffffu, x, ks), ys = __shfl_sync(0xffffffffu, y, ks);
+                        const float ds = __shfl_sync(0xffffffffu, delta, ks);
+                        ca = a0 + (double)xs * (double)F.rSmm;
+                        cb = b0 + (double)ys * (double)F.rS;
+                        cc = conval + (double)ds * L.inv_nq;
                     }
                 } else {
                     // Gram totals over warps / ranks
                     for (int i = lane; i < NGP; i += 32) {
-                        float x = 0.f;
+                        float v = 0.f;
                         if (C > 1) {
-                            for (int r = 0; r < C; ++r) x += ((const float *)(part + (size_t)r * XU + 2 * KCAP + 8))[i];
+                            for (int r = 0; r < C; ++r) v += ((const float *)(part + (size_t)r * XU + 2 * KCAP + 8))[i];
                         } else {
-                            for (int wv = 0; wv < WQ; ++wv) x += s_gram[wv * NGP + i];
+                            for (int wv = 0; wv < WQ; ++wv) v += s_gram[wv * NGP + i];
                         }
-                        s_gtot[i] = x;
+                        s_gtot[i] = v;
                     }
                     __syncwarp();
                     int pos = 0;
                     for (int it = 0; it <= FGRP && !wd; ++it) {
-                        double rss = 0., an = 0., bn = 0., e1 = 0., e2 = 0.;
+                        float delta = 0.f, x = 0.f, y = 0.f, h11 = 1.f, h12 = 0.f, e1 = 0.f, e2 = 0.f;
                         bool better = false;
                         if (mine && lane >= pos) {
-                            fast_solve(B, L.find_bg, L.pos_bg, s1, s2, s3, s4, rss, an, bn, e1, e2);
-                            const double chi = rss * L.inv_nq;
-                            better = chi < cc;                   // :379 against the state reached so far
-                            s_chi[lane] = chi;
+                            fast_solve_f(F, L.find_bg, L.pos_bg, s1, s2, s3, s4, delta, x, y, h11, h12, e1, e2);
+                            better = delta < 0.f;                // :379 against the state reached so far
+                            s_chi[lane] = cc + (double)delta * L.inv_nq;
                         }
                         const unsigned mask = __ballot_sync(0xffffffffu, better);
                         if (!mask) break;
                         const int i = __ffs(mask) - 1;
-                        const double ai = __shfl_sync(0xffffffffu, an, i), bi = __shfl_sync(0xffffffffu, bn, i);
-                        const double ri = __shfl_sync(0xffffffffu, rss, i);
-                        const double e1i = __shfl_sync(0xffffffffu, e1, i), e2i = __shfl_sync(0xffffffffu, e2, i);
-                        const double s2i = __shfl_sync(0xffffffffu, s2, i), s3i = __shfl_sync(0xffffffffu, s3, i);
-                        const double s4i = __shfl_sync(0xffffffffu, s4, i);
-                        const double da = ai - B.a0, db = bi - B.b0;
+                        const float xi = __shfl_sync(0xffffffffu, x, i), yi = __shfl_sync(0xffffffffu, y, i);
+                        const float di = __shfl_sync(0xffffffffu, delta, i);
+                        const float h11i = __shfl_sync(0xffffffffu, h11, i), h12i = __shfl_sync(0xffffffffu, h12, i);
+                        const float e1i = __shfl_sync(0xffffffffu, e1, i), e2i = __shfl_sync(0xffffffffu, e2, i);
+                        const float da = xi * F.rSmm, db = yi * F.rS;
+                        ca += (double)xi * (double)F.rSmm; cb += (double)yi * (double)F.rS;
+                        cc += (double)di * L.inv_nq;
+                        const float an = (float)ca;
                         if (mine && lane > i) {                  // sums of later proposals w.r.t. the new state
-                            const double G = (double)s_gtot[tri_idx_rt(FGRP, i, lane)];
-                            s1 = s1 - da * s3 - ai * G - db * s4;
+                            const float G = s_gtot[tri_idx_rt(FGRP, i, lane)];
+                            s1 = s1 - da * s3 - an * G - db * s4;
                             s3 += G;
                         }
-                        B.Sm += s4i; B.Smm += 2. * s3i + s2i;
-                        B.E0 = ri; B.E1 = e1i; B.E2 = e2i; B.a0 = ai; B.b0 = bi;
-                        ca = ai; cb = bi; cc = ri * L.inv_nq;
+                        const float sq = rsqrtf(h11i);           // Smm' = h11 Smm
+                        F.rSmm *= sq; F.c12 = h12i * sq; F.e1s = e1i * sq; F.e2s = e2i;
+                        F.a0 = an; F.b0 = (float)cb;
                         accmask |= 1 << i;
                         pos = i + 1;
                     }
