@@ -269,6 +269,19 @@ def main():
                                      "6.55 TB/s measured (MEASURED_PEAKS.json); inputs/outputs are 24 KB / 1.1 MB per fit",
                          "sm_count": info["sm_count"], "ctas": N_REPS},
         }
+        if world == 1:
+            # the same kernel with every SM busy: 16 datasets x 100 repetitions (not part of `value`)
+            eng = algo.engine
+            eng.upload_datasets(synth.sphere_batch(16, nq=NQ))
+            eng.set_model(0, [10e-9, 1e14], [0], [RADIUS_RANGE[0]], [RADIUS_RANGE[1]], [0])
+            from mcsas_b200 import Engine, FP32
+            ms_sat = eng.run(Engine.make_config(n_contribs=N_CONTRIBS, n_reps=N_REPS, precision=FP32, seed=99,
+                                                max_retries=0))
+            rs = eng.fetch()
+            sat = float(rs["steps_all"].sum()) / (ms_sat * 1e-3)
+            line["saturated"] = {"value": sat, "unit": "MC steps/s", "chains": 1600, "kernel_ms": ms_sat,
+                                 "mufu_frac_algorithmic": sat * MUFU_PER_STEP * 1e-9 / peaks["mufu_gops"],
+                                 "mufu_frac_executed": sat * MUFU_EXECUTED_PER_STEP * 1e-9 / peaks["mufu_gops"]}
         if not args.no_cpu_baseline and world == 1:
             threads = host_threads()
             v, el = oracle_cpu_steps_per_s(150000, threads)

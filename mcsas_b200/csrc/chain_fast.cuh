@@ -655,6 +655,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         // committed up to the first accepted one) when moves are rare, and GRAM (exactly FGRP
         // steps, all of them consumed: the Gram matrix of the proposals' changes lets warp 0
         // re-derive the sums of later proposals after each accepted one) when moves are frequent.
+        const double rS_const = rsqrt(L.S);
         FastBaseF F;                                             // meaningful in warp 0 only
         F.rSmm = 1.f; F.rS = 1.f; F.c12 = 0.f; F.a0 = (float)a0; F.b0 = (float)b0; F.e1s = 0.f; F.e2s = 0.f;
         while (live) {
@@ -949,7 +950,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     const double E0 = __shfl_sync(0xffffffffu, x, 0), E1 = __shfl_sync(0xffffffffu, x, 1);
                     const double E2 = __shfl_sync(0xffffffffu, x, 2), Sm = __shfl_sync(0xffffffffu, x, 3);
                     const double Smm = __shfl_sync(0xffffffffu, x, 4);
-                    const double rSmm = rsqrt(Smm), rS = rsqrt(L.S);
+                    const double rSmm = rsqrt(Smm), rS = rS_const;
                     F.rSmm = (float)rSmm; F.rS = (float)rS; F.c12 = (float)(Sm * rSmm * rS);
                     F.a0 = (float)a0; F.b0 = (float)b0;
                     F.e1s = (float)(E1 * rSmm); F.e2s = (float)(E2 * rS);
@@ -1074,12 +1075,12 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     for (int j = 0; j < QPT; ++j) {
                         const int ql = qtid * QPT + j;
                         const double sq = s_sw[ql];
-                        double du = 0.;
+                        float du = 0.f;
 #pragma unroll
                         for (int s = 0; s < FGRP; ++s)
-                            if ((accmask >> (s ^ perm)) & 1) du += (double)uu[s][j];
+                            if ((accmask >> (s ^ perm)) & 1) du += uu[s][j];
                         // uu = (new - old)/sigma in the model's units: undo the 1/sigma
-                        const double f = s_ft[cur * FAST_QCAP + ql] + (sq > 0. ? du / sq : 0.);
+                        const double f = s_ft[cur * FAST_QCAP + ql] + (om[j] > 0.f ? (double)__fdividef(du, om[j]) : 0.);
                         if (grp == 0) s_ft[(cur ^ 1) * FAST_QCAP + ql] = f;
                         rho[j] = (float)(sq * (s_In[ql] - (a0 * f + b0)));
                         mu[j] = (float)(sq * f);
