@@ -325,3 +325,47 @@ def run_histogram_case():
 
 if __name__ == "__main__" and (not sys.argv[1:] or "hist" in sys.argv[1:]):
     run_histogram_case()
+
+
+def run_dataprep_cases():
+    """Data preparation of the reference: loaddatafile -> SASData ->
+    config.updateFuMin() -> setConfig (dataobj.py:204-226, 239-269, 288-345) on the shipped
+    test data; raw table + DataConfig values + the vectors mcFit would read."""
+    rh.install()
+    from mcsas.datafile import loaddatafile
+    out = {}
+
+    def case(tag, fn, nbin=None, qlow=None, qhigh=None, maskneg=None, fumin=None):
+        d = loaddatafile(os.path.join(rh.REFERENCE_TESTDATA, fn)).getDataObj()
+        c = d.config
+        if nbin is not None:
+            c.nBin.setValue(nbin)
+        if fumin is not None:
+            c.fuMin.setValue(fumin)
+        if qlow is not None:
+            c.x0Low.setValue(qlow)
+        if qhigh is not None:
+            c.x0High.setValue(qhigh)
+        if maskneg is not None:
+            c.fMaskNeg.setValue(maskneg)
+        c.updateFuMin()
+        d.setConfig(c)
+        out[tag + "_raw"] = np.stack([np.asarray(d.x0.rawData, float), np.asarray(d.f.rawData, float),
+                                      np.asarray(d.f.rawDataU, float)], 1)
+        out[tag + "_cfg"] = np.array([c.nBin(), c.fuMin(), c.x0Low(), c.x0High(),
+                                      float(c.fMaskZero()), float(c.fMaskNeg())])
+        binned = d.f.binnedData is not None
+        out[tag + "_q"] = np.asarray(d.q, float).ravel()
+        out[tag + "_I"] = np.asarray(d.f.binnedData if binned else d.f.sanitized, float).ravel()
+        out[tag + "_sigma"] = np.asarray(d.f.binnedDataU if binned else d.f.sanitizedU, float).ravel()
+        print("dataprep", tag, out[tag + "_raw"].shape, "->", out[tag + "_q"].shape)
+
+    case("sphere10_default", "sasfit_sphere-10-1.dat")
+    case("quick_default", "quickstartdemo1.csv")
+    case("quick_nbin50_lim", "quickstartdemo1.csv", nbin=50, qlow=0.05e9, qhigh=1.5e9, maskneg=True)
+    case("quick_nobin", "quickstartdemo1.csv", nbin=0, fumin=0.02)
+    np.savez_compressed(os.path.join(OUT, "dataprep.npz"), **out)
+
+
+if __name__ == "__main__" and (not sys.argv[1:] or "dataprep" in sys.argv[1:]):
+    run_dataprep_cases()

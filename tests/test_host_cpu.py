@@ -177,3 +177,30 @@ def test_gloo_world2_gather(tmp_path):
                           "29731", str(script)], capture_output=True, text=True, timeout=240)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+@pytest.mark.parametrize("tag", ["sphere10_default", "quick_default", "quick_nbin50_lim", "quick_nobin"])
+def test_dataprep_matches_reference(tag):
+    """mcsas_b200.dataprep against the vectors the unmodified reference hands
+    to mcFit after loaddatafile -> updateFuMin -> setConfig (golden: oracle/gen_golden.py dataprep)."""
+    from mcsas_b200 import dataprep
+    g = np.load(os.path.join(common.GOLDEN, "dataprep.npz"))
+    raw, cfg = g[tag + "_raw"], g[tag + "_cfg"]
+    d = dataprep.prepare(raw[:, 0], raw[:, 1], raw[:, 2], n_bin=cfg[0], fu_min=cfg[1], x0_low=cfg[2],
+                         x0_high=cfg[3], mask_zero=bool(cfg[4]), mask_neg=bool(cfg[5]))
+    assert d.q.size == g[tag + "_q"].size
+    np.testing.assert_allclose(d.q, g[tag + "_q"], rtol=1e-14)
+    np.testing.assert_allclose(d.f.binnedData, g[tag + "_I"], rtol=1e-14)
+    np.testing.assert_allclose(d.f.binnedDataU, g[tag + "_sigma"], rtol=1e-13)
+
+
+def test_dataprep_edge_cases():
+    from mcsas_b200 import dataprep
+    q = np.array([0.1, 0.2, 0.3, 0.4])
+    I = np.array([10., np.nan, 0., -1.])
+    d = dataprep.prepare(q, I, None, n_bin=0, mask_zero=True, mask_neg=True)
+    assert d.q.size == 1 and d.f.binnedDataU[0] == pytest.approx(0.1)       # fuMin * I, no sigma column
+    d = dataprep.prepare(q, np.ones(4), np.zeros(4), n_bin=2)
+    assert d.q.size == 2 and (d.f.binnedDataU >= 0.01).all()                # floor at 1 % of I
+    with pytest.raises(ValueError):
+        dataprep.prepare(q, np.ones(3))
