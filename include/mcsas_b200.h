@@ -70,7 +70,7 @@ enum mcsas_quad_rule {
 
 enum mcsas_precision {
     MCSAS_FP64 = 0,   /* parity mode: all float64, reference operation order */
-    MCSAS_FP32 = 1    /* production: fp32 form factors (MUFU), fp64 LSQ sums */
+    MCSAS_FP32 = 1    /* production: fp32 form factors (MUFU) and delta sums, fp64 base sums and fit */
 };
 
 /* Settings of McSAS (src/mcsas/mcsas/mcsasparameters.json) that reach the hot path. */

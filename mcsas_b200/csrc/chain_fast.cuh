@@ -1,8 +1,8 @@
 // chain_fast.cuh -- the PRODUCTION (fp32) MC-chain kernel.
 //
 // Same contract as chain_kernel (chain_kernel.cuh): one greedy chain of McSAS.mcFit
-// (src/mcsas/mcsas/mcsas.py:287-439) per thread-block cluster, speculative batches,
-// producer warp + ring, time slices.  What differs is the arithmetic of the inner loop:
+// (src/mcsas/mcsas/mcsas.py:287-439) per thread-block cluster, speculative batches, a ring
+// of prepared proposals, time slices.  What differs:
 //
 //  * RESIDUAL-DELTA least squares.  The reference re-solves scale/background for every
 //    proposal (backgroundscalingfit.py:112-139).  chi^2(a,b) is an exact quadratic, so for
@@ -14,11 +14,20 @@
 //    fp32 accumulation resolves the accept test `chi2_new < chi2_old` (mcsas.py:379) to
 //    ~1e-6 of the CHANGE of chi2 -- no fp64 and no conversion in the inner loop.  The base
 //    sums of the accepted state are re-accumulated exactly in fp64 inside the next batch.
+//  * GRAM batches while moves are frequent: 8 steps per batch, all consumed; the Gram matrix
+//    of the proposals' changes lets warp 0 re-derive the sums of later proposals after each
+//    accepted one, so several moves are committed per batch (exact sequential semantics).
+//  * CONTRIBUTION-ROW CACHE: the scaled intensity rows of the current contributions live in
+//    a per-SM region of global memory (L2/HBM); the replaced contribution of a step is one
+//    coalesced 16-byte load per thread instead of a second evaluation (mcsas.py:362).
 //  * the 1/(qr)^3 of the sphere amplitude is split into a per-contribution factor (folded
-//    into the amplitude by the producer warp) and a per-q factor (folded into 1/sigma), so
-//    an evaluation costs MUFU.SIN + MUFU.COS and no MUFU.RCP.
-//  * wide CTAs: up to 31 eval warps; when the q slice of a CTA needs fewer warps the
-//    spare warps form further PROPOSAL GROUPS that evaluate other proposals of the batch.
+//    into the amplitude when a ring entry is prepared) and a per-q factor (folded into
+//    1/sigma), so an evaluation costs MUFU.SIN + MUFU.COS and no MUFU.RCP; the 32
+//    evaluations of a chunk of 8 proposals form one basic block (one warp vote selects the
+//    small-x series variant), which ptxas interleaves.
+//  * no dedicated producer warp: all 8 warps evaluate; while warp 0 solves the batch, the
+//    last warp prepares the ring entries of the next one.  When the q slice of a CTA needs
+//    fewer warps, the spare warps form PROPOSAL GROUPS that evaluate other chunks.
 #pragma once
 #include "chain_kernel.cuh"
 
@@ -263,41 +272,9 @@ __device__ __forceinline__ int tri_idx_rt(int n, int t, int s)
     return t * n - t * (t + 1) / 2 + (s - t - 1);
 }
 
-// Minimum of the exact quadratic chi^2 of the proposal with delta sums (s1..s4) around the
-// centre (a0,b0) of a state with base sums S, Sm, Smm, E0, E1, E2 (see file header).
-struct FastBase { double S, Sm, Smm, E0, E1, E2, a0, b0; };
-__device__ __forceinline__ void fast_solve(const FastBase &B, int find_bg, int pos_bg, double s1, double s2,
-                                           double s3, double s4, double &rss, double &an, double &bn,
-                                           double &e1n, double &e2n)
-{
-    const double Smp = B.Sm + s4, Smmp = B.Smm + 2. * s3 + s2;
-    const double f0 = B.E0 - 2. * B.a0 * s1 + B.a0 * B.a0 * s2;
-    const double ga = -2. * (B.E1 + s1 - B.a0 * (s3 + s2));
-    const double gb = -2. * (B.E2 - B.a0 * s4);
-    const double Haa = 2. * Smmp, Hab = 2. * Smp, Hbb = 2. * B.S;
-    double da, db = 0.;
-    if (find_bg) {
-        const double inv = 1. / (Haa * Hbb - Hab * Hab);
-        da = -(Hbb * ga - Hab * gb) * inv;
-        db = -(Haa * gb - Hab * ga) * inv;
-        rss = f0 + .5 * (ga * da + gb * db);
-        if (pos_bg && B.b0 + db < 0.) {                          // |b| residual -> b = 0 (:60-63)
-            db = -B.b0;
-            da = -(ga + Hab * db) / Haa;
-            rss = f0 + ga * da + gb * db + .5 * (Haa * da * da + 2. * Hab * da * db + Hbb * db * db);
-        }
-    } else {                                                     // chiNoBg (:66-70), b0 == 0
-        da = -ga / Haa;
-        rss = f0 + .5 * ga * da;
-    }
-    an = B.a0 + da;
-    bn = B.b0 + db;
-    // sum w e M and sum w e at the new centre (zero at an unconstrained minimum)
-    e1n = -.5 * (ga + Haa * da + Hab * db);
-    e2n = -.5 * (gb + Hab * da + Hbb * db);
-}
-
-// The same minimum in SCALED fp32 variables (decision latency: an fp64 chain of ~60
+// Minimum of the exact quadratic chi^2 of a proposal with delta sums (s1..s4) around the centre
+// (a0,b0) of a state with base sums S, Sm, Smm, E1 = sum w e M, E2 = sum w e (see file header),
+// in SCALED fp32 variables (decision latency: an fp64 chain of ~60
 // dependent operations per proposal is the critical path of a batch).  Unknowns
 // x = da sqrt(Smm), y = db sqrt(S); scaled Hessian 2 [[h11, h12], [h12, 1]] with entries of
 // order one for any data scale; every term is delta sized, the exact chi2 of the base state
