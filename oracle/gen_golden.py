@@ -369,3 +369,37 @@ def run_dataprep_cases():
 
 if __name__ == "__main__" and (not sys.argv[1:] or "dataprep" in sys.argv[1:]):
     run_dataprep_cases()
+
+
+def run_output_cases():
+    """Text layout of the reference's result files: Calculator.writeResults
+    (gui/calc.py:128-155) = AsciiFile.writeHeaderLine + appendFile (asciifile.py:15-68) on a
+    fit table and on a statistics-like table of pre-formatted cells."""
+    import tempfile
+    rh.install()
+    from mcsas.datafile.asciifile import AsciiFile
+    rng = np.random.default_rng(5)
+    cols = {"fitX0": np.logspace(7, 9, 7), "dataMean": rng.uniform(1, 1e6, 7),
+            "dataStd": rng.uniform(0.01, 10, 7), "fitMeasValMean": rng.uniform(1, 1e6, (1, 7)),
+            "fitMeasValStd": rng.uniform(0, 1, (1, 7))}
+    names = ('fitX0', 'dataMean', 'dataStd', 'fitMeasValMean', 'fitMeasValStd')
+    fn = tempfile.mktemp()
+    AsciiFile.writeHeaderLine(fn, names)
+    AsciiFile.appendFile(fn, np.vstack([cols[c] for c in names]).T)
+    fit_txt = open(fn).read()
+    stats = {"lower": [AsciiFile.formatValue(1e-9), AsciiFile.formatValue(5e-9)],
+             "upper": [AsciiFile.formatValue(1e-7)] * 2,
+             "weighting": [AsciiFile.formatValue("vol"), AsciiFile.formatValue("num")],
+             "mean": [AsciiFile.formatValue(9.7455e-9), AsciiFile.formatValue(-1.5)]}
+    sn = ("lower", "upper", "weighting", "mean")
+    AsciiFile.writeHeaderLine(fn, sn)
+    AsciiFile.appendFile(fn, np.vstack([stats[c] for c in sn]).T)
+    stats_txt = open(fn).read()
+    os.remove(fn)
+    np.savez_compressed(os.path.join(OUT, "output_formats.npz"), fit_txt=np.array(fit_txt),
+                        stats_txt=np.array(stats_txt), **{"col_" + k: v for k, v in cols.items()})
+    print("output formats ok:", len(fit_txt), len(stats_txt))
+
+
+if __name__ == "__main__" and (not sys.argv[1:] or "output" in sys.argv[1:]):
+    run_output_cases()

@@ -204,3 +204,50 @@ def test_dataprep_edge_cases():
     assert d.q.size == 2 and (d.f.binnedDataU >= 0.01).all()                # floor at 1 % of I
     with pytest.raises(ValueError):
         dataprep.prepare(q, np.ones(3))
+
+
+def test_output_tables_match_reference_layout(tmp_path):
+    """mcsas_b200.output: byte-identical to the reference's AsciiFile writer
+    (golden text recorded by oracle/gen_golden.py output)."""
+    from mcsas_b200 import output
+    g = np.load(os.path.join(common.GOLDEN, "output_formats.npz"))
+    res = dict((c, g["col_" + c]) for c in output.FIT_COLUMNS)
+    fn = output.write_fit(str(tmp_path / "x_fit.dat"), res)
+    assert open(fn).read() == str(g["fit_txt"])
+    cells = [[output.format_value(1e-9), output.format_value(5e-9)], [output.format_value(1e-7)] * 2,
+             [output.format_value("vol"), output.format_value("num")],
+             [output.format_value(9.7455e-9), output.format_value(-1.5)]]
+    fn = output.write_table(str(tmp_path / "x_stats.dat"), ("lower", "upper", "weighting", "mean"), cells)
+    assert open(fn).read() == str(g["stats_txt"])
+
+
+def test_output_files_from_a_result(tmp_path):
+    """Distribution / statistics / contributions / settings files from host objects (no GPU:
+    the histogram is fed with a synthetic contribution set)."""
+    import pickle
+    from mcsas_b200 import output
+    from mcsas_b200.mcsas import McSAS
+    from mcsas_b200.models import Sphere
+    from mcsas_b200.parameter import Histogram
+    rng = np.random.default_rng(0)
+    N, R = 50, 4
+    contribs = rng.uniform(2e-9, 9e-8, (N, 1, R))
+    frac = rng.uniform(0.1, 1., (N, R))
+    algo = McSAS.factory()()
+    algo.model = Sphere()
+    p = algo.model.radius
+    p.setActiveRange((1e-9, 1e-7))
+    p.histograms().append(Histogram(p, 1e-9, 1e-7, 10, 'log', 'vol'))
+    fractions = dict(vol=(frac, frac * 0.1), num=(frac, frac * 0.1), int=(frac, frac * 0.1), surf=(frac, frac * 0.1))
+    p.histograms().calc(contribs, 0, fractions)
+    h = p.histograms()[0]
+    lines = open(output.write_distribution(str(tmp_path / "h.dat"), h)).read().split("\n")
+    assert lines[0] == "xMean xWidth yMean yStd Obs cdfMean cdfStd" and len(lines) == 11
+    assert all(len(l) == 7 * 14 + 6 for l in lines[1:])
+    lines = open(output.write_statistics(str(tmp_path / "s.dat"), p)).read().split("\n")
+    assert lines[0].split()[:3] == ["lower", "upper", "weighting"] and len(lines) == 2
+    assert " vol " in lines[1]
+    fn = output.write_contributions(str(tmp_path / "c.pickle"), dict(contribs=contribs))
+    assert np.array_equal(pickle.load(open(fn, "rb")), contribs)
+    txt = open(output.write_settings(str(tmp_path / "s.cfg"), algo, "in.dat", "out", (1e7, 1e9))).read()
+    assert "[MCSAS Settings]" in txt and "numcontribs = 300" in txt.lower() and "radius_min" in txt
