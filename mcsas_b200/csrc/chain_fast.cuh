@@ -354,7 +354,10 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     // one row region per SM: every layout of this kernel fills the register file of an SM, so
     // a CTA has its SM to itself; the lock word only guards that assumption
     unsigned smid = 0;
-    if (CACHE) asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (CACHE) {
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        smid %= FAST_CACHE_SMS;                    // (the lock keeps aliased SMs apart; B200: 148 SMs)
+    }
     float *const crow = CACHE ? a.cache + (size_t)smid * a.cache_stride + qtid * QPT : nullptr;
 
     // ---- shared memory carve-up (keep in sync with fast_smem_bytes) -----------------------
