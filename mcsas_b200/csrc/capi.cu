@@ -519,6 +519,7 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     const size_t smem_limit = (size_t)ctx->prop.sharedMemPerBlockOptin;
     int ring = N < RING_MAX ? N : RING_MAX;
     if (cfg->precision == MCSAS_FP32) {                  // fp32 kernel indexes the ring with a mask
+        ring = N < FAST_RING_MAX ? N : FAST_RING_MAX;
         int p2 = 1;
         while (p2 * 2 <= ring) p2 *= 2;
         ring = p2;
@@ -536,7 +537,9 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
         smem = (size_t)120 * 1024;
     if (smem > smem_limit)
         return fail(ctx, MCSAS_ERR_ARG, "run: configuration needs %zu B shared memory (> %zu)", smem, smem_limit);
-    int kcap = cfg->spec_max <= 0 ? MCSAS_MAX_SPEC : (cfg->spec_max > MCSAS_MAX_SPEC ? MCSAS_MAX_SPEC : cfg->spec_max);
+    const int kcap_max = cfg->precision == MCSAS_FP32 ? FAST_KCAP : MCSAS_MAX_SPEC;
+    int kcap = cfg->spec_max <= 0 ? kcap_max : (cfg->spec_max > kcap_max ? kcap_max : cfg->spec_max);
+    if (const char *ke = getenv("MCSAS_B200_KMAX")) { if (atoi(ke) > 0 && atoi(ke) < kcap) kcap = atoi(ke); }
     if (kcap > ring / 4) kcap = ring / 4;
     if (kcap < 1) kcap = 1;
     if (cfg->precision == MCSAS_FP32) {                  // fp32 kernel: batches are powers of two
@@ -747,7 +750,9 @@ extern "C" int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms)
         }
         // ---- start backups: few chains alive, SMs idle, chain is late in its attempt -------------
         bool new_backups = false;
-        if (ctx->backups && n_primary > 0 && n_primary * 8 <= ctx->prop.multiProcessorCount) {
+        int bdiv = 8;
+        if (const char *bd = getenv("MCSAS_B200_BACKUP_DIV")) bdiv = atoi(bd) > 0 ? atoi(bd) : 8;
+        if (ctx->backups && n_primary > 0 && n_primary * bdiv <= ctx->prop.multiProcessorCount) {
             for (int c = 0; c < NC; ++c) {
                 if (ctx->done[c] || ctx->bak[c] >= 0) continue;
                 const int pslot = ctx->cur[c];

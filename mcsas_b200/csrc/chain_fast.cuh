@@ -369,15 +369,15 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     double *s_rset = (double *)carve(sizeof(double) * N * (P > 0 ? P : 1));
     carve(64);
     RingEntry<float> *s_ring = (RingEntry<float> *)carve((size_t)RING * sizeof(RingEntry<float>));
-    float4 *s_wsum = (float4 *)carve(16 * (size_t)FAST_MAX_WARPS * KCAP);
+    float4 *s_wsum = (float4 *)carve(16 * (size_t)FAST_MAX_WARPS * FAST_KCAP);
     double *s_bsum = (double *)carve(8 * (size_t)(FAST_MAX_WARPS + 1) * 6);
     constexpr int XU = FAST_XU;                    // b64 units per rank in an exchange buffer
     double *s_part = (double *)carve(8 * 2 * (size_t)MAX_CLUSTER * XU);
     uint64_t *s_xbar = (uint64_t *)carve(16);
     float *s_gram = (float *)carve(4 * (size_t)FAST_MAX_WARPS * 28);  // per-warp Gram pairs
     float *s_gtot = (float *)carve(4 * 32);
-    double *s_chi = (double *)carve(8 * (size_t)KCAP + 128);
-    FastDec *s_dec = (FastDec *)(s_chi + KCAP);
+    double *s_chi = (double *)carve(8 * (size_t)FAST_KCAP + 128);
+    FastDec *s_dec = (FastDec *)(s_chi + FAST_KCAP);
     double *s_asum = (double *)carve(8 * (size_t)(FAST_MAX_WARPS + 2) * 3 + 8 * 2 * MAX_CLUSTER * 3);
     double *s_apart = s_asum + (FAST_MAX_WARPS + 2) * 3;
     double *s_ft = (double *)carve(8 * 2 * FAST_QCAP);            // model intensity, double buffered
@@ -760,7 +760,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                             for (int i = 0; i < NGP; ++i) gq[i] += __shfl_xor_sync(0xffffffffu, gq[i], off);
                         }
                         if ((lane & (32 / FGRP - 1)) == 0)
-                            s_wsum[wq * KCAP + perm] = make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
+                            s_wsum[wq * FAST_KCAP + perm] = make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
                         if (lane == 0) {                          // perm == 0: natural proposal order
 #pragma unroll
                             for (int i = 0; i < NGP; ++i) s_gram[wq * NGP + i] = gq[i];
@@ -824,7 +824,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                             for (int i = 0; i < 4; ++i)
                                 acc[0][i] += __shfl_xor_sync(0xffffffffu, acc[0][i], off);
                         if ((lane & (32 / FGRP - 1)) == 0)
-                            s_wsum[wq * KCAP + k0 + perm] = make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
+                            s_wsum[wq * FAST_KCAP + k0 + perm] = make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
                         if (a.prof) { ptc[k0 == 0 ? 0 : 1] += clock64() - ptk; ptc[k0 == 0 ? 2 : 3] += 1; }
                     }
                 } else if (grp == 0) {
@@ -857,7 +857,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                         for (int off = 16; off >= 1; off >>= 1)
 #pragma unroll
                             for (int i = 0; i < 4; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
-                        if (lane == 0) s_wsum[wq * KCAP + k] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                        if (lane == 0) s_wsum[wq * FAST_KCAP + k] = make_float4(acc[0], acc[1], acc[2], acc[3]);
                     }
                 }
             }
@@ -875,7 +875,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             filled = max(filled, fill_to);
             // ---- exchange the partial sums over the cluster (st.async + mbarrier) -------------
             // units of a rank's exchange row: [0, 2K) two floats each of the proposal sums,
-            // [2 KCAP, +5) base sums, [2 KCAP + 5] watchdog flag, [2 KCAP + 8, +NGU) Gram pairs
+            // [2 FAST_KCAP, +5) base sums, [2 FAST_KCAP + 5] watchdog flag, [2 FAST_KCAP + 8, +NGU) Gram pairs
             double *part = s_part + (size_t)abuf * MAX_CLUSTER * XU;
             const int nb5 = dirty ? 5 : 0;
             if (C > 1) {
@@ -887,16 +887,16 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     if (i < nprop) {                             // two floats of proposal i/2
                         const float *src = (const float *)s_wsum + (size_t)(i >> 1) * 4 + (i & 1) * 2;
                         float x0 = 0.f, x1 = 0.f;
-                        for (int wv = 0; wv < WQ; ++wv) { x0 += src[(size_t)wv * KCAP * 4]; x1 += src[(size_t)wv * KCAP * 4 + 1]; }
+                        for (int wv = 0; wv < WQ; ++wv) { x0 += src[(size_t)wv * FAST_KCAP * 4]; x1 += src[(size_t)wv * FAST_KCAP * 4 + 1]; }
                         x = __hiloint2double(__float_as_int(x1), __float_as_int(x0));
                         du = i;
                     } else if (i < nprop + nb5) {
                         x = 0.;
                         for (int wv = 0; wv < WQ; ++wv) x += s_bsum[wv * 6 + (i - nprop)];
-                        du = 2 * KCAP + (i - nprop);
+                        du = 2 * FAST_KCAP + (i - nprop);
                     } else if (i == nprop + nb5) {
                         x = wd ? 1. : 0.;
-                        du = 2 * KCAP + 5;
+                        du = 2 * FAST_KCAP + 5;
                     } else {                                     // two Gram pairs
                         const int g = 2 * (i - nprop - nb5 - 1);
                         float x0 = 0.f, x1 = 0.f;
@@ -905,7 +905,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                             if (g + 1 < NGP) x1 += s_gram[wv * NGP + g + 1];
                         }
                         x = __hiloint2double(__float_as_int(x1), __float_as_int(x0));
-                        du = 2 * KCAP + 8 + (g >> 1);
+                        du = 2 * FAST_KCAP + 8 + (g >> 1);
                     }
                     double *dst = part + (size_t)rank * XU + du;
                     for (int r = 0; r < C; ++r) dsmem_store_async(dst, s_xbar + abuf, (uint32_t)r, x);
@@ -913,7 +913,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                 if (warp == 0) {
                     mbar_wait(s_xbar + abuf, (xphase >> abuf) & 1);
                     bool anywd = false;
-                    for (int r = 0; r < C; ++r) anywd |= part[(size_t)r * XU + 2 * KCAP + 5] != 0.;
+                    for (int r = 0; r < C; ++r) anywd |= part[(size_t)r * XU + 2 * FAST_KCAP + 5] != 0.;
                     wd = anywd;
                 }
                 xphase ^= 1u << abuf;
@@ -924,7 +924,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                 if (dirty) {                                     // fresh base sums: lane i < 5 adds quantity i
                     double x = 0.;
                     if (lane < 5) {
-                        if (C > 1) { for (int r = 0; r < C; ++r) x += part[(size_t)r * XU + 2 * KCAP + lane]; }
+                        if (C > 1) { for (int r = 0; r < C; ++r) x += part[(size_t)r * XU + 2 * FAST_KCAP + lane]; }
                         else { for (int wv = 0; wv < WQ; ++wv) x += s_bsum[wv * 6 + lane]; }
                     }
                     const double E0 = __shfl_sync(0xffffffffu, x, 0), E1 = __shfl_sync(0xffffffffu, x, 1);
@@ -939,8 +939,9 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     conval = E0 * L.inv_nq;
                 }
                 if (a.prof) pd[1] = clock64();
-                float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
-                const bool mine = lane < Kb && !wd;
+                // lane l owns proposals l and l + 32 (second round only for batches of 64)
+                float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, t4 = 0.f;
+                const bool mine = lane < Kb && !wd, mine2 = lane + 32 < Kb && !wd;
                 if (mine) {
                     if (C > 1) {
                         for (int r = 0; r < C; ++r) {
@@ -949,8 +950,21 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                         }
                     } else {
                         for (int wv = 0; wv < WQ; ++wv) {
-                            const float4 v = s_wsum[wv * KCAP + lane];
+                            const float4 v = s_wsum[wv * FAST_KCAP + lane];
                             s1 += v.x; s2 += v.y; s3 += v.z; s4 += v.w;
+                        }
+                    }
+                }
+                if (mine2) {
+                    if (C > 1) {
+                        for (int r = 0; r < C; ++r) {
+                            const float4 v = *(const float4 *)(part + (size_t)r * XU + 2 * (lane + 32));
+                            t1 += v.x; t2 += v.y; t3 += v.z; t4 += v.w;
+                        }
+                    } else {
+                        for (int wv = 0; wv < WQ; ++wv) {
+                            const float4 v = s_wsum[wv * FAST_KCAP + lane + 32];
+                            t1 += v.x; t2 += v.y; t3 += v.z; t4 += v.w;
                         }
                     }
                 }
@@ -965,11 +979,23 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                         better = delta < 0.f;                    // :379 strict: chi2' < chi2
                         s_chi[lane] = conval + (double)delta * L.inv_nq;
                     }
-                    const unsigned mask = __ballot_sync(0xffffffffu, better);
-                    ks = mask ? (__ffs(mask) - 1) : -1;
+                    unsigned mask = __ballot_sync(0xffffffffu, better);
+                    int koff = 0;
+                    if (!mask && Kb > 32) {                      // second round: proposals 32 .. 63
+                        better = false;
+                        if (mine2) {
+                            fast_solve_f(F, L.find_bg, L.pos_bg, t1, t2, t3, t4, delta, x, y, h11, h12, e1, e2);
+                            better = delta < 0.f;
+                            s_chi[lane + 32] = conval + (double)delta * L.inv_nq;
+                        }
+                        mask = __ballot_sync(0xffffffffu, better);
+                        koff = 32;
+                    }
+                    const int kl = mask ? (__ffs(mask) - 1) : -1;
+                    ks = kl >= 0 ? kl + koff : -1;
                     if (ks >= 0) {
-                        const float xs = __shfl_sync(0xffffffffu, x, ks), ys = __shfl_sync(0xffffffffu, y, ks);
-                        const float ds = __shfl_sync(0xffffffffu, delta, ks);
+                        const float xs = __shfl_sync(0xffffffffu, x, kl), ys = __shfl_sync(0xffffffffu, y, kl);
+                        const float ds = __shfl_sync(0xffffffffu, delta, kl);
                         ca = a0 + (double)xs * (double)F.rSmm;
                         cb = b0 + (double)ys * (double)F.rS;
                         cc = conval + (double)ds * L.inv_nq;
@@ -979,7 +1005,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     for (int i = lane; i < NGP; i += 32) {
                         float v = 0.f;
                         if (C > 1) {
-                            for (int r = 0; r < C; ++r) v += ((const float *)(part + (size_t)r * XU + 2 * KCAP + 8))[i];
+                            for (int r = 0; r < C; ++r) v += ((const float *)(part + (size_t)r * XU + 2 * FAST_KCAP + 8))[i];
                         } else {
                             for (int wv = 0; wv < WQ; ++wv) v += s_gram[wv * NGP + i];
                         }

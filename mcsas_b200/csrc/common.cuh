@@ -129,7 +129,9 @@ __host__ __device__ inline size_t chain_smem_bytes(int nq_pad, int N, int P, int
 
 // ---- shared-memory footprint of chain_fast_kernel (mirrors its carve-up) -----------------------------
 #define FAST_MAX_WARPS 32
-#define FAST_XU (2 * KCAP + 8 + 16) // 64-bit units per rank in a cluster exchange buffer
+#define FAST_KCAP 64               // fp32 kernel: speculative proposals per batch (2 per decision lane)
+#define FAST_RING_MAX 256          // ... ring entries (>= 4 * FAST_KCAP)
+#define FAST_XU (2 * FAST_KCAP + 8 + 16) // 64-bit units per rank in a cluster exchange buffer
 #define FAST_CACHE_SMS 256         // row regions allocated (>= %nsmid of a B200)
 #define FAST_QCAP 1024            // q points per CTA (QPT * 32 * warps_q)
 __host__ __device__ inline size_t fast_smem_bytes(int nq_pad, int N, int P, int D, int narr, int ring)
@@ -140,12 +142,12 @@ __host__ __device__ inline size_t fast_smem_bytes(int nq_pad, int N, int P, int 
     s += AL16(8 * (size_t)N * (P > 0 ? P : 1));                  // rset
     s += AL16(64);                                               // ctrl
     s += AL16((size_t)ring * (8 * MCSAS_MAX_ACTIVE + 2 * 4 * 8));// ring entries
-    s += AL16(16 * (size_t)FAST_MAX_WARPS * KCAP);               // per-warp proposal sums (float4)
+    s += AL16(16 * (size_t)FAST_MAX_WARPS * FAST_KCAP);          // per-warp proposal sums (float4)
     s += AL16(8 * (size_t)(FAST_MAX_WARPS + 1) * 6);             // per-warp base sums
     s += AL16(8 * 2 * (size_t)MAX_CLUSTER * FAST_XU);            // cluster exchange, 2 buffers
     s += AL16(4 * (size_t)FAST_MAX_WARPS * 28) + AL16(4 * 32);   // Gram pairs per warp + totals
     s += 16;                                                     // exchange mbarriers
-    s += AL16(8 * (size_t)KCAP + 128);                           // chi per proposal + decision
+    s += AL16(8 * (size_t)FAST_KCAP + 128);                      // chi per proposal + decision
     s += AL16(8 * (size_t)(FAST_MAX_WARPS + 2) * 3 + 8 * 2 * MAX_CLUSTER * 3);   // full-LSQ all-sum
     s += AL16(8 * 2 * FAST_QCAP) + 2 * AL16(8 * FAST_QCAP) + AL16(4 * FAST_QCAP);   // ft (x2), I, 1/sigma, q scale
     s += 2 * AL16(4 * (size_t)(D + 1));                          // quadrature table

@@ -17,7 +17,7 @@ for tag, env in runs:
     eng = Engine(0)
     eng.upload_datasets([(q, I, sig)])
     eng.set_model(0, [10e-9, 1e14], [0], [1e-9], [100e-9], [0])
-    cfg = Engine.make_config(n_contribs=300, n_reps=100, precision=FP32, seed=7919, max_iter=100000, max_retries=-1)
+    cfg = Engine.make_config(n_contribs=300, n_reps=int(os.environ.get('REPS', '100')), precision=FP32, seed=7919, max_iter=100000, max_retries=-1)
     print("==", tag, flush=True)
     sys.stderr.flush()
     try:
