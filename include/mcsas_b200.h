@@ -136,6 +136,9 @@ int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms);
 int mcsas_request_stop(mcsas_ctx *ctx);
 /* Facts about the last run: kernel launches (time slices), last cluster size, summed kernel ms. */
 int mcsas_run_info(mcsas_ctx *ctx, int *n_launches, int *last_cluster, float *kernel_ms);
+/* Scheduler facts of the last run: backup attempts (the next retry of a late chain, mcsas.py:220-246,
+ * started ahead of time on idle SMs) started and promoted to the chain's current attempt. */
+int mcsas_scheduler_info(mcsas_ctx *ctx, int *backups_started, int *backups_used);
 
 /* -- results of the last run (any pointer may be NULL).  Layouts:
  *    contribs [set][N][P][R] (numpy zeros((N,P,R)) per set, mcsas.py:203-205),

@@ -17,7 +17,7 @@ GEN_UNIFORM, GEN_EXP1, GEN_EXP2, GEN_EXP3 = 0, 1, 2, 3
 EXPORTS = [
     "mcsas_ctx_create", "mcsas_ctx_destroy", "mcsas_last_error", "mcsas_device_info",
     "mcsas_upload_datasets", "mcsas_set_model", "mcsas_eval", "mcsas_run", "mcsas_run_async",
-    "mcsas_wait", "mcsas_request_stop", "mcsas_run_info", "mcsas_fetch", "mcsas_fetch_trace", "mcsas_fractions",
+    "mcsas_wait", "mcsas_request_stop", "mcsas_run_info", "mcsas_scheduler_info", "mcsas_fetch", "mcsas_fetch_trace", "mcsas_fractions",
     "mcsas_measure_peaks",
 ]
 
@@ -66,6 +66,7 @@ def lib():
     L.mcsas_wait.argtypes = [vp, C.POINTER(C.c_float)]
     L.mcsas_request_stop.argtypes = [vp]
     L.mcsas_run_info.argtypes = [vp, ip, ip, C.POINTER(C.c_float)]
+    L.mcsas_scheduler_info.argtypes = [vp, ip, ip]
     L.mcsas_fetch.argtypes = [vp, dp, dp, dp, dp, dp, dp, llp, llp, ip, dp, llp, llp]
     L.mcsas_fetch_trace.argtypes = [vp, C.c_int, C.POINTER(C.c_ubyte), dp, C.c_longlong]
     L.mcsas_fractions.argtypes = [vp, C.POINTER(RunConfig)] + [dp] * 11

@@ -826,6 +826,14 @@ extern "C" int mcsas_run_info(mcsas_ctx *ctx, int *n_launches, int *last_cluster
     return MCSAS_OK;
 }
 
+extern "C" int mcsas_scheduler_info(mcsas_ctx *ctx, int *backups_started, int *backups_used)
+{
+    if (!ctx) return MCSAS_ERR_ARG;
+    if (backups_started) *backups_started = ctx->n_backups_started;
+    if (backups_used) *backups_used = ctx->n_backups_used;
+    return MCSAS_OK;
+}
+
 extern "C" int mcsas_fetch(mcsas_ctx *ctx, double *contribs, double *fit_meas, double *scaling,
                            double *background, double *conval, double *conval0, long long *num_iter,
                            long long *num_moves, int *attempts, double *elapsed_s, long long *evals,

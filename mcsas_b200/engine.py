@@ -134,6 +134,11 @@ class Engine(object):
         self._check(self._L.mcsas_run_info(self._ctx, C.byref(n), C.byref(c), C.byref(ms)), "run_info")
         return dict(launches=n.value, last_cluster=c.value, kernel_ms=ms.value)
 
+    def scheduler_info(self):
+        s, u = C.c_int(), C.c_int()
+        self._check(self._L.mcsas_scheduler_info(self._ctx, C.byref(s), C.byref(u)), "scheduler_info")
+        return dict(backups_started=s.value, backups_used=u.value)
+
     def request_stop(self):
         self._L.mcsas_request_stop(self._ctx)
 

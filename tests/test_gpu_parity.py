@@ -235,3 +235,36 @@ def test_many_chains_run_in_waves_and_do_not_depend_on_packing():
     assert abs(np.median(big["conval"][1]) / np.median(big["conval"][0]) - 1) < 0.2
     assert abs(np.median(big["scaling"][1]) / np.median(big["scaling"][0]) - 2.0) < 0.2
     assert abs(np.median(big["scaling"][2]) / np.median(big["scaling"][0]) - 0.5) < 0.05
+
+
+def test_backup_attempts_do_not_change_results():
+    """Scheduler: the next attempt of a late chain is started ahead of time on idle SMs
+    (capi.cu: mcsas_wait).  An attempt depends on (seed, chain, attempt number) only, so with a
+    fixed layout the results must be bit-identical with and without backups -- here every
+    attempt fails (unreachable criterion), i.e. every backup is promoted."""
+    from mcsas_b200 import Engine
+    g = common.load_chain("sphere_cfg1")
+    om = common.oracle_model(g)
+    kw = dict(n_contribs=60, n_reps=12, conv_crit=1e-6, max_iter=12000, max_retries=1, precision=FP32,
+              seed=31, cluster_size=1)
+    outs = []
+    for flag in ("1", "0"):
+        os.environ["MCSAS_B200_BACKUP"] = flag
+        try:
+            eng = gpu_common.engine_for(om, [(g["q"], g["I"], g["sigma"])])
+            eng.run(Engine.make_config(**kw))
+            outs.append(eng.fetch())
+            info = eng.scheduler_info()
+            eng.close()
+        finally:
+            del os.environ["MCSAS_B200_BACKUP"]
+        if flag == "1":
+            assert info["backups_started"] >= 12 and info["backups_used"] >= 12, info
+        else:
+            assert info["backups_started"] == 0
+    a, b = outs
+    assert (a["attempts"] == 3).all() and (b["attempts"] == 3).all()          # maxRetries + 2
+    assert (a["num_iter"] == 12000).all()
+    for k in ("contribs", "conval", "scaling", "background", "num_moves", "steps_all", "evals"):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+    assert (a["steps_all"] == 36000).all()
