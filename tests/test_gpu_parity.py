@@ -268,3 +268,63 @@ def test_backup_attempts_do_not_change_results():
     for k in ("contribs", "conval", "scaling", "background", "num_moves", "steps_all", "evals"):
         np.testing.assert_array_equal(a[k], b[k], err_msg=k)
     assert (a["steps_all"] == 36000).all()
+
+
+def _sphere_engine(sets, lo=1e-9, hi=100e-9):
+    from mcsas_b200 import Engine
+    eng = Engine(0)
+    eng.upload_datasets(sets)
+    eng.set_model(0, [10e-9, 1e14], [0], [lo], [hi], [0])
+    return eng
+
+
+@pytest.mark.parametrize("prec", [FP64, FP32])
+def test_ragged_datasets_in_one_launch(prec):
+    """Datasets of different length share a launch (nq 100, 37, 64): every chain uses its own
+    nq; results equal those of the dataset run alone."""
+    from mcsas_b200 import Engine, synth
+    sets = [synth.sphere_curve(nq=n, seed=i) for i, n in enumerate((100, 37, 64))]
+    kw = dict(n_contribs=40, n_reps=3, max_iter=600, max_retries=-1, precision=prec, seed=5, cluster_size=1)
+    eng = _sphere_engine(sets)
+    eng.run(Engine.make_config(**kw))
+    out = eng.fetch()
+    eng.close()
+    assert [f.shape for f in out["fit_meas"]] == [(100, 3), (37, 3), (64, 3)]
+    assert np.isfinite(out["conval"]).all() and (out["conval"] < out["conval0"]).all()
+    eng = _sphere_engine(sets[1:2])
+    eng.run(Engine.make_config(first_chain=3, **kw))          # same global chain ids as in the batch
+    one = eng.fetch()
+    eng.close()
+    np.testing.assert_array_equal(out["contribs"][1], one["contribs"][0])
+    np.testing.assert_allclose(out["fit_meas"][1], one["fit_meas"][0], rtol=1e-12)
+
+
+def test_maximum_nq_and_tiny_inputs():
+    """nq = MCSAS_MAX_NQ (4096: the q axis must be split over a cluster), nq = 3 and a single
+    contribution (mcsas.py:354: no MC step is made with one contribution)."""
+    from mcsas_b200 import Engine, McSASB200Error, synth
+    q, I, s = synth.sphere_curve(nq=4096)
+    eng = _sphere_engine([(q, I, s)])
+    eng.run(Engine.make_config(n_contribs=300, n_reps=2, max_iter=3000, max_retries=-1, precision=FP32, seed=1))
+    out = eng.fetch()
+    assert np.isfinite(out["conval"]).all() and (out["conval"] < out["conval0"]).all()
+    assert out["fit_meas"][0].shape == (4096, 2)
+    eng.run(Engine.make_config(n_contribs=300, n_reps=2, max_iter=3000, max_retries=-1, precision=FP64, seed=1))
+    ref = eng.fetch()                                      # the fp64 parity kernel on the same Philox streams
+    np.testing.assert_allclose(out["conval0"], ref["conval0"], rtol=1e-5)
+    np.testing.assert_allclose(out["conval"], ref["conval"], rtol=0.05)
+    with pytest.raises(McSASB200Error):
+        eng.upload_datasets([(np.ones(4097), np.ones(4097), np.ones(4097))])
+    with pytest.raises(McSASB200Error):
+        eng.upload_datasets([(np.array([1e8, np.nan]), np.ones(2), np.ones(2))])
+    eng.close()
+    q, I, s = synth.sphere_curve(nq=3)
+    for prec in (FP64, FP32):
+        eng = _sphere_engine([(q, I, s)])
+        eng.run(Engine.make_config(n_contribs=5, n_reps=2, max_iter=200, max_retries=-1, precision=prec, seed=2))
+        out = eng.fetch()
+        assert np.isfinite(out["conval"]).all()
+        eng.run(Engine.make_config(n_contribs=1, n_reps=2, max_iter=200, max_retries=-1, precision=prec, seed=2))
+        out = eng.fetch()
+        assert (out["num_iter"] == 0).all() and np.isfinite(out["conval"]).all()
+        eng.close()
