@@ -51,12 +51,17 @@ def config3(reps):
     m.aspect.setActive(True)
     m.radius.setActiveRange((1 * NM, 50 * NM))
     m.aspect.setActiveRange((1., 20.))
+    if os.environ.get("QUAD_GL"):                       # Gauss-Legendre orientation average, fewer nodes
+        from mcsas_b200 import _lib
+        m.quadRule, m.quadNodes = _lib.QUAD_GAUSS_LEGENDRE, int(os.environ["QUAD_GL"])
     rng = np.random.default_rng(3)
     radii = np.clip(rng.normal(5., 1., 400), 0.5, None) * NM
     pset = np.stack([radii, np.full_like(radii, 5.0)], 1)
     it = m.calc(q, pset, 1.0).cumInt          # sum of V^2 F^2
     I, sig = noisy(it, 3)
-    fit("configs[2]: CylindersIsotropic radius+aspect, 500 q", m, q, I, sig, reps)
+    fit("configs[2]: CylindersIsotropic radius+aspect, 500 q%s" % (
+        ", GL %s nodes" % os.environ["QUAD_GL"] if os.environ.get("QUAD_GL") else ", reference 100-node rule"),
+        m, q, I, sig, reps, max_iter=int(os.environ.get("CYL_MAXIT", "100000")))
 
 
 def config4(reps):
