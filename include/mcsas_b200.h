@@ -131,6 +131,8 @@ int mcsas_run(mcsas_ctx *ctx, const mcsas_run_config *cfg,
 int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
                     const double *proposal_stream, long long stream_stride,
                     volatile int *stop_flag);
+/* kernel_ms: device time (CUDA events) from the start of the first time-slice launch to the end of
+ * the last one, i.e. including the scheduler's gaps between slices. */
 int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms);
 /* Ask a running fit to stop at its next time-slice boundary (McSAS.stop). */
 int mcsas_request_stop(mcsas_ctx *ctx);

@@ -32,7 +32,8 @@ static const eval_launch_fn EVAL_FN[MCSAS_N_MODELS] = {
 struct mcsas_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_begin = nullptr;
+    float span_ms = 0.f;          // first launch start -> last slice end (host gaps between slices included)
     cudaDeviceProp prop;
     std::string err;
     // datasets
@@ -121,6 +122,7 @@ extern "C" int mcsas_ctx_create(int device, mcsas_ctx **out)
     if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess
         || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess
         || cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess
+        || cudaEventCreate(&ctx->ev_begin) != cudaSuccess
         || cudaHostAlloc((void **)&ctx->h_stop, sizeof(int), cudaHostAllocMapped) != cudaSuccess
         || cudaHostGetDevicePointer((void **)&ctx->d_stop, ctx->h_stop, 0) != cudaSuccess) {
         g_create_err = std::string("CUDA context setup failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -141,7 +143,7 @@ extern "C" void mcsas_ctx_destroy(mcsas_ctx *ctx)
     cudaFree(ctx->d_rset); cudaFree(ctx->d_fit); cudaFree(ctx->d_scal); cudaFree(ctx->d_cnt);
     cudaFree(ctx->d_att); cudaFree(ctx->d_tacc); cudaFree(ctx->d_tchi); cudaFree(ctx->d_ids); cudaFree(ctx->d_prof); cudaFree(ctx->d_cache); cudaFree(ctx->d_cache_lock);
     cudaFreeHost(ctx->h_stop);
-    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_begin);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -673,6 +675,7 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     ctx->kernel_ms = 0.f;
     ctx->stop_flag = stop_flag;
     *ctx->h_stop = 0;
+    CK(cudaEventRecord(ctx->ev_begin, ctx->stream));
     int rc = launch_slice(ctx, n_chains, false);
     if (rc) return rc;
     ctx->running = true;
@@ -804,7 +807,8 @@ extern "C" int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms)
                     (double)tot[17] / tot[6]);
         }
     }
-    if (kernel_ms) *kernel_ms = ctx->kernel_ms;
+    CK(cudaEventElapsedTime(&ctx->span_ms, ctx->ev_begin, ctx->ev1));
+    if (kernel_ms) *kernel_ms = ctx->span_ms;
     ctx->have_run = true;
     return MCSAS_OK;
 }
