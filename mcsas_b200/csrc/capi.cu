@@ -615,6 +615,7 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
         // auto: a slice is a number of BATCHES (similar duration whether a chain is in its
         // move-rich early phase or late), the step limit stays as an upper bound
         a.slice_batches = 384;
+        if (const char *sb = getenv("MCSAS_B200_SLICE_BATCHES")) { if (atoi(sb) > 0) a.slice_batches = atoi(sb); }
         a.slice_steps = 16384;
     }
     a.sets = ctx->d_sets; a.data = ctx->d_data;

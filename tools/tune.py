@@ -17,7 +17,7 @@ REPS = int(os.environ.get("TUNE_REPS", "100"))
 
 def run(tag, env, seeds=(1, 2, 4, 7), **cfgkw):
     for k in list(os.environ):
-        if k.startswith("MCSAS_B200_") and k not in ("MCSAS_B200_DEBUG", "MCSAS_B200_BACKUP", "MCSAS_B200_BACKUP_DIV", "MCSAS_B200_KMAX"):
+        if k.startswith("MCSAS_B200_") and k not in ("MCSAS_B200_DEBUG", "MCSAS_B200_BACKUP", "MCSAS_B200_BACKUP_DIV", "MCSAS_B200_KMAX", "MCSAS_B200_SLICE_BATCHES"):
             del os.environ[k]
     os.environ.update(env)
     q, I, sig = synth.sphere_curve(nq=NQ)
