@@ -273,41 +273,41 @@ __device__ __forceinline__ int tri_idx_rt(int n, int t, int s)
 }
 
 // Minimum of the exact quadratic chi^2 of a proposal with delta sums (s1..s4) around the centre
-// (a0,b0) of a state with base sums S, Sm, Smm, E1 = sum w e M, E2 = sum w e (see file header),
-// in SCALED fp32 variables (decision latency: an fp64 chain of ~60
-// dependent operations per proposal is the critical path of a batch).  Unknowns
-// x = da sqrt(Smm), y = db sqrt(S); scaled Hessian 2 [[h11, h12], [h12, 1]] with entries of
-// order one for any data scale; every term is delta sized, the exact chi2 of the base state
-// enters only as  chi2' = chi2 + delta / nq.
-struct FastBaseF {
-    float rSmm, rS, c12, a0, b0, e1s, e2s;     // 1/sqrt(Smm), 1/sqrt(S), Sm rSmm rS, centre, E1 rSmm, E2 rS
-};
-__device__ __forceinline__ void fast_solve_f(const FastBaseF &F, int find_bg, int pos_bg, float s1, float s2,
-                                             float s3, float s4, float &delta, float &x, float &y,
-                                             float &h11, float &h12, float &e1n, float &e2n)
+// (a0,b0) of a state with base sums S, Sm, Smm, E0 = sum w e^2, E1 = sum w e M, E2 = sum w e (see
+// file header).  fp64: the direct change of chi^2 and the gain of the re-fit cancel to the
+// ~1e-8 level on high signal-to-noise data (an fp32 version of this solve was measured no
+// faster -- the decision is bound by its cold code, not by arithmetic latency -- and flipped
+// accept decisions on the 0.01 %-uncertainty golden set).
+struct FastBase { double S, Sm, Smm, E0, E1, E2, a0, b0; };
+__device__ __forceinline__ void fast_solve(const FastBase &B, int find_bg, int pos_bg, double s1, double s2,
+                                           double s3, double s4, double &rss, double &an, double &bn,
+                                           double &e1n, double &e2n)
 {
-    const float gx = -2.f * (F.e1s + (s1 - F.a0 * (s3 + s2)) * F.rSmm);
-    const float gy = -2.f * (F.e2s - F.a0 * s4 * F.rS);
-    h11 = fmaf(2.f * s3 + s2, F.rSmm * F.rSmm, 1.f);
-    h12 = fmaf(s4, F.rSmm * F.rS, F.c12);
-    const float d0 = F.a0 * (F.a0 * s2 - 2.f * s1);
+    const double Smp = B.Sm + s4, Smmp = B.Smm + 2. * s3 + s2;
+    const double f0 = B.E0 - 2. * B.a0 * s1 + B.a0 * B.a0 * s2;
+    const double ga = -2. * (B.E1 + s1 - B.a0 * (s3 + s2));
+    const double gb = -2. * (B.E2 - B.a0 * s4);
+    const double Haa = 2. * Smmp, Hab = 2. * Smp, Hbb = 2. * B.S;
+    double da, db = 0.;
     if (find_bg) {
-        const float inv = 0.5f / (h11 - h12 * h12);
-        x = -(gx - h12 * gy) * inv;
-        y = -(h11 * gy - h12 * gx) * inv;
-        delta = d0 + .5f * (gx * x + gy * y);
-        if (pos_bg && F.b0 + y * F.rS < 0.f) {                   // |b| residual -> b = 0 (:60-63)
-            y = -F.b0 / F.rS;
-            x = -(gx + 2.f * h12 * y) / (2.f * h11);
-            delta = d0 + gx * x + gy * y + (h11 * x * x + 2.f * h12 * x * y + y * y);
+        const double inv = 1. / (Haa * Hbb - Hab * Hab);
+        da = -(Hbb * ga - Hab * gb) * inv;
+        db = -(Haa * gb - Hab * ga) * inv;
+        rss = f0 + .5 * (ga * da + gb * db);
+        if (pos_bg && B.b0 + db < 0.) {                          // |b| residual -> b = 0 (:60-63)
+            db = -B.b0;
+            da = -(ga + Hab * db) / Haa;
+            rss = f0 + ga * da + gb * db + .5 * (Haa * da * da + 2. * Hab * da * db + Hbb * db * db);
         }
     } else {                                                     // chiNoBg (:66-70), b0 == 0
-        y = 0.f;
-        x = -gx / (2.f * h11);
-        delta = d0 + .5f * gx * x;
+        da = -ga / Haa;
+        rss = f0 + .5 * ga * da;
     }
-    e1n = -.5f * (gx + 2.f * h11 * x + 2.f * h12 * y);
-    e2n = -.5f * (gy + 2.f * h12 * x + 2.f * y);
+    an = B.a0 + da;
+    bn = B.b0 + db;
+    // sum w e M and sum w e at the new centre (zero at an unconstrained minimum)
+    e1n = -.5 * (ga + Haa * da + Hab * db);
+    e2n = -.5 * (gb + Hab * da + Hbb * db);
 }
 
 template <int NG> __device__ __forceinline__ int grp_perm(int lane)
@@ -635,9 +635,8 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         // committed up to the first accepted one) when moves are rare, and GRAM (exactly FGRP
         // steps, all of them consumed: the Gram matrix of the proposals' changes lets warp 0
         // re-derive the sums of later proposals after each accepted one) when moves are frequent.
-        const double rS_const = rsqrt(L.S);
-        FastBaseF F;                                             // meaningful in warp 0 only
-        F.rSmm = 1.f; F.rS = 1.f; F.c12 = 0.f; F.a0 = (float)a0; F.b0 = (float)b0; F.e1s = 0.f; F.e2s = 0.f;
+        FastBase B;                                              // meaningful in warp 0 only
+        B.S = L.S; B.Sm = 0.; B.Smm = 0.; B.E0 = 0.; B.E1 = 0.; B.E2 = 0.; B.a0 = a0; B.b0 = b0;
         while (live) {
             const long long pt0 = a.prof ? clock64() : 0;
             int Kb = min(K, kmax);
@@ -927,16 +926,13 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                         if (C > 1) { for (int r = 0; r < C; ++r) x += part[(size_t)r * XU + 2 * FAST_KCAP + lane]; }
                         else { for (int wv = 0; wv < WQ; ++wv) x += s_bsum[wv * 6 + lane]; }
                     }
-                    const double E0 = __shfl_sync(0xffffffffu, x, 0), E1 = __shfl_sync(0xffffffffu, x, 1);
-                    const double E2 = __shfl_sync(0xffffffffu, x, 2), Sm = __shfl_sync(0xffffffffu, x, 3);
-                    const double Smm = __shfl_sync(0xffffffffu, x, 4);
-                    const double rSmm = rsqrt(Smm), rS = rS_const;
-                    F.rSmm = (float)rSmm; F.rS = (float)rS; F.c12 = (float)(Sm * rSmm * rS);
-                    F.a0 = (float)a0; F.b0 = (float)b0;
-                    F.e1s = (float)(E1 * rSmm); F.e2s = (float)(E2 * rS);
+                    B.E0 = __shfl_sync(0xffffffffu, x, 0); B.E1 = __shfl_sync(0xffffffffu, x, 1);
+                    B.E2 = __shfl_sync(0xffffffffu, x, 2); B.Sm = __shfl_sync(0xffffffffu, x, 3);
+                    B.Smm = __shfl_sync(0xffffffffu, x, 4);
+                    B.a0 = a0; B.b0 = b0;
                     // the centre is the fit of this state up to the fp32 error of the delta sums:
                     // chi2 at the centre exceeds the minimum by O(1e-14) relative
-                    conval = E0 * L.inv_nq;
+                    conval = B.E0 * L.inv_nq;
                 }
                 if (a.prof) pd[1] = clock64();
                 // lane l owns proposals l and l + 32 (second round only for batches of 64)
@@ -972,21 +968,23 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                 int ks = -1, accmask = 0;
                 double ca = a0, cb = b0, cc = conval;
                 if (!gram) {
-                    float delta = 0.f, x = 0.f, y = 0.f, h11, h12, e1, e2;
+                    double chi = 0., an = 0., bn = 0., e1, e2, rss;
                     bool better = false;
                     if (mine) {
-                        fast_solve_f(F, L.find_bg, L.pos_bg, s1, s2, s3, s4, delta, x, y, h11, h12, e1, e2);   // mcsas.py:376
-                        better = delta < 0.f;                    // :379 strict: chi2' < chi2
-                        s_chi[lane] = conval + (double)delta * L.inv_nq;
+                        fast_solve(B, L.find_bg, L.pos_bg, s1, s2, s3, s4, rss, an, bn, e1, e2);   // mcsas.py:376
+                        chi = rss * L.inv_nq;
+                        better = chi < conval;                   // :379 strict
+                        s_chi[lane] = chi;
                     }
                     unsigned mask = __ballot_sync(0xffffffffu, better);
                     int koff = 0;
                     if (!mask && Kb > 32) {                      // second round: proposals 32 .. 63
                         better = false;
                         if (mine2) {
-                            fast_solve_f(F, L.find_bg, L.pos_bg, t1, t2, t3, t4, delta, x, y, h11, h12, e1, e2);
-                            better = delta < 0.f;
-                            s_chi[lane + 32] = conval + (double)delta * L.inv_nq;
+                            fast_solve(B, L.find_bg, L.pos_bg, t1, t2, t3, t4, rss, an, bn, e1, e2);
+                            chi = rss * L.inv_nq;
+                            better = chi < conval;
+                            s_chi[lane + 32] = chi;
                         }
                         mask = __ballot_sync(0xffffffffu, better);
                         koff = 32;
@@ -994,11 +992,8 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     const int kl = mask ? (__ffs(mask) - 1) : -1;
                     ks = kl >= 0 ? kl + koff : -1;
                     if (ks >= 0) {
-                        const float xs = __shfl_sync(0xffffffffu, x, kl), ys = __shfl_sync(0xffffffffu, y, kl);
-                        const float ds = __shfl_sync(0xffffffffu, delta, kl);
-                        ca = a0 + (double)xs * (double)F.rSmm;
-                        cb = b0 + (double)ys * (double)F.rS;
-                        cc = conval + (double)ds * L.inv_nq;
+                        ca = __shfl_sync(0xffffffffu, an, kl); cb = __shfl_sync(0xffffffffu, bn, kl);
+                        cc = __shfl_sync(0xffffffffu, chi, kl);
                     }
                 } else {
                     // Gram totals over warps / ranks
@@ -1013,33 +1008,33 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     }
                     __syncwarp();
                     int pos = 0;
+                    double g1 = s1, g2 = s2, g3 = s3, g4 = s4;      // fp64 copies updated per accepted move
                     for (int it = 0; it <= FGRP && !wd; ++it) {
-                        float delta = 0.f, x = 0.f, y = 0.f, h11 = 1.f, h12 = 0.f, e1 = 0.f, e2 = 0.f;
+                        double rss = 0., an = 0., bn = 0., e1 = 0., e2 = 0.;
                         bool better = false;
                         if (mine && lane >= pos) {
-                            fast_solve_f(F, L.find_bg, L.pos_bg, s1, s2, s3, s4, delta, x, y, h11, h12, e1, e2);
-                            better = delta < 0.f;                // :379 against the state reached so far
-                            s_chi[lane] = cc + (double)delta * L.inv_nq;
+                            fast_solve(B, L.find_bg, L.pos_bg, g1, g2, g3, g4, rss, an, bn, e1, e2);
+                            const double chi = rss * L.inv_nq;
+                            better = chi < cc;                   // :379 against the state reached so far
+                            s_chi[lane] = chi;
                         }
                         const unsigned mask = __ballot_sync(0xffffffffu, better);
                         if (!mask) break;
                         const int i = __ffs(mask) - 1;
-                        const float xi = __shfl_sync(0xffffffffu, x, i), yi = __shfl_sync(0xffffffffu, y, i);
-                        const float di = __shfl_sync(0xffffffffu, delta, i);
-                        const float h11i = __shfl_sync(0xffffffffu, h11, i), h12i = __shfl_sync(0xffffffffu, h12, i);
-                        const float e1i = __shfl_sync(0xffffffffu, e1, i), e2i = __shfl_sync(0xffffffffu, e2, i);
-                        const float da = xi * F.rSmm, db = yi * F.rS;
-                        ca += (double)xi * (double)F.rSmm; cb += (double)yi * (double)F.rS;
-                        cc += (double)di * L.inv_nq;
-                        const float an = (float)ca;
+                        const double ai = __shfl_sync(0xffffffffu, an, i), bi = __shfl_sync(0xffffffffu, bn, i);
+                        const double ri = __shfl_sync(0xffffffffu, rss, i);
+                        const double e1i = __shfl_sync(0xffffffffu, e1, i), e2i = __shfl_sync(0xffffffffu, e2, i);
+                        const double s2i = __shfl_sync(0xffffffffu, g2, i), s3i = __shfl_sync(0xffffffffu, g3, i);
+                        const double s4i = __shfl_sync(0xffffffffu, g4, i);
+                        const double da = ai - B.a0, db = bi - B.b0;
                         if (mine && lane > i) {                  // sums of later proposals w.r.t. the new state
-                            const float G = s_gtot[tri_idx_rt(FGRP, i, lane)];
-                            s1 = s1 - da * s3 - an * G - db * s4;
-                            s3 += G;
+                            const double G = (double)s_gtot[tri_idx_rt(FGRP, i, lane)];
+                            g1 = g1 - da * g3 - ai * G - db * g4;
+                            g3 += G;
                         }
-                        const float sq = rsqrtf(h11i);           // Smm' = h11 Smm
-                        F.rSmm *= sq; F.c12 = h12i * sq; F.e1s = e1i * sq; F.e2s = e2i;
-                        F.a0 = an; F.b0 = (float)cb;
+                        B.Sm += s4i; B.Smm += 2. * s3i + s2i;
+                        B.E0 = ri; B.E1 = e1i; B.E2 = e2i; B.a0 = ai; B.b0 = bi;
+                        ca = ai; cb = bi; cc = ri * L.inv_nq;
                         accmask |= 1 << i;
                         pos = i + 1;
                     }

@@ -170,8 +170,9 @@ def test_missing_device_or_bad_args_fail_loudly():
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["sphere_small", "sphere_nobg", "sphere_posbg", "sphcs_small", "cyl_small"])
-@pytest.mark.parametrize("spec_max,cluster", [(1, 1), (32, 1), (32, 2), (8, 4)])
+@pytest.mark.parametrize("name", ["sphere_small", "sphere_nobg", "sphere_posbg", "sphcs_small", "cyl_small",
+                                  "gauss_small"])
+@pytest.mark.parametrize("spec_max,cluster", [(1, 1), (32, 1), (64, 1), (32, 2), (8, 4)])
 def test_fp32_chain_tracks_fp64_chain(name, spec_max, cluster):
     """Production kernel (fp32 residual-delta sums, Gram batches, cached rows) against the
     fp64 parity kernel on the SAME Philox stream: identical accept/reject sequence over the
@@ -205,7 +206,8 @@ def test_fp32_chain_tracks_fp64_chain(name, spec_max, cluster):
         differ = np.nonzero(acc != racc)[0]
         first = int(differ[0]) if differ.size else n
         assert first >= min(n, 300), (first, n)            # marginal flips may appear much later
-        np.testing.assert_allclose(chi[:first], rchi[:first], rtol=1e-4)
+        # gauss_small: 0.01 % uncertainties amplify the ~3e-7 error of the fp32 form factors
+        np.testing.assert_allclose(chi[:first], rchi[:first], rtol=1e-2 if name == "gauss_small" else 1e-4)
         assert abs(out["conval0"][0, r] / ref["conval0"][0, r] - 1) < 1e-5
 
 
