@@ -113,6 +113,14 @@ int mcsas_set_model(mcsas_ctx *ctx, int model_id, const double *params, int n_pa
                     const double *active_lo, const double *active_hi, const int *generator_kind,
                     int quad_rule, int quad_nodes);
 
+/* -- smearing: replaces data.config.smearing.prepared (qOffset, weights) and data.locs of the
+ *    smeared branch of SASModel.calcIntensity (sasmodel.py:56-73; sasconfig.py:122-149, 209-233,
+ *    308-339).  Applies to the reference's canSmear models (Sphere, LMADenseSphere) in
+ *    mcsas_eval / mcsas_run / mcsas_fractions; two_d_coll = SmearingConfig.twoDColl (0: slit,
+ *    locations sqrt(q^2 + qOffset^2); 1: 2-D averaged, q + qOffset).  n_points = 0 switches it off. */
+int mcsas_set_smearing(mcsas_ctx *ctx, int n_points, const double *q_offset, const double *weights,
+                       int two_d_coll);
+
 /* -- ScatteringModel.calc(data, pset, compExp) (scatteringmodel.py:79-105) for M
  *    single contributions of dataset `set`: intensity[M][nq] (=F^2*w), v, w, s [M]. */
 int mcsas_eval(mcsas_ctx *ctx, int set, const double *pset, int m, double comp_exp, int precision,

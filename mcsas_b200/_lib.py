@@ -16,7 +16,7 @@ GEN_UNIFORM, GEN_EXP1, GEN_EXP2, GEN_EXP3 = 0, 1, 2, 3
 
 EXPORTS = [
     "mcsas_ctx_create", "mcsas_ctx_destroy", "mcsas_last_error", "mcsas_device_info",
-    "mcsas_upload_datasets", "mcsas_set_model", "mcsas_eval", "mcsas_run", "mcsas_run_async",
+    "mcsas_upload_datasets", "mcsas_set_model", "mcsas_set_smearing", "mcsas_eval", "mcsas_run", "mcsas_run_async",
     "mcsas_wait", "mcsas_request_stop", "mcsas_run_info", "mcsas_scheduler_info", "mcsas_fetch", "mcsas_fetch_trace", "mcsas_fractions",
     "mcsas_measure_peaks",
 ]
@@ -60,6 +60,7 @@ def lib():
     L.mcsas_device_info.argtypes = [vp, ip, ip, C.c_char_p, C.c_int]
     L.mcsas_upload_datasets.argtypes = [vp, C.c_int, ip, dp, dp, dp]
     L.mcsas_set_model.argtypes = [vp, C.c_int, dp, C.c_int, ip, C.c_int, dp, dp, ip, C.c_int, C.c_int]
+    L.mcsas_set_smearing.argtypes = [vp, C.c_int, dp, dp, C.c_int]
     L.mcsas_eval.argtypes = [vp, C.c_int, dp, C.c_int, C.c_double, C.c_int, dp, dp, dp, dp]
     L.mcsas_run.argtypes = [vp, C.POINTER(RunConfig), dp, C.c_longlong, ip]
     L.mcsas_run_async.argtypes = [vp, C.POINTER(RunConfig), dp, C.c_longlong, ip]

@@ -45,6 +45,7 @@ struct mcsas_ctx {
     // model
     bool have_model = false;
     ModelParams mp;
+    SmearTab smear;               // n = 0: no smearing
     double *d_quad = nullptr;     // [2][quad_nodes]
     // run state
     int n_chains = 0, n_contribs = 0, n_reps = 0, n_active = 0;
@@ -119,6 +120,7 @@ extern "C" int mcsas_ctx_create(int device, mcsas_ctx **out)
     }
     mcsas_ctx *ctx = new mcsas_ctx();
     ctx->device = device;
+    memset(&ctx->smear, 0, sizeof ctx->smear);
     if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess
         || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess
         || cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess
@@ -311,6 +313,30 @@ extern "C" int mcsas_set_model(mcsas_ctx *ctx, int model_id, const double *param
     return MCSAS_OK;
 }
 
+extern "C" int mcsas_set_smearing(mcsas_ctx *ctx, int n_points, const double *q_offset, const double *weights,
+                                  int two_d_coll)
+{
+    if (!ctx) return MCSAS_ERR_ARG;
+    if (n_points == 0) { memset(&ctx->smear, 0, sizeof ctx->smear); ctx->have_run = false; return MCSAS_OK; }
+    if (n_points < 2 || n_points > MCSAS_MAX_SMEAR || !q_offset || !weights)
+        return fail(ctx, MCSAS_ERR_ARG, "set_smearing: n_points %d outside [2,%d] or null profile", n_points, MCSAS_MAX_SMEAR);
+    SmearTab t;
+    memset(&t, 0, sizeof t);
+    t.n = n_points; t.two_d = two_d_coll != 0;
+    for (int k = 0; k < n_points; ++k) {
+        if (!std::isfinite(q_offset[k]) || !std::isfinite(weights[k]))
+            return fail(ctx, MCSAS_ERR_ARG, "set_smearing: non-finite profile value at %d", k);
+        // 2 * numpy.trapz(y * weights, x = qOffset)  (sasmodel.py:72-73) as a weighted sum of y
+        const double left = k > 0 ? q_offset[k] - q_offset[k - 1] : 0.;
+        const double right = k + 1 < n_points ? q_offset[k + 1] - q_offset[k] : 0.;
+        t.off[k] = q_offset[k];
+        t.tw[k] = 2. * weights[k] * 0.5 * (left + right);
+    }
+    ctx->smear = t;
+    ctx->have_run = false;
+    return MCSAS_OK;
+}
+
 extern "C" int mcsas_eval(mcsas_ctx *ctx, int set, const double *pset, int m, double comp_exp,
                           int precision, double *intensity, double *v, double *w, double *s)
 {
@@ -325,7 +351,7 @@ extern "C" int mcsas_eval(mcsas_ctx *ctx, int set, const double *pset, int m, do
     CK(cudaMalloc(&d_out, sizeof(double) * nout));
     if (P) CK(cudaMemcpyAsync(d_p, pset, sizeof(double) * (size_t)m * P, cudaMemcpyHostToDevice, ctx->stream));
     EvalArgs a;
-    a.mp = ctx->mp; a.sets = ctx->d_sets; a.data = ctx->d_data;
+    a.mp = ctx->mp; a.smear = ctx->smear; a.sets = ctx->d_sets; a.data = ctx->d_data;
     a.quad_x = ctx->d_quad; a.quad_w = ctx->d_quad + D;
     a.set = set; a.m = m; a.comp_exp = comp_exp; a.pset = d_p;
     a.intensity = d_out; a.v = d_out + (size_t)m * nq; a.w = a.v + m; a.s = a.w + m;
@@ -592,6 +618,7 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     ChainArgs a;
     memset(&a, 0, sizeof a);
     a.mp = mp;
+    a.smear = ctx->smear;
     a.n_contribs = N; a.n_reps = cfg->n_reps; a.n_chains = n_chains;
     a.max_attempts = proposal_stream ? 1 : (cfg->max_retries < 0 ? 1 : cfg->max_retries + 2);
     a.max_iter = cfg->max_iter; a.conv_crit = cfg->conv_crit; a.comp_exp = cfg->comp_exp;
@@ -929,7 +956,7 @@ extern "C" int mcsas_fractions(mcsas_ctx *ctx, const mcsas_run_config *cfg, cons
     CK(cudaMalloc(&d_o, sizeof(double) * nout));
     CK(cudaMemcpyAsync(d_r, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
     FractionArgs a;
-    a.mp = ctx->mp; a.sets = ctx->d_sets; a.data = ctx->d_data;
+    a.mp = ctx->mp; a.smear = ctx->smear; a.sets = ctx->d_sets; a.data = ctx->d_data;
     a.quad_x = ctx->d_quad; a.quad_w = ctx->d_quad + D;
     a.n_contribs = N; a.n_reps = R; a.n_chains = C; a.comp_exp = cfg->comp_exp;
     a.find_bg = cfg->find_background != 0; a.pos_bg = cfg->positive_background != 0;

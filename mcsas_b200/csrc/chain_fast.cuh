@@ -44,7 +44,7 @@ template <int MODEL> struct FastOps {
     __device__ __forceinline__ static float evalS(const Contrib<float> &cc, const float *nodes,
                                                   const QuadTab<float> &qt, const QRep<float> &Q)
     {
-        return O::eval(cc, nodes, qt, Q);
+        return eval_q<MODEL, float>(cc, nodes, qt, Q);
     }
     // scaled intensity of one contribution for the thread's q points
     template <int QPT>
@@ -137,8 +137,9 @@ template <> struct FastOps<MCSAS_SPHERE> {
         cc.c[1] = cc.c[0];                                   // (r, A) = one aligned 8-byte load
     }
     __device__ __forceinline__ static float evalS(const Contrib<float> &cc, const float *,
-                                                  const QuadTab<float> &, const QRep<float> &Q)
+                                                  const QuadTab<float> &qt, const QRep<float> &Q)
     {
+        if (qt.sm->n) return eval_q<MCSAS_SPHERE, float>(cc, nullptr, qt, Q);     // smeared: no q fold
         const float q[1] = {Q.q}, th[1] = {Q.th}, tl[1] = {Q.tl}, r[1] = {cc.c[0]};
         float g[1];
         sph_g_vec<1, true>(q, th, tl, r, g);
@@ -148,9 +149,14 @@ template <> struct FastOps<MCSAS_SPHERE> {
     // radius: one vote per proposal selects the variant without the series.  Callers are
     // warp-convergent.
     template <int QPT>
-    __device__ __forceinline__ static void evalN(const Contrib<float> &cc, const float *, const QuadTab<float> &,
+    __device__ __forceinline__ static void evalN(const Contrib<float> &cc, const float *, const QuadTab<float> &qt,
                                                  const QRep<float> (&Q)[QPT], float (&d)[QPT])
     {
+        if (qt.sm->n) {
+#pragma unroll
+            for (int j = 0; j < QPT; ++j) d[j] = eval_q<MCSAS_SPHERE, float>(cc, nullptr, qt, Q[j]);
+            return;
+        }
         float q[QPT], th[QPT], tl[QPT], r[QPT], g[QPT];
         bool small = false;
 #pragma unroll
@@ -169,9 +175,17 @@ template <> struct FastOps<MCSAS_SPHERE> {
     // the NS x QPT evaluations form a single basic block that ptxas can interleave freely
     template <int QPT, int NS>
     __device__ __forceinline__ static void evalChunk(const RingEntry<float> *ring, const int (&ent)[NS],
-                                                     const float *, size_t, const QuadTab<float> &,
+                                                     const float *, size_t, const QuadTab<float> &qt,
                                                      const QRep<float> (&Q)[QPT], float (&d)[NS][QPT])
     {
+        if (qt.sm->n) {
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const Contrib<float> cn = ring[ent[s]].cn;
+                evalN<QPT>(cn, nullptr, qt, Q, d[s]);
+            }
+            return;
+        }
         float rr[NS], aa[NS];
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
@@ -211,9 +225,15 @@ template <> struct FastOps<MCSAS_SPHERE> {
     }
     template <int QPT>
     __device__ __forceinline__ static void diffS(const Contrib<float> &cn, const Contrib<float> &co,
-                                                 const float *, const float *, const QuadTab<float> &,
+                                                 const float *, const float *, const QuadTab<float> &qt,
                                                  const QRep<float> (&Q)[QPT], float (&d)[QPT])
     {
+        if (qt.sm->n) {
+#pragma unroll
+            for (int j = 0; j < QPT; ++j)
+                d[j] = eval_q<MCSAS_SPHERE, float>(cn, nullptr, qt, Q[j]) - eval_q<MCSAS_SPHERE, float>(co, nullptr, qt, Q[j]);
+            return;
+        }
         float q[2 * QPT], th[2 * QPT], tl[2 * QPT], r[2 * QPT], g[2 * QPT];
         const float rmin = fminf(cn.c[0], co.c[0]);
         bool small = false;
@@ -408,7 +428,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     }
     mbar_wait(s_bar, 0);
     __syncthreads();
-    const QuadTab<float> qt = { D, a.mp.quad_rule, s_qx, s_qw };
+    const QuadTab<float> qt = { D, a.mp.quad_rule, s_qx, s_qw, &a.smear };
     const float qref = (float)(ds.q_ref * 1e-9);   // 1/nm
 
     // ---- per-thread resident state of q points (rank*TQ + qtid)*QPT + j, j < QPT (contiguous:
@@ -428,7 +448,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         if (ev == 0.0) ev = 1. * inorm;                          // backgroundscalingfit.py:117
         Q[j].set(qv);
         double qsd = 1.;
-        if (FO::QS_POW > 0) {
+        if (FO::QS_POW > 0 && a.smear.n == 0) {                  // (smeared: locations differ per profile point)
             double t = (double)qref / (qv * 1e-9);
             double t2 = t * t;
             qsd = FO::QS_POW == 6 ? t2 * t2 * t2 : (FO::QS_POW == 4 ? t2 * t2 : t2);

@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(288) chain_kernel(const __grid_constant__ Chai
     }
     mbar_wait(s_bar, 0);
     __syncthreads();
-    const QuadTab<Real> qt = { D, a.mp.quad_rule, s_qx, s_qw };
+    const QuadTab<Real> qt = { D, a.mp.quad_rule, s_qx, s_qw, &a.smear };
 
     // ---- per-thread resident state: q point (j*C + rank)*T + tid -------------------------
     constexpr bool TWO_PASS = sizeof(Real) == 8;   // parity mode: residual-form chi-squared
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(288) chain_kernel(const __grid_constant__ Chai
                     const Contrib<Real> cc = s_ring[e].co;
                     const Real *nd = s_nodes + (size_t)(e * 2 + 1) * NSTR;
 #pragma unroll
-                    for (int j = 0; j < QPT; ++j) ft[j] += (double)O::eval(cc, nd, qt, Q[j]);
+                    for (int j = 0; j < QPT; ++j) ft[j] += (double)eval_q<MODEL, Real>(cc, nd, qt, Q[j]);
                 }
             }
             __syncthreads();
@@ -462,8 +462,8 @@ __global__ void __launch_bounds__(288) chain_kernel(const __grid_constant__ Chai
                         const Real *nn = s_nodes + (size_t)(e * 2) * NSTR, *no = nn + NSTR;
 #pragma unroll
                         for (int j = 0; j < QPT; ++j) {
-                            Real inew = O::eval(cn, nn, qt, Q[j]);       // mcsas.py:360
-                            Real iold = O::eval(co, no, qt, Q[j]);       // mcsas.py:362
+                            Real inew = eval_q<MODEL, Real>(cn, nn, qt, Q[j]);       // mcsas.py:360
+                            Real iold = eval_q<MODEL, Real>(co, no, qt, Q[j]);       // mcsas.py:362
                             double M = model_sum<Real>(ft[j], inew, iold);   // :366
                             double t = w[j] * M;
                             acc[s][0] += t;
@@ -558,8 +558,8 @@ __global__ void __launch_bounds__(288) chain_kernel(const __grid_constant__ Chai
                             const double ak = s_chi[k * 3 + 1], bk = s_chi[k * 3 + 2];
 #pragma unroll
                             for (int j = 0; j < QPT; ++j) {
-                                Real inew = O::eval(cn, nn, qt, Q[j]);
-                                Real iold = O::eval(co, no, qt, Q[j]);
+                                Real inew = eval_q<MODEL, Real>(cn, nn, qt, Q[j]);
+                                Real iold = eval_q<MODEL, Real>(co, no, qt, Q[j]);
                                 double M = model_sum<Real>(ft[j], inew, iold);
                                 double r = Iq[j] - (M * ak + bk);
                                 acc[s] = fma(w[j] * r, r, acc[s]);
@@ -618,8 +618,8 @@ __global__ void __launch_bounds__(288) chain_kernel(const __grid_constant__ Chai
                 const Real *nn = s_nodes + (size_t)(e * 2) * NSTR, *no = nn + NSTR;
 #pragma unroll
                 for (int j = 0; j < QPT; ++j) {
-                    Real inew = O::eval(cn, nn, qt, Q[j]);
-                    Real iold = O::eval(co, no, qt, Q[j]);
+                    Real inew = eval_q<MODEL, Real>(cn, nn, qt, Q[j]);
+                    Real iold = eval_q<MODEL, Real>(co, no, qt, Q[j]);
                     ft[j] = model_sum<Real>(ft[j], inew, iold);
                 }
                 conval = s_chi[kstar * 3]; sc_a = s_chi[kstar * 3 + 1]; sc_b = s_chi[kstar * 3 + 2];
@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(128) eval_kernel(const __grid_constant__ EvalA
         s_qw[j] = (Real)a.quad_w[j];
     }
     __syncthreads();
-    const QuadTab<Real> qt = { D, a.mp.quad_rule, s_qx, s_qw };
+    const QuadTab<Real> qt = { D, a.mp.quad_rule, s_qx, s_qw, &a.smear };
     if (tid == 0) {
         PVec p(a.mp, a.pset + (long long)c * a.mp.n_active);
         double G = 1.;
@@ -732,6 +732,6 @@ __global__ void __launch_bounds__(128) eval_kernel(const __grid_constant__ EvalA
     for (int i = tid; i < ds.nq; i += blockDim.x) {
         QRep<Real> Q;
         Q.set(q[i]);
-        a.intensity[(long long)c * ds.nq + i] = (double)O::eval(s_cc, s_nodes, qt, Q) / s_G;
+        a.intensity[(long long)c * ds.nq + i] = (double)eval_q<MODEL, Real>(s_cc, s_nodes, qt, Q) / s_G;
     }
 }

@@ -5,6 +5,7 @@
 #include "../../include/mcsas_b200.h"
 
 #define MCSAS_MAX_NODES 512      // orientation-average nodes kept in shared memory
+#define MCSAS_MAX_SMEAR 64       // points of the smearing profile (sasconfig.py: nSteps + 1 or + 2)
 #define KCAP MCSAS_MAX_SPEC       // speculative proposals per batch
 #define RING_MAX 128              // ring entries (>= 4 * KCAP)
 #define MAX_CLUSTER 8             // CTAs per chain
@@ -24,6 +25,15 @@ struct ModelParams {
     double hi[MCSAS_MAX_ACTIVE];
 };
 
+// Smearing profile (sasmodel.py:56-73): intensity(q_i) = sum_k tw[k] I(loc_ik) with
+// loc_ik = sqrt(q_i^2 + off[k]^2) (slit) or q_i + off[k] (2-D averaged); tw = 2 * trapezoid
+// coefficients of qOffset * profile weights.  n = 0: no smearing.
+struct SmearTab {
+    int n, two_d;
+    double off[MCSAS_MAX_SMEAR];
+    double tw[MCSAS_MAX_SMEAR];
+};
+
 // One dataset inside the packed device array: [q | I | sigma], each nq_pad doubles.
 struct DatasetDesc {
     long long offset;   // in doubles, 16-byte aligned
@@ -36,6 +46,7 @@ struct DatasetDesc {
 
 struct ChainArgs {
     ModelParams mp;
+    SmearTab smear;
     // settings (mcsasparameters.json)
     int n_contribs;
     int n_reps;
@@ -82,6 +93,7 @@ struct ChainArgs {
 
 struct EvalArgs {
     ModelParams mp;
+    SmearTab smear;
     const DatasetDesc *sets;
     const double *data;
     const double *quad_x, *quad_w;
@@ -95,6 +107,7 @@ struct EvalArgs {
 
 struct FractionArgs {
     ModelParams mp;
+    SmearTab smear;
     const DatasetDesc *sets;
     const double *data;
     const double *quad_x, *quad_w;

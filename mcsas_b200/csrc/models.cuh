@@ -19,6 +19,7 @@ template <class Real> struct QRep;
 template <> struct QRep<double> {
     double q;
     __device__ void set(double q_si) { q = q_si; }
+    __device__ double q_si() const { return q; }
 };
 template <> struct QRep<float> {
     float q;        // 1/nm
@@ -30,6 +31,7 @@ template <> struct QRep<float> {
         th = (float)t;
         tl = (float)(t - (double)th);
     }
+    __device__ double q_si() const { return (double)q * 1e9; }
 };
 
 template <class Real> struct Units;
@@ -159,6 +161,7 @@ template <class Real> struct QuadTab {
     int rule;
     const Real *x;
     const Real *wt;
+    const SmearTab *sm;      // smearing profile (n = 0: none)
 };
 
 template <int MODEL, class Real> struct Ops;
@@ -550,3 +553,23 @@ template <class Real> struct Ops<MCSAS_KHOLODENKO, Real> {
     }
 };
 
+// ---- smearing (sasmodel.py:56-73): only the reference's canSmear models -----------------
+template <int MODEL> struct CanSmear { static constexpr bool value = MODEL == MCSAS_SPHERE || MODEL == MCSAS_LMA_DENSE_SPHERE; };
+
+// Intensity of one contribution at one q point, smeared over the profile when one is set.
+template <int MODEL, class Real>
+__device__ __forceinline__ Real eval_q(const Contrib<Real> &cc, const Real *nodes, const QuadTab<Real> &qt,
+                                       const QRep<Real> &Q)
+{
+    using O = Ops<MODEL, Real>;
+    if (!CanSmear<MODEL>::value || qt.sm->n == 0) return O::eval(cc, nodes, qt, Q);
+    const double q = Q.q_si();
+    Real acc = 0;
+    for (int k = 0; k < qt.sm->n; ++k) {
+        const double o = qt.sm->off[k];
+        QRep<Real> Qk;
+        Qk.set(qt.sm->two_d ? q + o : sqrt(q * q + o * o));      // sasconfig.py:326-337
+        acc += (Real)qt.sm->tw[k] * O::eval(cc, nodes, qt, Qk);
+    }
+    return acc;
+}

@@ -28,6 +28,7 @@ class SASData(object):
         self.title = title
         self.x0 = DataVector(q)
         self.f = DataVector(intensity, sigma)
+        self.smearing = None        # a mcsas_b200.smearing.SmearingConfig (data.config.smearing)
 
     @property
     def q(self):

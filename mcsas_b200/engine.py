@@ -87,6 +87,18 @@ class Engine(object):
                     "set_model")
         self.n_active = int(active_idx.size)
 
+    def set_smearing(self, q_offset=None, weights=None, two_d_coll=False):
+        """SmearingConfig.prepared of the data set (None: no smearing); canSmear models only."""
+        if q_offset is None:
+            self._check(self._L.mcsas_set_smearing(self._ctx, 0, None, None, 0), "set_smearing")
+            return
+        qo = np.ascontiguousarray(q_offset, dtype=np.float64)
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        if qo.size != w.size:
+            raise McSASB200Error("smearing profile: qOffset and weights differ in length")
+        self._check(self._L.mcsas_set_smearing(self._ctx, int(qo.size), _dp(qo), _dp(w), int(bool(two_d_coll))),
+                    "set_smearing")
+
     def eval(self, pset, comp_exp, set_index=0, precision=_lib.FP64):
         """ScatteringModel.calc on single contributions -> (it[M,nq], v, w, s)."""
         pset = np.ascontiguousarray(np.atleast_2d(pset), dtype=np.float64)

@@ -17,7 +17,7 @@ import time
 
 import numpy as np
 
-from . import _lib
+from . import _lib, smearing
 from .data import hot_path_vectors
 from .engine import Engine
 from .models import ScatteringModel, Sphere
@@ -120,12 +120,22 @@ class McSAS(object):
         eng.upload_datasets([(q, I, sigma)])
         self.model.compensationExponent = float(self.compensationExponent())
         self.model.configureEngine(eng)
+        self._configureSmearing(eng)
         cfg = self._config(numContribs, numReps, record_trace)
         eng.run_async(cfg, stream)
         if self.stop:
             eng.request_stop()
         self.lastKernelMs = eng.wait()
         return eng.fetch()
+
+    def _configureSmearing(self, eng):
+        """sasmodel.py:56-60: smear when the data carries a valid, enabled profile and the model
+        can be smeared."""
+        prof = smearing.profile_for(self.data, self.model)
+        if prof is None:
+            eng.set_smearing(None)
+        else:
+            eng.set_smearing(*prof)
 
     def analyse(self):
         """mcsas.py:191-285: numReps independent chains, retried up to maxRetries+2 times
@@ -214,6 +224,7 @@ class McSAS(object):
         q, I, sigma = hot_path_vectors(self.data)
         eng.upload_datasets([(q, I, sigma)])
         self.model.configureEngine(eng)
+        self._configureSmearing(eng)
         cfg = self._config(numContribs, numReps)
         cfg.precision = _lib.FP64
         f = eng.fractions(cfg, contribs[np.newaxis])

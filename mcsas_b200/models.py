@@ -136,6 +136,12 @@ class ScatteringModel(object):
             sigma = np.ones_like(q)
         self._engine.upload_datasets([(q, I, sigma)])
         self.configureEngine(self._engine)
+        from . import smearing
+        prof = None if isinstance(data, np.ndarray) else smearing.profile_for(data, self)
+        if prof is None:
+            self._engine.set_smearing(None)
+        else:
+            self._engine.set_smearing(*prof)
         return self._engine
 
     def calc(self, data, pset, compensationExponent=None, precision=_lib.FP64):

@@ -35,6 +35,12 @@ CASES = {
                          bg=-50.0),
     "sphere_startmin": dict(model="Sphere", active=[("radius", 1 * NM, 100 * NM)],
                             nq=48, N=30, max_iter=1500, seed=10, start_from_minimum=True),
+    "sphere_smear": dict(model="Sphere", active=[("radius", 1 * NM, 100 * NM)],
+                         nq=40, N=30, max_iter=1200, seed=21,
+                         smear=dict(umbra=0.02e9, penumbra=0.05e9, two_d=False)),
+    "lma_smear2d": dict(model="LMADenseSphere", active=[("radius", 1 * NM, 50 * NM)],
+                        nq=40, N=24, max_iter=800, seed=22,
+                        smear=dict(umbra=0.004e9, penumbra=0.012e9, two_d=True)),
     "lma_small": dict(model="LMADenseSphere", active=[("radius", 1 * NM, 50 * NM)],
                       nq=48, N=30, max_iter=1500, seed=11),
     "sphcs_small": dict(model="SphericalCoreShell", active=[("radius", 1 * NM, 50 * NM)],
@@ -90,6 +96,19 @@ def synth_data(case, model):
     return rh.make_data(q_nm, I, sig)
 
 
+def apply_smearing(data, smear):
+    """Enable the reference's TrapezoidSmearing on a SASData (sasconfig.py:76-149, 308-339)."""
+    sm = data.config.smearing
+    sm.doSmear.setValue(True)
+    sm.twoDColl.setValue(bool(smear.get("two_d", False)))
+    sm.umbra.setValue(smear["umbra"])
+    sm.penumbra.setValue(smear["penumbra"])
+    assert sm.inputValid()
+    data.setConfig(data.config)
+    assert data.locs.ndim == 2
+    return sm
+
+
 def run_chain_case(name, case):
     rh.install()
     model = make_model(case)
@@ -97,6 +116,12 @@ def run_chain_case(name, case):
         data = rh.load_data(os.path.join(rh.REFERENCE_TESTDATA, case["file"]))
     else:
         data = synth_data(case, model)
+    smear_out = {}
+    if "smear" in case:
+        sm = apply_smearing(data, case["smear"])
+        qo, w = sm.prepared
+        smear_out = dict(smear_off=np.asarray(qo, float), smear_w=np.asarray(w, float),
+                         smear_two_d=bool(sm.twoDColl()))
     st = dict(numContribs=case["N"], maxIterations=case["max_iter"])
     for k in ("findBackground", "positiveBackground", "startFromMinimum"):
         pyk = {"findBackground": "find_background", "positiveBackground": "positive_background",
@@ -145,6 +170,7 @@ def run_chain_case(name, case):
     )
     if case.get("store_stream", True):
         out["stream"] = stream
+    out.update(smear_out)
     np.savez_compressed(os.path.join(OUT, "chain_%s.npz" % name), **out)
     print("chain %-16s nit=%6d moves=%5d chi0=%.6g chi=%.6g  (%.1fs)" % (
         name, nit, details["numMoves"], chis[1], conval, el))
@@ -200,6 +226,46 @@ def run_eval_cases():
         out[name + "_s"] = np.array(ss)
         print("eval", name, "ok")
     np.savez_compressed(os.path.join(OUT, "eval_models.npz"), **out)
+
+
+def run_smear_eval_cases():
+    """Smeared ScatteringModel.calc (sasmodel.py:56-73) of the canSmear models for a slit and a
+    2-D averaged trapezoidal profile and a Gaussian one."""
+    rh.install()
+    from mcsas.dataobj.sasconfig import GaussianSmearing
+    q_nm = np.logspace(np.log10(0.03), np.log10(3.0), 40)
+    out = dict(q=q_nm * 1e9)
+    for tag, mname, pset, conf in [
+            ("sphere_slit", "Sphere", [[1.3 * NM], [10 * NM], [60 * NM]], dict(umbra=0.02e9, penumbra=0.05e9, two_d=False)),
+            ("sphere_2d", "Sphere", [[1.3 * NM], [10 * NM], [60 * NM]], dict(umbra=0.004e9, penumbra=0.012e9, two_d=True)),
+            ("lma_slit", "LMADenseSphere", [[1.3 * NM], [10 * NM], [40 * NM]], dict(umbra=0.01e9, penumbra=0.03e9, two_d=False)),
+            ("sphere_gauss", "Sphere", [[2 * NM], [25 * NM]], dict(variance=0.01e9, two_d=False))]:
+        data = rh.make_data(q_nm, np.ones(q_nm.size), 0.01 * np.ones(q_nm.size))
+        if "variance" in conf:
+            sm = GaussianSmearing()
+            data.config.smearing = sm
+            sm.doSmear.setValue(True)
+            sm.twoDColl.setValue(conf["two_d"])
+            sm.variance.setValue(conf["variance"])
+            data.setConfig(data.config)
+        else:
+            sm = apply_smearing(data, conf)
+        model = rh.model_class(mname)()
+        for p in model.params():
+            if hasattr(p, "setActive"):
+                p.setActive(False)
+        model.radius.setActive(True)
+        md = [model.calc(data, np.array([row]), 0.6666666) for row in pset]
+        qo, w = sm.prepared
+        out[tag + "_model"] = np.array(mname)
+        out[tag + "_pvalues"] = np.array([float(p()) for p in model.params()])
+        out[tag + "_pset"] = np.array(pset)
+        out[tag + "_it"] = np.array([np.asarray(m.cumInt).flatten() for m in md])
+        out[tag + "_off"] = np.asarray(qo, float)
+        out[tag + "_w"] = np.asarray(w, float)
+        out[tag + "_two_d"] = np.array(bool(sm.twoDColl()))
+        print("smear eval", tag, out[tag + "_it"].shape, len(qo))
+    np.savez_compressed(os.path.join(OUT, "eval_smeared.npz"), **out)
 
 
 def run_fit_cases():
@@ -269,6 +335,8 @@ if __name__ == "__main__":
         run_eval_cases()
     if not which or "bgfit" in which:
         run_fit_cases()
+    if not which or "smear" in which:
+        run_smear_eval_cases()
     if not which or "sasfit" in which:
         run_sasfit_fixtures()
     for name, case in CASES.items():

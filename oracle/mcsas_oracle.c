@@ -201,8 +201,50 @@ static void patch_params(const orc_model *m, const double *pvals, double *p)
 
 /* One contribution: it[nq] = F(q)^2 * w, v = absVolume, w = volume^(2c), s = surface
  * (sasmodel.py:46-79 non-smeared branch, sasmodel.py:37-44, scatteringmodel.py:27-42). */
+static int orc_eval_plain(const orc_model *m, int nq, const double *q, const double *pvals,
+                          double comp_exp, double *it, double *v_out, double *w_out, double *s_out);
+
+/* Smearing (sasmodel.py:56-73, sasconfig.py:122-149, 209-233, 308-339): for canSmear models
+ * (Sphere, LMADenseSphere) the intensity at q_i is 2 * trapz(F^2 w weight, x = qOffset) over the
+ * locations sqrt(q_i^2 + off_k^2) (slit) or q_i + off_k (2-D averaged).  The profile (qOffset,
+ * weights) comes from SmearingConfig.prepared; it is process-global here like the reference's
+ * data.config.smearing. */
+#define ORC_MAX_SMEAR 64
+static struct { int n, two_d; double off[ORC_MAX_SMEAR], wt[ORC_MAX_SMEAR]; } g_smear = {0, 0, {0}, {0}};
+
+int orc_set_smearing(int n, const double *q_offset, const double *weights, int two_d_coll)
+{
+    if (n < 0 || n > ORC_MAX_SMEAR || n == 1) return -1;
+    g_smear.n = n; g_smear.two_d = two_d_coll;
+    for (int k = 0; k < n; ++k) { g_smear.off[k] = q_offset[k]; g_smear.wt[k] = weights[k]; }
+    return 0;
+}
+
 int orc_eval(const orc_model *m, int nq, const double *q, const double *pvals,
              double comp_exp, double *it, double *v_out, double *w_out, double *s_out)
+{
+    const int n = g_smear.n;
+    const int can_smear = m->model_id == ORC_SPHERE || m->model_id == ORC_LMA_DENSE_SPHERE;  /* canSmear */
+    if (n == 0 || !can_smear) return orc_eval_plain(m, nq, q, pvals, comp_exp, it, v_out, w_out, s_out);
+    double *locs = (double *)malloc(sizeof(double) * 2 * (size_t)nq * n), *il = locs + (size_t)nq * n;
+    for (int i = 0; i < nq; ++i)
+        for (int k = 0; k < n; ++k)                       /* sasconfig.py:326-337 */
+            locs[(size_t)i * n + k] = g_smear.two_d ? q[i] + g_smear.off[k]
+                                                    : sqrt(q[i] * q[i] + g_smear.off[k] * g_smear.off[k]);
+    int rc = orc_eval_plain(m, nq * n, locs, pvals, comp_exp, il, v_out, w_out, s_out);
+    for (int i = 0; i < nq && rc == 0; ++i) {            /* 2 * trapz(y, x = qOffset)  sasmodel.py:72-73 */
+        double acc = 0.;
+        for (int k = 0; k + 1 < n; ++k)
+            acc += (g_smear.off[k + 1] - g_smear.off[k])
+                   * (il[(size_t)i * n + k] * g_smear.wt[k] + il[(size_t)i * n + k + 1] * g_smear.wt[k + 1]) / 2.;
+        it[i] = 2. * acc;
+    }
+    free(locs);
+    return rc;
+}
+
+static int orc_eval_plain(const orc_model *m, int nq, const double *q, const double *pvals,
+                          double comp_exp, double *it, double *v_out, double *w_out, double *s_out)
 {
     double p[ORC_MAX_PARAMS];
     patch_params(m, pvals, p);

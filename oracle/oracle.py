@@ -164,6 +164,19 @@ def settings(n_contribs=300, conv_crit=1.0, max_iter=100000, comp_exp=0.6666666,
                      int(bool(start_from_minimum)), float(q_limit_hi))
 
 
+def set_smearing(q_offset=None, weights=None, two_d_coll=False):
+    """SmearingConfig.prepared (qOffset, weights) for the canSmear models; None switches it off.
+    Process-global, like data.config.smearing in the reference."""
+    if q_offset is None:
+        rc = lib().orc_set_smearing(0, None, None, 0)
+    else:
+        qo = np.ascontiguousarray(q_offset, dtype=np.float64)
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        assert qo.size == w.size
+        rc = lib().orc_set_smearing(int(qo.size), _dp(qo), _dp(w), int(bool(two_d_coll)))
+    assert rc == 0
+
+
 def eval_contribs(model, q, pset, comp_exp=0.6666666):
     """ScatteringModel.calc per contribution (scatteringmodel.py:79-105):
     returns it[M, nq], v[M], w[M], s[M]."""

@@ -73,6 +73,12 @@ def install():
     def linspace(start, stop, num=50, *a, **kw):
         return _linspace(start, stop, int(num), *a, **kw)
     np.linspace = linspace
+    # same numpy >= 2 incompatibility in sasconfig.py:133,220 (logspace(num=np.ceil(n / 2.)))
+    _logspace = np.logspace
+
+    def logspace(start, stop, num=50, *a, **kw):
+        return _logspace(start, stop, int(num), *a, **kw)
+    np.logspace = logspace
     if not hasattr(np, "trapz"):
         np.trapz = np.trapezoid
     import mcsas.mcsas  # noqa: F401  (calls logging.basicConfig(INFO), mcsas.py:15)

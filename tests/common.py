@@ -7,6 +7,7 @@ import oracle as orc
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
+SMEAR_CHAINS = ["sphere_smear", "lma_smear2d"]      # chains recorded with data.config.smearing on
 CHAIN_CASES = ["sphere_small", "sphere_nobg", "sphere_posbg", "sphere_startmin", "lma_small",
                "sphcs_small", "ellcs_small", "elliso_small", "cyl_small", "gauss_small",
                "kho_small", "sphere_cfg1"]
@@ -51,3 +52,10 @@ def oracle_settings(g, **over):
               start_from_minimum=g["start_from_minimum"], q_limit_hi=float(g["q_limit_hi"]))
     kw.update(over)
     return orc.settings(**kw)
+
+
+def smear_of(g):
+    """(qOffset, weights, twoDColl) of a golden chain recorded with smearing, else None."""
+    if "smear_off" not in g:
+        return None
+    return np.asarray(g["smear_off"]), np.asarray(g["smear_w"]), bool(g["smear_two_d"])

@@ -14,13 +14,15 @@ def have_gpu():
         return False
 
 
-def engine_for(om, datasets, device=0):
+def engine_for(om, datasets, device=0, smear=None):
     """Engine with datasets uploaded and the oracle-described model set."""
     from mcsas_b200 import Engine
     eng = Engine(device)
     eng.upload_datasets(datasets)
     eng.set_model(om.model_id, om.values, [om.pnames.index(a) for a in om.active],
                   om.lo, om.hi, om.gen_kind, om.quad_rule, om.quad_nodes)
+    if smear is not None:
+        eng.set_smearing(*smear)
     return eng
 
 
@@ -28,7 +30,7 @@ def run_golden_chain(g, precision, spec_max, pad_steps=8, quad_rule=0, cluster=0
     """Replay a golden chain (uploaded generator-output stream) on the GPU."""
     from mcsas_b200 import Engine
     om = common.oracle_model(g, quad_rule=quad_rule)
-    eng = engine_for(om, [(g["q"], g["I"], g["sigma"])])
+    eng = engine_for(om, [(g["q"], g["I"], g["sigma"])], smear=common.smear_of(g))
     P = om.n_active
     max_iter = min(g["max_iter"], g["num_iter"] + pad_steps)
     n0 = 0 if g["start_from_minimum"] else g["N"] * P

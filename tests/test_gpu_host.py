@@ -130,3 +130,35 @@ def test_stop_flag():
     algo.stop = True                          # McSAS.stop, mcsas.py:357
     algo.analyse()
     assert (algo.details["num_iter"] < 10 ** 7).all()
+
+
+def test_smearing_profile_on_the_data_reaches_the_kernels():
+    """data.smearing (mcsas_b200.smearing.TrapezoidSmearing) is applied for a canSmear model in
+    model.calc and in McSAS.mcFit, and ignored when disabled (sasmodel.py:56-60)."""
+    from mcsas_b200 import synth
+    from mcsas_b200.data import SASData
+    from mcsas_b200.mcsas import McSAS
+    from mcsas_b200.models import Sphere, GaussianChain
+    from mcsas_b200.smearing import TrapezoidSmearing
+    q, I, s = synth.sphere_curve(nq=60)
+    data = SASData(q, I, s)
+    m = Sphere()
+    m.radius.setActiveRange((1 * NM, 100 * NM))
+    plain = m.calc(data, np.array([[10 * NM]]), 0.6666666).cumInt
+    data.smearing = TrapezoidSmearing(0.02e9, 0.05e9)
+    smeared = m.calc(data, np.array([[10 * NM]]), 0.6666666).cumInt
+    assert np.abs(smeared / plain - 1).max() > 0.05
+    data.smearing = TrapezoidSmearing(0.02e9, 0.05e9, doSmear=False)
+    np.testing.assert_array_equal(m.calc(data, np.array([[10 * NM]]), 0.6666666).cumInt, plain)
+    gc = GaussianChain()                                    # canSmear = False: profile ignored
+    data.smearing = TrapezoidSmearing(0.02e9, 0.05e9)
+    a = gc.calc(data, np.array([[10 * NM]]), 0.6666666).cumInt
+    data.smearing = None
+    np.testing.assert_array_equal(gc.calc(data, np.array([[10 * NM]]), 0.6666666).cumInt, a)
+    # a smeared fit runs and improves
+    data.smearing = TrapezoidSmearing(0.02e9, 0.05e9)
+    algo = McSAS(seed=3)
+    algo.model, algo.data = m, data
+    algo.maxIterations.setValue(1500)
+    rset, conval, details = algo.mcFit(40, False, True, nRun=0)
+    assert np.isfinite(conval) and details["numMoves"] > 10

@@ -330,3 +330,65 @@ def test_maximum_nq_and_tiny_inputs():
         out = eng.fetch()
         assert (out["num_iter"] == 0).all() and np.isfinite(out["conval"]).all()
         eng.close()
+
+
+# ---- smearing (sasmodel.py:56-73) ------------------------------------------
+@pytest.mark.parametrize("tag", ["sphere_slit", "sphere_2d", "lma_slit", "sphere_gauss"])
+@pytest.mark.parametrize("prec", [FP64, FP32])
+def test_smeared_eval_matches_reference(tag, prec):
+    g = np.load(os.path.join(common.GOLDEN, "eval_smeared.npz"))
+    name = str(g[tag + "_model"])
+    spec = orc.MODEL_SPECS[name][1]
+    om = orc.Model(name, active=["radius"], values=dict(zip([p[0] for p in spec], g[tag + "_pvalues"])))
+    q = g["q"]
+    eng = gpu_common.engine_for(om, [(q, np.ones_like(q), np.ones_like(q))],
+                                smear=(g[tag + "_off"], g[tag + "_w"], bool(g[tag + "_two_d"])))
+    it, v, w, s = eng.eval(g[tag + "_pset"], 0.6666666, precision=prec)
+    eng.set_smearing(None)
+    it_plain, _, _, _ = eng.eval(g[tag + "_pset"], 0.6666666, precision=prec)
+    eng.close()
+    ref = g[tag + "_it"]
+    if prec == FP64:
+        np.testing.assert_allclose(it, ref, rtol=1e-9)
+    else:
+        env = np.maximum.accumulate(np.abs(ref[:, ::-1]), axis=1)[:, ::-1]
+        assert (np.abs(it - ref) / env).max() < 5e-4
+    assert np.abs(it_plain / ref - 1).max() > 1e-2          # smearing was really on / is really off
+
+
+@pytest.mark.parametrize("name", common.SMEAR_CHAINS)
+@pytest.mark.parametrize("spec_max,cluster", [(1, 1), (32, 1), (32, 2)])
+def test_deterministic_smeared_chain_matches_reference(name, spec_max, cluster):
+    g = common.load_chain(name)
+    out = gpu_common.run_golden_chain(g, FP64, spec_max, cluster=cluster)
+    assert int(out["num_iter"][0, 0]) == g["num_iter"]
+    assert int(out["num_moves"][0, 0]) == g["num_moves"]
+    assert np.array_equal(out["accept"], g["accept"])
+    assert abs(out["conval0"][0, 0] / g["conval0"] - 1) < REL_CHI
+    assert abs(out["conval"][0, 0] / g["conval"] - 1) < REL_CHI
+    np.testing.assert_allclose(out["contribs"][0, :, :, 0], g["rset"], rtol=1e-12, atol=0)
+    np.testing.assert_allclose(out["fit_meas"][0][:, 0], g["fit_meas"], rtol=1e-6)
+
+
+def test_smeared_production_chain_tracks_fp64_chain():
+    """fp32 production kernel with a smearing profile (the sphere's q fold is off, rows cached)
+    against the fp64 kernel on the same Philox stream."""
+    from mcsas_b200 import Engine
+    g = common.load_chain("sphere_smear")
+    om = common.oracle_model(g)
+    outs = []
+    for prec in (FP64, FP32):
+        eng = gpu_common.engine_for(om, [(g["q"], g["I"], g["sigma"])], smear=common.smear_of(g))
+        eng.run(Engine.make_config(n_contribs=g["N"], n_reps=2, conv_crit=1.0, max_iter=800, max_retries=-1,
+                                   comp_exp=float(g["comp_exp"]), precision=prec, seed=11, record_trace=True))
+        out = eng.fetch()
+        out["tr"] = [eng.fetch_trace(r, 800) for r in range(2)]
+        eng.close()
+        outs.append(out)
+    a, b = outs
+    for r in range(2):
+        n = 800
+        differ = np.nonzero(a["tr"][r][0][:n] != b["tr"][r][0][:n])[0]
+        first = int(differ[0]) if differ.size else n
+        assert first >= 300, first
+        np.testing.assert_allclose(b["tr"][r][1][:first], a["tr"][r][1][:first], rtol=2e-4)

@@ -109,3 +109,50 @@ def test_philox_known_answer():
     assert orc.philox4x32(0, 0, 0, 0) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
     o = orc.philox4x32(0xffffffffffffffff, 0xffffffffffffffff, 0xffffffff, 0xffffffff)
     assert o == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+
+
+@pytest.mark.parametrize("tag", ["sphere_slit", "sphere_2d", "lma_slit", "sphere_gauss"])
+def test_oracle_smeared_eval_matches_reference(tag):
+    """Smeared branch of SASModel.calcIntensity (sasmodel.py:56-73) in the oracle against the
+    unmodified reference (golden: oracle/gen_golden.py smear)."""
+    g = np.load(os.path.join(common.GOLDEN, "eval_smeared.npz"))
+    name = str(g[tag + "_model"])
+    spec = orc.MODEL_SPECS[name][1]
+    om = orc.Model(name, active=["radius"], values=dict(zip([p[0] for p in spec], g[tag + "_pvalues"])))
+    orc.set_smearing(g[tag + "_off"], g[tag + "_w"], bool(g[tag + "_two_d"]))
+    try:
+        it, _, _, _ = orc.eval_contribs(om, g["q"], g[tag + "_pset"], 0.6666666)
+    finally:
+        orc.set_smearing(None)
+    np.testing.assert_allclose(it, g[tag + "_it"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", common.SMEAR_CHAINS)
+def test_oracle_smeared_chain_matches_reference(name):
+    g = common.load_chain(name)
+    om, st = common.oracle_model(g), common.oracle_settings(g)
+    orc.set_smearing(*common.smear_of(g))
+    try:
+        o = orc.chain(om, st, g["q"], g["I"], g["sigma"], g["stream"], trace=True)
+    finally:
+        orc.set_smearing(None)
+    assert o["num_iter"] == g["num_iter"] and o["num_moves"] == g["num_moves"]
+    assert np.array_equal(o["accept"], g["accept"])
+    assert abs(o["conval"] / g["conval"] - 1) < 1e-9
+    np.testing.assert_allclose(o["rset"], g["rset"], rtol=1e-12)
+
+
+def test_smearing_profiles_match_reference():
+    """mcsas_b200.smearing (sasconfig.py:110-149, 209-233) against the reference's prepared
+    (qOffset, weights)."""
+    from mcsas_b200.smearing import GaussianSmearing, TrapezoidSmearing
+    g = np.load(os.path.join(common.GOLDEN, "eval_smeared.npz"))
+    for tag, sm in [("sphere_slit", TrapezoidSmearing(0.02e9, 0.05e9)),
+                    ("sphere_2d", TrapezoidSmearing(0.004e9, 0.012e9, twoDColl=True)),
+                    ("lma_slit", TrapezoidSmearing(0.01e9, 0.03e9)),
+                    ("sphere_gauss", GaussianSmearing(0.01e9))]:
+        qo, w = sm.setIntPoints(g["q"])
+        np.testing.assert_allclose(qo, g[tag + "_off"], rtol=1e-14, atol=0)
+        np.testing.assert_allclose(w, g[tag + "_w"], rtol=1e-14)
+        assert sm.inputValid() and sm.locs(g["q"]).shape == (g["q"].size, qo.size)
+    assert not TrapezoidSmearing(0.05e9, 0.02e9).inputValid()
