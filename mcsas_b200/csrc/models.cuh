@@ -556,14 +556,13 @@ template <class Real> struct Ops<MCSAS_KHOLODENKO, Real> {
 // ---- smearing (sasmodel.py:56-73): only the reference's canSmear models -----------------
 template <int MODEL> struct CanSmear { static constexpr bool value = MODEL == MCSAS_SPHERE || MODEL == MCSAS_LMA_DENSE_SPHERE; };
 
-// Intensity of one contribution at one q point, smeared over the profile when one is set.
+// Smeared intensity of one contribution at one q point.  Out of line on purpose: the loop
+// (fp64 location + phase split per profile point) must not bloat the unsmeared hot loops.
 template <int MODEL, class Real>
-__device__ __forceinline__ Real eval_q(const Contrib<Real> &cc, const Real *nodes, const QuadTab<Real> &qt,
-                                       const QRep<Real> &Q)
+__device__ __noinline__ Real eval_q_smeared(const Contrib<Real> &cc, const Real *nodes, const QuadTab<Real> &qt,
+                                            double q)
 {
     using O = Ops<MODEL, Real>;
-    if (!CanSmear<MODEL>::value || qt.sm->n == 0) return O::eval(cc, nodes, qt, Q);
-    const double q = Q.q_si();
     Real acc = 0;
     for (int k = 0; k < qt.sm->n; ++k) {
         const double o = qt.sm->off[k];
@@ -572,4 +571,13 @@ __device__ __forceinline__ Real eval_q(const Contrib<Real> &cc, const Real *node
         acc += (Real)qt.sm->tw[k] * O::eval(cc, nodes, qt, Qk);
     }
     return acc;
+}
+
+// Intensity of one contribution at one q point, smeared over the profile when one is set.
+template <int MODEL, class Real>
+__device__ __forceinline__ Real eval_q(const Contrib<Real> &cc, const Real *nodes, const QuadTab<Real> &qt,
+                                       const QRep<Real> &Q)
+{
+    if (!CanSmear<MODEL>::value || qt.sm->n == 0) return Ops<MODEL, Real>::eval(cc, nodes, qt, Q);
+    return eval_q_smeared<MODEL, Real>(cc, nodes, qt, Q.q_si());
 }
