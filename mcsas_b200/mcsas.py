@@ -56,13 +56,13 @@ class McSAS(object):
         """`McSAS.factory()()` as in the reference (mcsas.py:143-147)."""
         return cls
 
-    def __init__(self, device=0, seed=None, precision=_lib.FP32, first_chain=0, specMax=0):
+    def __init__(self, device=0, seed=None, precision=None, first_chain=0, specMax=0):
         self._params = _settings()
         for p in self._params:
             setattr(self, p.name(), p)
         self.device = device
         self.seed = seed if seed is not None else int(time.time_ns() & 0x7FFFFFFFFFFFFFFF)
-        self.precision = precision
+        self.precision = precision      # None: chosen per data set (_resolvePrecision)
         self.firstChain = first_chain
         self.specMax = specMax
         self.proposalStream = None      # deterministic parity mode: [numReps][stream] in [0,1)
@@ -110,9 +110,23 @@ class McSAS(object):
             max_retries=int(self.maxRetries()), comp_exp=float(self.compensationExponent()),
             find_background=bool(self.findBackground()),
             positive_background=bool(self.positiveBackground()),
-            start_from_minimum=bool(self.startFromMinimum()), precision=self.precision,
+            start_from_minimum=bool(self.startFromMinimum()), precision=self._resolvePrecision(),
             seed=self.seed, spec_max=self.specMax, record_trace=record_trace,
             first_chain=self.firstChain)
+
+    # fp32 form factors are ~3e-7 accurate: enough while the relative uncertainties are well
+    # above that; data with sigma/I below this run the fp64 kernel
+    FP32_MIN_REL_SIGMA = 1e-3
+
+    def _resolvePrecision(self):
+        if self.precision is not None:
+            return self.precision
+        _, I, sigma = hot_path_vectors(self.data)
+        nz = np.abs(I) > 0
+        if not nz.any():
+            return _lib.FP32
+        rel = np.median(np.abs(sigma[nz] / I[nz]))
+        return _lib.FP32 if rel >= self.FP32_MIN_REL_SIGMA else _lib.FP64
 
     def _launch(self, numContribs, numReps, stream=None, record_trace=False):
         eng = self.engine

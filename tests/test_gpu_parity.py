@@ -48,6 +48,30 @@ def test_eval_matches_oracle_and_reference(name, prec):
         assert np.median(err) < 2e-5
 
 
+@pytest.mark.parametrize("prec", [FP64, FP32])
+def test_kholodenko_series_integral_matches_oracle_at_high_q(prec):
+    """kho_p0sq_series (Gauss-Legendre near the origin + closed-form exponential series) against
+    the oracle's adaptive Gauss-Kronrod integral (kholodenko.py:31-38) on the config-4 q range
+    (0.01 - 10 1/nm: q lK/3 up to ~170, ~1000 oscillations of the integrand)."""
+    NM = 1e-9
+    om = orc.Model("Kholodenko", active=["radius", "lenKuhn", "lenContour"])
+    q = np.logspace(np.log10(0.01), np.log10(10.0), 40) * 1e9
+    rng = np.random.default_rng(5)
+    pset = np.stack([rng.uniform(1, 5, 6) * NM, rng.uniform(10, 50, 6) * NM,
+                     rng.uniform(100, 1000, 6) * NM], 1)
+    pset[0] = [1 * NM, 10 * NM, 1000 * NM]
+    pset[1] = [5 * NM, 50 * NM, 100 * NM]
+    eng = gpu_common.engine_for(om, [(q, np.ones_like(q), np.ones_like(q))])
+    it, v, w, s = eng.eval(pset, 0.6666666, precision=prec)
+    eng.close()
+    oit, ov, ow, os_ = orc.eval_contribs(om, q, pset, 0.6666666)
+    # relative to the running envelope: the cross-section factor 2 J1(qR)/(qR) has zeros
+    env = np.maximum.accumulate(np.abs(oit[:, ::-1]), axis=1)[:, ::-1]
+    err = np.abs(it - oit) / env
+    # fp32 mode: q, R, lK enter as fp32 (6e-8 relative), amplified by q R <= 50 near the J1 lobes
+    assert err.max() < (1e-8 if prec == FP64 else 1e-4), err.max()
+
+
 CHAINS = [c for c in common.CHAIN_CASES if c != "sphere_posbg"]
 
 

@@ -251,3 +251,20 @@ def test_output_files_from_a_result(tmp_path):
     assert np.array_equal(pickle.load(open(fn, "rb")), contribs)
     txt = open(output.write_settings(str(tmp_path / "s.cfg"), algo, "in.dat", "out", (1e7, 1e9))).read()
     assert "[MCSAS Settings]" in txt and "numcontribs = 300" in txt.lower() and "radius_min" in txt
+
+
+def test_precision_follows_the_data_uncertainty():
+    """Production (fp32) arithmetic only where the relative uncertainties are well above the
+    fp32 form-factor accuracy; an explicit choice is kept."""
+    from mcsas_b200 import _lib
+    from mcsas_b200.data import SASData
+    from mcsas_b200.mcsas import McSAS
+    q = np.logspace(-1, 0, 20) * 1e9
+    I = np.linspace(10., 1., 20)
+    algo = McSAS(seed=1)
+    algo.data = SASData(q, I, 0.01 * I)
+    assert algo._resolvePrecision() == _lib.FP32
+    algo.data = SASData(q, I, 1e-4 * I)
+    assert algo._resolvePrecision() == _lib.FP64
+    algo.precision = _lib.FP32
+    assert algo._resolvePrecision() == _lib.FP32

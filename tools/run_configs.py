@@ -33,6 +33,8 @@ def fit(tag, model, q, I, sig, reps, max_iter=100000):
     algo.numReps.setValue(reps)
     algo.maxIterations.setValue(max_iter)
     algo.showIncomplete.setValue(True)
+    if os.environ.get("MAX_RETRIES"):
+        algo.maxRetries.setValue(int(os.environ["MAX_RETRIES"]))
     t0 = time.perf_counter()
     algo.analyse()
     wall = time.perf_counter() - t0
