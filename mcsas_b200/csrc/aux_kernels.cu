@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(FR_THREADS) fractions_kernel(const __grid_cons
     for (int j = tid; j < D; j += T) { s_qx[j] = (Real)a.quad_x[j]; s_qw[j] = (Real)a.quad_w[j]; }
     for (int i = tid; i < nq; i += T) s_ft[i] = 0.;
     __syncthreads();
-    const QuadTab<Real> qt = { D, a.mp.quad_rule, s_qx, s_qw, &a.smear };
+    const QuadTab<Real> qt = { D, a.mp.quad_rule, s_qx, s_qw, &a.smear, a.smear.n };
     if (tid == 0) {
         double G = 1.;
         if (sizeof(Real) == 4) {

@@ -1,6 +1,7 @@
 // capi.cu -- the C-ABI of libmcsas_b200.so (include/mcsas_b200.h): context, uploads,
 // launch of the chain / eval / fraction kernels, result fetch.  No torch types, no CPU
 // fallback: every compute entry point needs a CUDA device.
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -31,8 +32,8 @@ static const eval_launch_fn EVAL_FN[MCSAS_N_MODELS] = {
 
 struct mcsas_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_begin = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;     // stream2: the larger-cluster half of a mixed slice
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_begin = nullptr, ev_mix = nullptr;
     float span_ms = 0.f;          // first launch start -> last slice end (host gaps between slices included)
     cudaDeviceProp prop;
     std::string err;
@@ -52,6 +53,7 @@ struct mcsas_ctx {
     int n_slots = 0;              // state slots on the device: 2 per chain (current attempt + backup attempt)
     bool backups = false;         // speculative next attempts of late chains on idle SMs
     int max_attempts = 1;
+    std::vector<double> h_conval;                  // per slot: chi-squared after the last slice (mixed slices)
     std::vector<int> cur, bak, bak_state;          // per chain: slot of the current attempt, backup slot (-1), 1 running / 2 finished
     std::vector<char> done;
     std::vector<long long> carry_steps, carry_evals;   // work of the failed attempts left behind in the other slot
@@ -79,7 +81,7 @@ struct mcsas_ctx {
     float *d_cache = nullptr;
     int *d_cache_lock = nullptr;
     size_t cache_cap = 0;
-    int n_live = 0, n_launches = 0, last_cluster = 1, last_threads = 0, last_qpt = 0, last_resident = 0;
+    int n_live = 0, n_launches = 0, last_up = 0, last_cluster = 1, last_threads = 0, last_qpt = 0, last_resident = 0;
     float kernel_ms = 0.f;
     volatile int *stop_flag = nullptr;
     std::map<long long, int> occ_cache;
@@ -125,6 +127,8 @@ extern "C" int mcsas_ctx_create(int device, mcsas_ctx **out)
         || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess
         || cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess
         || cudaEventCreate(&ctx->ev_begin) != cudaSuccess
+        || cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess
+        || cudaEventCreateWithFlags(&ctx->ev_mix, cudaEventDisableTiming) != cudaSuccess
         || cudaHostAlloc((void **)&ctx->h_stop, sizeof(int), cudaHostAllocMapped) != cudaSuccess
         || cudaHostGetDevicePointer((void **)&ctx->d_stop, ctx->h_stop, 0) != cudaSuccess) {
         g_create_err = std::string("CUDA context setup failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -145,8 +149,8 @@ extern "C" void mcsas_ctx_destroy(mcsas_ctx *ctx)
     cudaFree(ctx->d_rset); cudaFree(ctx->d_fit); cudaFree(ctx->d_scal); cudaFree(ctx->d_cnt);
     cudaFree(ctx->d_att); cudaFree(ctx->d_tacc); cudaFree(ctx->d_tchi); cudaFree(ctx->d_ids); cudaFree(ctx->d_prof); cudaFree(ctx->d_cache); cudaFree(ctx->d_cache_lock);
     cudaFreeHost(ctx->h_stop);
-    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_begin);
-    cudaStreamDestroy(ctx->stream);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_begin); cudaEventDestroy(ctx->ev_mix);
+    cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->stream2);
     delete ctx;
 }
 
@@ -384,13 +388,14 @@ struct ChainPlan { int cluster, layout, threads, resident, warps_q; };
 
 static int query_resident(mcsas_ctx *ctx, int c, int layout, int block_threads, int *resident)
 {
-    const long long key = ((((long long)ctx->mp.model_id * 2 + ctx->precision) * 16 + c) * 8 + layout) * 2048
+    const int smear = ctx->smear.n > 0;
+    const long long key = (((((long long)ctx->mp.model_id * 2 + ctx->precision) * 2 + smear) * 16 + c) * 8 + layout) * 2048
                           + block_threads + ((long long)ctx->smem << 26);
     auto it = ctx->occ_cache.find(key);
     if (it != ctx->occ_cache.end()) { *resident = it->second; return 0; }
     int regs = 0;
     *resident = 0;
-    cudaError_t e = QUERY_FN[ctx->mp.model_id](ctx->precision, layout, block_threads, ctx->smem, c, resident, &regs);
+    cudaError_t e = QUERY_FN[ctx->mp.model_id](ctx->precision, smear, layout, block_threads, ctx->smem, c, resident, &regs);
     if (e != cudaSuccess) { cudaGetLastError(); *resident = 0; }
     ctx->occ_cache[key] = *resident;
     return 0;
@@ -500,29 +505,80 @@ static int plan_chain(mcsas_ctx *ctx, int nq, int n_live, ChainPlan *out)
 }
 
 // Launch one time slice for the chains listed in ctx->h_ids[0..n_live).
+//
+// Mixed slices (fp32 production kernel, automatic layout): when the planned cluster size C
+// leaves SMs idle (config 2: 100 chains x 1 CTA on 148 SMs), n_up = idle / C chains run this
+// slice as 2C-CTA clusters in a second, concurrent launch: those with the largest chi-squared.  Their slice is 11/8 as many batches (a 2C cluster runs a batch ~1.4x faster,
+// tools/tune.py), so both launches end together.
 static int launch_slice(mcsas_ctx *ctx, int n_live, bool resume)
 {
     ChainArgs a = ctx->args;
     ChainPlan pl;
     int prc = plan_chain(ctx, ctx->nq_max, n_live, &pl);
     if (prc) return prc;
-    a.cluster = pl.cluster;
-    a.warps_q = pl.warps_q;
-    ctx->last_threads = pl.threads; ctx->last_qpt = CHAIN_QPT[pl.layout]; ctx->last_resident = pl.resident;
     a.resume = resume ? 1 : 0;
+    int n_up = 0;
+    ChainPlan pu = pl;
+    const char *mixed_env = getenv("MCSAS_B200_MIXED");
+    const bool mixed_on = mixed_env ? atoi(mixed_env) != 0 : true;
+    if (mixed_on && ctx->precision == MCSAS_FP32 && ctx->forced_cluster == 0 && !getenv("MCSAS_B200_CLUSTER")
+        && a.slice_batches > 0 && pl.cluster < 4 && n_live <= pl.resident) {
+        const int spare = ctx->prop.multiProcessorCount - n_live * pl.cluster;
+        n_up = spare / pl.cluster;
+        if (n_up > n_live) n_up = n_live;
+        if (n_up >= 1) {
+            ctx->forced_cluster = 2 * pl.cluster;
+            prc = plan_chain(ctx, ctx->nq_max, n_up, &pu);
+            ctx->forced_cluster = 0;
+            if (prc || pu.cluster != 2 * pl.cluster || pu.resident < n_up) n_up = 0;
+        } else n_up = 0;
+    }
+    ctx->last_threads = pl.threads; ctx->last_qpt = CHAIN_QPT[pl.layout]; ctx->last_resident = pl.resident;
     a.chain_ids = nullptr;
-    if (n_live != ctx->n_chains || resume) {
+    if (n_up > 0 && n_up < n_live && (int)ctx->h_conval.size() == ctx->n_slots) {
+        // the chains that are furthest from the criterion get the larger clusters: they are the
+        // likely critical path of the fit (deterministic: a function of the chains' states only)
+        const std::vector<double> &cv = ctx->h_conval;
+        std::stable_sort(ctx->h_ids.begin(), ctx->h_ids.begin() + n_live,
+                         [&cv](int x, int y) { return cv[x] > cv[y]; });
+    }
+    if (n_live != ctx->n_chains || resume || n_up > 0) {
         CK(cudaMemcpyAsync(ctx->d_ids, ctx->h_ids.data(), sizeof(int) * n_live, cudaMemcpyHostToDevice, ctx->stream));
         a.chain_ids = ctx->d_ids;
     }
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    cudaError_t e = CHAIN_FN[a.mp.model_id](ctx->precision, pl.layout, n_live * pl.cluster,
-                                            pl.threads + (ctx->precision == MCSAS_FP64 ? 32 : 0),   // fp64: + producer warp
-                                            ctx->smem, ctx->stream, a);
-    if (e != cudaSuccess) return fail(ctx, MCSAS_ERR_CUDA, "chain kernel launch: %s", cudaGetErrorString(e));
+    const int extra = ctx->precision == MCSAS_FP64 ? 32 : 0;                          // fp64: + producer warp
+    if (n_up > 0) {
+        // the clusters go first, on the main stream, so that they are placed while the SMs are
+        // still empty; the single-size CTAs follow on stream2 (behind ev0 only) and fill the rest
+        ChainArgs u = a;
+        u.cluster = pu.cluster;
+        u.warps_q = pu.warps_q;
+        u.slice_batches = a.slice_batches * 11 / 8;
+        u.slice_steps = a.slice_steps * 11 / 8;
+        cudaError_t e = CHAIN_FN[a.mp.model_id](ctx->precision, pu.layout, n_up * pu.cluster, pu.threads + extra,
+                                                ctx->smem, ctx->stream, u);
+        if (e != cudaSuccess) return fail(ctx, MCSAS_ERR_CUDA, "chain kernel launch (mixed slice): %s", cudaGetErrorString(e));
+        ctx->n_launches++;
+        a.chain_ids = ctx->d_ids + n_up;
+    }
+    if (n_live - n_up > 0) {
+        cudaStream_t st = ctx->stream;
+        if (n_up > 0) { st = ctx->stream2; CK(cudaStreamWaitEvent(st, ctx->ev0, 0)); }
+        a.cluster = pl.cluster;
+        a.warps_q = pl.warps_q;
+        cudaError_t e = CHAIN_FN[a.mp.model_id](ctx->precision, pl.layout, (n_live - n_up) * pl.cluster,
+                                                pl.threads + extra, ctx->smem, st, a);
+        if (e != cudaSuccess) return fail(ctx, MCSAS_ERR_CUDA, "chain kernel launch: %s", cudaGetErrorString(e));
+        ctx->n_launches++;
+        if (n_up > 0) {
+            CK(cudaEventRecord(ctx->ev_mix, st));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_mix, 0));
+        }
+    }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    ctx->n_launches++;
-    ctx->last_cluster = pl.cluster;
+    ctx->last_cluster = n_live - n_up > 0 ? pl.cluster : pu.cluster;
+    ctx->last_up = n_up;
     return MCSAS_OK;
 }
 
@@ -699,6 +755,7 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     ctx->h_ids.resize(n_slots);
     for (int i = 0; i < n_chains; ++i) ctx->h_ids[i] = i;
     ctx->n_live = n_chains;
+    ctx->h_conval.clear();
     ctx->n_launches = 0;
     ctx->kernel_ms = 0.f;
     ctx->stop_flag = stop_flag;
@@ -735,8 +792,8 @@ extern "C" int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms)
         CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         ctx->kernel_ms += ms;
         if (getenv("MCSAS_B200_DEBUG"))
-            fprintf(stderr, "[mcsas_b200] slice %d: live %d cluster %d T %d qpt %d resident %d  %.3f ms\n",
-                    ctx->n_launches, ctx->n_live, ctx->last_cluster, ctx->last_threads, ctx->last_qpt,
+            fprintf(stderr, "[mcsas_b200] slice %d: live %d cluster %d (%d chains at twice that) T %d qpt %d resident %d  %.3f ms\n",
+                    ctx->n_launches, ctx->n_live, ctx->last_cluster, ctx->last_up, ctx->last_threads, ctx->last_qpt,
                     ctx->last_resident, ms);
         if (ctx->args.slice_steps <= 0) break;
         CK(cudaMemcpy(att.data(), ctx->d_att, sizeof(int) * att.size(), cudaMemcpyDeviceToHost));
@@ -747,6 +804,10 @@ extern "C" int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms)
                 return fail(ctx, MCSAS_ERR_CUDA, "chain %d: kernel watchdog fired (status %d)", s % NC, status[s]);
         }
         if (ctx->backups) CK(cudaMemcpy(cnt.data(), ctx->d_cnt, sizeof(long long) * cnt.size(), cudaMemcpyDeviceToHost));
+        if (ctx->precision == MCSAS_FP32 && ctx->args.slice_batches > 0) {
+            ctx->h_conval.resize(NS);
+            CK(cudaMemcpy(ctx->h_conval.data(), ctx->d_scal + 2 * (size_t)NS, sizeof(double) * NS, cudaMemcpyDeviceToHost));
+        }
         const long long *num_iter = cnt.data(), *evals = cnt.data() + 2 * (size_t)NS, *steps_all = cnt.data() + 3 * (size_t)NS;
         // ---- per chain: current attempt finished / failed / continues; backup bookkeeping --------
         int n = 0, n_primary = 0;

@@ -139,7 +139,7 @@ template <> struct FastOps<MCSAS_SPHERE> {
     __device__ __forceinline__ static float evalS(const Contrib<float> &cc, const float *,
                                                   const QuadTab<float> &qt, const QRep<float> &Q)
     {
-        if (qt.sm->n) return eval_q<MCSAS_SPHERE, float>(cc, nullptr, qt, Q);     // smeared: no q fold
+        if (qt.nsm) return eval_q<MCSAS_SPHERE, float>(cc, nullptr, qt, Q);     // smeared: no q fold
         const float q[1] = {Q.q}, th[1] = {Q.th}, tl[1] = {Q.tl}, r[1] = {cc.c[0]};
         float g[1];
         sph_g_vec<1, true>(q, th, tl, r, g);
@@ -152,7 +152,7 @@ template <> struct FastOps<MCSAS_SPHERE> {
     __device__ __forceinline__ static void evalN(const Contrib<float> &cc, const float *, const QuadTab<float> &qt,
                                                  const QRep<float> (&Q)[QPT], float (&d)[QPT])
     {
-        if (qt.sm->n) {
+        if (qt.nsm) {
 #pragma unroll
             for (int j = 0; j < QPT; ++j) d[j] = eval_q<MCSAS_SPHERE, float>(cc, nullptr, qt, Q[j]);
             return;
@@ -178,7 +178,7 @@ template <> struct FastOps<MCSAS_SPHERE> {
                                                      const float *, size_t, const QuadTab<float> &qt,
                                                      const QRep<float> (&Q)[QPT], float (&d)[NS][QPT])
     {
-        if (qt.sm->n) {
+        if (qt.nsm) {
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
                 const Contrib<float> cn = ring[ent[s]].cn;
@@ -228,7 +228,7 @@ template <> struct FastOps<MCSAS_SPHERE> {
                                                  const float *, const float *, const QuadTab<float> &qt,
                                                  const QRep<float> (&Q)[QPT], float (&d)[QPT])
     {
-        if (qt.sm->n) {
+        if (qt.nsm) {
 #pragma unroll
             for (int j = 0; j < QPT; ++j)
                 d[j] = eval_q<MCSAS_SPHERE, float>(cn, nullptr, qt, Q[j]) - eval_q<MCSAS_SPHERE, float>(co, nullptr, qt, Q[j]);
@@ -339,7 +339,9 @@ template <int NG> __device__ __forceinline__ int grp_perm(int lane)
 // memory (L2 resident: N x nq floats per chain), so the "old" half of every evaluation
 // (mcsas.py:362 recomputes it) is one coalesced load; rows are rebuilt with the initial sum
 // of every launch and rewritten when a move is accepted.
-template <int MODEL, int QPT, bool CACHE>
+// SMEAR: instantiation for data with a smearing profile (sasmodel.py:56-73); the unsmeared
+// instantiation folds every smearing branch away at compile time.
+template <int MODEL, int QPT, bool CACHE, bool SMEAR>
 __global__ void __launch_bounds__(QPT == 1 ? 1024 : (QPT == 2 ? 512 : 256), 1)
 chain_fast_kernel(const __grid_constant__ ChainArgs a)
 {
@@ -428,7 +430,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     }
     mbar_wait(s_bar, 0);
     __syncthreads();
-    const QuadTab<float> qt = { D, a.mp.quad_rule, s_qx, s_qw, &a.smear };
+    const QuadTab<float> qt = { D, a.mp.quad_rule, s_qx, s_qw, &a.smear, SMEAR ? a.smear.n : 0 };
     const float qref = (float)(ds.q_ref * 1e-9);   // 1/nm
 
     // ---- per-thread resident state of q points (rank*TQ + qtid)*QPT + j, j < QPT (contiguous:
@@ -448,7 +450,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         if (ev == 0.0) ev = 1. * inorm;                          // backgroundscalingfit.py:117
         Q[j].set(qv);
         double qsd = 1.;
-        if (FO::QS_POW > 0 && a.smear.n == 0) {                  // (smeared: locations differ per profile point)
+        if (FO::QS_POW > 0 && qt.nsm == 0) {                  // (smeared: locations differ per profile point)
             double t = (double)qref / (qv * 1e-9);
             double t2 = t * t;
             qsd = FO::QS_POW == 6 ? t2 * t2 * t2 : (FO::QS_POW == 4 ? t2 * t2 : t2);

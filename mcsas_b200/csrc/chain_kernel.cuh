@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(288) chain_kernel(const __grid_constant__ Chai
     }
     mbar_wait(s_bar, 0);
     __syncthreads();
-    const QuadTab<Real> qt = { D, a.mp.quad_rule, s_qx, s_qw, &a.smear };
+    const QuadTab<Real> qt = { D, a.mp.quad_rule, s_qx, s_qw, &a.smear, a.smear.n };
 
     // ---- per-thread resident state: q point (j*C + rank)*T + tid -------------------------
     constexpr bool TWO_PASS = sizeof(Real) == 8;   // parity mode: residual-form chi-squared
@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(128) eval_kernel(const __grid_constant__ EvalA
         s_qw[j] = (Real)a.quad_w[j];
     }
     __syncthreads();
-    const QuadTab<Real> qt = { D, a.mp.quad_rule, s_qx, s_qw, &a.smear };
+    const QuadTab<Real> qt = { D, a.mp.quad_rule, s_qx, s_qw, &a.smear, a.smear.n };
     if (tid == 0) {
         PVec p(a.mp, a.pset + (long long)c * a.mp.n_active);
         double G = 1.;

@@ -18,12 +18,12 @@ typedef cudaError_t (*chain_launch_fn)(int prec, int layout, int grid, int threa
 typedef cudaError_t (*eval_launch_fn)(int prec, int grid, size_t smem, cudaStream_t st,
                                       const EvalArgs &a);
 
-typedef cudaError_t (*chain_query_fn)(int prec, int layout, int threads, size_t smem, int cluster,
+typedef cudaError_t (*chain_query_fn)(int prec, int smear, int layout, int threads, size_t smem, int cluster,
                                       int *max_clusters, int *regs);
 
 #define DECL_MODEL(N) \
     cudaError_t mcsas_launch_chain_##N(int, int, int, int, size_t, cudaStream_t, const ChainArgs &); \
-    cudaError_t mcsas_query_chain_##N(int, int, int, size_t, int, int *, int *); \
+    cudaError_t mcsas_query_chain_##N(int, int, int, int, size_t, int, int *, int *); \
     cudaError_t mcsas_launch_eval_##N(int, int, size_t, cudaStream_t, const EvalArgs &);
 DECL_MODEL(0) DECL_MODEL(1) DECL_MODEL(2) DECL_MODEL(3)
 DECL_MODEL(4) DECL_MODEL(5) DECL_MODEL(6) DECL_MODEL(7)

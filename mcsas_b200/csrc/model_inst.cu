@@ -10,22 +10,24 @@
 #define CAT(a, b) CAT2(a, b)
 
 // kernel of one (precision, layout): fp64 -> parity kernel, fp32 -> production kernel
-template <class Real, int QPT> struct KernelOf {
+// SMEAR selects the production kernel's instantiation for smeared data (only for the models
+// the reference can smear; the parity kernel decides at run time)
+template <class Real, int QPT, bool SMEAR> struct KernelOf {
     static auto get() { return chain_kernel<MODEL_ID, Real, QPT>; }
 };
-template <int QPT> struct KernelOf<float, QPT> {
-    static auto get() { return chain_fast_kernel<MODEL_ID, QPT, false>; }
+template <int QPT, bool SMEAR> struct KernelOf<float, QPT, SMEAR> {
+    static auto get() { return chain_fast_kernel<MODEL_ID, QPT, false, SMEAR && CanSmear<MODEL_ID>::value>; }
 };
 struct CachedF {};            // tag: fp32 production kernel with the contribution-row cache
-template <int QPT> struct KernelOf<CachedF, QPT> {
-    static auto get() { return chain_fast_kernel<MODEL_ID, QPT, true>; }
+template <int QPT, bool SMEAR> struct KernelOf<CachedF, QPT, SMEAR> {
+    static auto get() { return chain_fast_kernel<MODEL_ID, QPT, true, SMEAR && CanSmear<MODEL_ID>::value>; }
 };
 
-template <class Real, int QPT>
+template <class Real, int QPT, bool SMEAR>
 static cudaError_t launch_one(int grid, int threads, size_t smem, cudaStream_t st,
                               const ChainArgs &a)
 {
-    auto k = KernelOf<Real, QPT>::get();
+    auto k = KernelOf<Real, QPT, SMEAR>::get();
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
@@ -43,10 +45,10 @@ static cudaError_t launch_one(int grid, int threads, size_t smem, cudaStream_t s
     return cudaLaunchKernelEx(&cfg, k, a);
 }
 
-template <class Real, int QPT>
+template <class Real, int QPT, bool SMEAR>
 static cudaError_t query_one(int threads, size_t smem, int cluster, int *max_clusters, int *regs)
 {
-    auto k = KernelOf<Real, QPT>::get();
+    auto k = KernelOf<Real, QPT, SMEAR>::get();
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaFuncAttributes fa;
@@ -67,33 +69,34 @@ static cudaError_t query_one(int threads, size_t smem, int cluster, int *max_clu
     return cudaOccupancyMaxActiveClusters(max_clusters, k, &cfg);
 }
 
-template <class Real>
+template <class Real, bool SMEAR>
 static cudaError_t query_prec(int layout, int threads, size_t smem, int cluster, int *mc, int *regs)
 {
     switch (layout) {
-    case 0: return query_one<Real, 1>(threads, smem, cluster, mc, regs);
-    case 1: return query_one<Real, 2>(threads, smem, cluster, mc, regs);
-    case 2: return query_one<Real, 4>(threads, smem, cluster, mc, regs);
+    case 0: return query_one<Real, 1, SMEAR>(threads, smem, cluster, mc, regs);
+    case 1: return query_one<Real, 2, SMEAR>(threads, smem, cluster, mc, regs);
+    case 2: return query_one<Real, 4, SMEAR>(threads, smem, cluster, mc, regs);
     }
     return cudaErrorInvalidValue;
 }
 
 // co-resident clusters of this configuration on the current device
-cudaError_t CAT(mcsas_query_chain_, MODEL_ID)(int prec, int layout, int threads, size_t smem,
+cudaError_t CAT(mcsas_query_chain_, MODEL_ID)(int prec, int smear, int layout, int threads, size_t smem,
                                               int cluster, int *max_clusters, int *regs)
 {
-    return prec == MCSAS_FP64 ? query_prec<double>(layout, threads, smem, cluster, max_clusters, regs)
-                              : query_prec<CachedF>(layout, threads, smem, cluster, max_clusters, regs);
+    if (prec == MCSAS_FP64) return query_prec<double, false>(layout, threads, smem, cluster, max_clusters, regs);
+    return smear ? query_prec<CachedF, true>(layout, threads, smem, cluster, max_clusters, regs)
+                 : query_prec<CachedF, false>(layout, threads, smem, cluster, max_clusters, regs);
 }
 
-template <class Real>
+template <class Real, bool SMEAR>
 static cudaError_t launch_prec(int layout, int grid, int threads, size_t smem, cudaStream_t st,
                                const ChainArgs &a)
 {
     switch (layout) {
-    case 0: return launch_one<Real, 1>(grid, threads, smem, st, a);
-    case 1: return launch_one<Real, 2>(grid, threads, smem, st, a);
-    case 2: return launch_one<Real, 4>(grid, threads, smem, st, a);
+    case 0: return launch_one<Real, 1, SMEAR>(grid, threads, smem, st, a);
+    case 1: return launch_one<Real, 2, SMEAR>(grid, threads, smem, st, a);
+    case 2: return launch_one<Real, 4, SMEAR>(grid, threads, smem, st, a);
     }
     return cudaErrorInvalidValue;
 }
@@ -101,9 +104,12 @@ static cudaError_t launch_prec(int layout, int grid, int threads, size_t smem, c
 cudaError_t CAT(mcsas_launch_chain_, MODEL_ID)(int prec, int layout, int grid, int threads,
                                                size_t smem, cudaStream_t st, const ChainArgs &a)
 {
-    if (prec == MCSAS_FP64) return launch_prec<double>(layout, grid, threads, smem, st, a);
-    return a.cache ? launch_prec<CachedF>(layout, grid, threads, smem, st, a)
-                   : launch_prec<float>(layout, grid, threads, smem, st, a);
+    if (prec == MCSAS_FP64) return launch_prec<double, false>(layout, grid, threads, smem, st, a);
+    if (a.smear.n > 0)
+        return a.cache ? launch_prec<CachedF, true>(layout, grid, threads, smem, st, a)
+                       : launch_prec<float, true>(layout, grid, threads, smem, st, a);
+    return a.cache ? launch_prec<CachedF, false>(layout, grid, threads, smem, st, a)
+                   : launch_prec<float, false>(layout, grid, threads, smem, st, a);
 }
 
 cudaError_t CAT(mcsas_launch_eval_, MODEL_ID)(int prec, int grid, size_t smem, cudaStream_t st,

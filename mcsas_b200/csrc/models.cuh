@@ -162,6 +162,8 @@ template <class Real> struct QuadTab {
     const Real *x;
     const Real *wt;
     const SmearTab *sm;      // smearing profile (n = 0: none)
+    int nsm;                 // profile points in use: sm->n, or a compile-time 0 in the kernel
+                             // instantiations for unsmeared data (their hot loops carry no smear code)
 };
 
 template <int MODEL, class Real> struct Ops;
@@ -689,6 +691,6 @@ template <int MODEL, class Real>
 __device__ __forceinline__ Real eval_q(const Contrib<Real> &cc, const Real *nodes, const QuadTab<Real> &qt,
                                        const QRep<Real> &Q)
 {
-    if (!CanSmear<MODEL>::value || qt.sm->n == 0) return Ops<MODEL, Real>::eval(cc, nodes, qt, Q);
+    if (!CanSmear<MODEL>::value || qt.nsm == 0) return Ops<MODEL, Real>::eval(cc, nodes, qt, Q);
     return eval_q_smeared<MODEL, Real>(cc, nodes, qt, Q.q_si());
 }

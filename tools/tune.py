@@ -50,6 +50,9 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["base"]
     if "base" in which:
         run("auto", {})
+    if "mixed" in which:
+        for m in ("0", "1", "0", "1"):
+            run("mixed=%s" % m, {"MCSAS_B200_MIXED": m}, seeds=(1, 2, 4, 7, 9, 11))
     if "grid" in which:
         for c in (1, 2, 4, 8):
             for qpt in (1, 2, 4):
