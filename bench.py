@@ -260,7 +260,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "sfu", "achieved": mufu_ach, "peak": peaks["mufu_gops"],
                          "unit": "GMUFU/s", "frac": mufu_ach / peaks["mufu_gops"],
-                         "traffic": 3.31e9,   # ncu dram read+write bytes of one time-slice launch (profiles/r01c_ncu_chain_fast_summary.txt)
+                         "traffic": 3.07e9,   # ncu dram read+write bytes of one time-slice launch (profiles/r01e_ncu_chain_fast_summary.txt)
                          "executed_mufu_frac": per_gpu * MUFU_EXECUTED_PER_STEP * 1e-9 / peaks["mufu_gops"],
                          "peak_source": "measured live: mcsas_measure_peaks (sin+cos+rcp MUFU mix)",
                          "fp32": {"achieved": fp32_ach, "peak": peaks["ffma_tflops"],
