@@ -52,6 +52,10 @@ template <int MODEL> struct FastOps {
                                                  const QuadTab<float> &qt, const QRep<float> (&Q)[QPT],
                                                  float (&d)[QPT])
     {
+        if constexpr (MODEL == MCSAS_CYLINDERS_ISOTROPIC && QPT > 1) {
+            O::template evalV<QPT>(cc, nodes, qt, Q, d);       // q points interleaved in the node loop
+            return;
+        }
 #pragma unroll
         for (int j = 0; j < QPT; ++j) d[j] = evalS(cc, nodes, qt, Q[j]);
     }

@@ -385,6 +385,95 @@ __device__ __forceinline__ float bessel_j1(float x)
 __device__ __forceinline__ double recip(double x) { return 1. / x; }
 __device__ __forceinline__ float recip(float x) { return fast_rcp(x); }
 
+// M independent J1 evaluations written stage by stage (same arithmetic as bessel_j1(float)):
+// ptxas keeps program order, so this form gives M-way instruction-level parallelism where M
+// scalar calls in a row are scheduled as M serial dependency chains.
+template <int M> __device__ __forceinline__ void bessel_j1_vec(const float (&x)[M], float (&out)[M])
+{
+    float y[M], n1[M], d1[M], z[M], w[M], p[M], qv[M], t[M], nn[M], sn[M], cs[M], rt[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) y[i] = x[i] * x[i];
+#pragma unroll
+    for (int i = 0; i < M; ++i) n1[i] = fmaf(y[i], -30.16036606f, 15704.48260f);
+#pragma unroll
+    for (int i = 0; i < M; ++i) d1[i] = y[i] + 376.9991397f;
+#pragma unroll
+    for (int i = 0; i < M; ++i) z[i] = fast_rcp(fmaxf(x[i], 1e-20f));
+#pragma unroll
+    for (int i = 0; i < M; ++i) t[i] = fmaf(x[i], 0.15915494309189535f, -0.375f);   // (x - 3 pi/4) in turns
+#pragma unroll
+    for (int i = 0; i < M; ++i) n1[i] = fmaf(y[i], n1[i], -2972611.439f);
+#pragma unroll
+    for (int i = 0; i < M; ++i) d1[i] = fmaf(y[i], d1[i], 99447.43394f);
+#pragma unroll
+    for (int i = 0; i < M; ++i) nn[i] = (t[i] + 12582912.f) - 12582912.f;
+#pragma unroll
+    for (int i = 0; i < M; ++i) n1[i] = fmaf(y[i], n1[i], 242396853.1f);
+#pragma unroll
+    for (int i = 0; i < M; ++i) d1[i] = fmaf(y[i], d1[i], 18583304.74f);
+#pragma unroll
+    for (int i = 0; i < M; ++i) t[i] = (t[i] - nn[i]) * 6.2831853071795865f;
+#pragma unroll
+    for (int i = 0; i < M; ++i) n1[i] = fmaf(y[i], n1[i], -7895059235.f);
+#pragma unroll
+    for (int i = 0; i < M; ++i) d1[i] = fmaf(y[i], d1[i], 2300535178.f);
+#pragma unroll
+    for (int i = 0; i < M; ++i) cs[i] = __cosf(t[i]);
+#pragma unroll
+    for (int i = 0; i < M; ++i) sn[i] = __sinf(t[i]);
+#pragma unroll
+    for (int i = 0; i < M; ++i) n1[i] = fmaf(y[i], n1[i], 72362614232.f);
+#pragma unroll
+    for (int i = 0; i < M; ++i) d1[i] = fmaf(y[i], d1[i], 144725228442.f);
+#pragma unroll
+    for (int i = 0; i < M; ++i) { z[i] = 8.f * z[i]; w[i] = z[i] * z[i]; }            // z8, w
+#pragma unroll
+    for (int i = 0; i < M; ++i) d1[i] = fast_rcp(d1[i]);
+#pragma unroll
+    for (int i = 0; i < M; ++i) p[i] = fmaf(w[i], -0.240337019e-6f, 0.2457520174e-5f);
+#pragma unroll
+    for (int i = 0; i < M; ++i) qv[i] = fmaf(w[i], 0.105787412e-6f, -0.88228987e-6f);
+#pragma unroll
+    for (int i = 0; i < M; ++i) rt[i] = sqrtf(0.636619772f * (0.125f * z[i]));
+#pragma unroll
+    for (int i = 0; i < M; ++i) p[i] = fmaf(w[i], p[i], -0.3516396496e-4f);
+#pragma unroll
+    for (int i = 0; i < M; ++i) qv[i] = fmaf(w[i], qv[i], 0.8449199096e-5f);
+#pragma unroll
+    for (int i = 0; i < M; ++i) p[i] = fmaf(w[i], p[i], 0.183105e-2f);
+#pragma unroll
+    for (int i = 0; i < M; ++i) qv[i] = fmaf(w[i], qv[i], -0.2002690873e-3f);
+#pragma unroll
+    for (int i = 0; i < M; ++i) p[i] = fmaf(w[i], p[i], 1.f);
+#pragma unroll
+    for (int i = 0; i < M; ++i) qv[i] = fmaf(w[i], qv[i], 0.04687499995f);
+#pragma unroll
+    for (int i = 0; i < M; ++i) n1[i] = x[i] * n1[i] * d1[i];                           // small-argument form
+#pragma unroll
+    for (int i = 0; i < M; ++i) p[i] = rt[i] * (cs[i] * p[i] - z[i] * sn[i] * qv[i]);   // Hankel form
+#pragma unroll
+    for (int i = 0; i < M; ++i) out[i] = x[i] < 8.f ? n1[i] : p[i];
+}
+
+// x_i = q_i r and sin(x_i) for M q points (the phase split of sincos_qr), stage by stage
+template <int M> __device__ __forceinline__ void sin_qr_vec(const QRep<float> (&Q)[M], float r, float (&s)[M],
+                                                            float (&x)[M])
+{
+    float t[M], fr[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) x[i] = Q[i].q * r;
+#pragma unroll
+    for (int i = 0; i < M; ++i) t[i] = Q[i].th * r;
+#pragma unroll
+    for (int i = 0; i < M; ++i) t[i] = (t[i] + 12582912.f) - 12582912.f;
+#pragma unroll
+    for (int i = 0; i < M; ++i) fr[i] = fmaf(Q[i].th, r, -t[i]);
+#pragma unroll
+    for (int i = 0; i < M; ++i) fr[i] = fmaf(Q[i].tl, r, fr[i]);
+#pragma unroll
+    for (int i = 0; i < M; ++i) s[i] = __sinf(fr[i] * 6.2831853071795865f);
+}
+
 template <class Real> struct Ops<MCSAS_CYLINDERS_ISOTROPIC, Real> {
     static constexpr int NARR = 2;
     template <bool FAST, class PV>
@@ -428,6 +517,48 @@ template <class Real> struct Ops<MCSAS_CYLINDERS_ISOTROPIC, Real> {
             acc += qt.wt[j] * (f * f);
         }
         return acc * cc.amp;                            // weights carry the factor 16 (:90)
+    }
+    // fp32 production path: the thread's M q points go through the node loop together (node
+    // data loaded once, M independent chains in flight); same arithmetic as eval()
+    template <int M>
+    __device__ __forceinline__ static void evalV(const Contrib<float> &cc, const float *nodes,
+                                                 const QuadTab<float> &qt, const QRep<float> (&Q)[M],
+                                                 float (&out)[M])
+    {
+        float acc[M];
+        int j0 = 0, j1e = qt.D;
+#pragma unroll
+        for (int i = 0; i < M; ++i) acc[i] = 0.f;
+        if (qt.rule == MCSAS_QUAD_REFERENCE) {
+            float qr[M], jv[M], s[M], x[M];
+#pragma unroll
+            for (int i = 0; i < M; ++i) qr[i] = Q[i].q * cc.c[0];
+            bessel_j1_vec<M>(qr, jv);
+            sin_qr_vec<M>(Q, cc.c[1], s, x);
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+                float f0 = 0.5f * (jv[i] / qr[i]);
+                float f1 = s[i] / x[i];
+                acc[i] = qt.wt[0] * (f0 * f0) + qt.wt[qt.D - 1] * (f1 * f1);
+            }
+            j0 = 1; j1e = qt.D - 1;
+        }
+        for (int j = j0; j < j1e; ++j) {
+            const float nj = nodes[j], mj = nodes[qt.D + j], wj = qt.wt[j];
+            float A[M], jv[M], s[M], hb[M], f[M];
+#pragma unroll
+            for (int i = 0; i < M; ++i) A[i] = Q[i].q * nj;
+            sin_qr_vec<M>(Q, mj, s, hb);                   // hb = B/2
+            bessel_j1_vec<M>(A, jv);
+#pragma unroll
+            for (int i = 0; i < M; ++i) f[i] = fast_rcp(A[i] * (2.f * hb[i]));
+#pragma unroll
+            for (int i = 0; i < M; ++i) f[i] = jv[i] * s[i] * f[i];          // :74-76
+#pragma unroll
+            for (int i = 0; i < M; ++i) acc[i] += wj * (f[i] * f[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < M; ++i) out[i] = acc[i] * cc.amp;
     }
 };
 
