@@ -52,7 +52,8 @@ template <int MODEL> struct FastOps {
                                                  const QuadTab<float> &qt, const QRep<float> (&Q)[QPT],
                                                  float (&d)[QPT])
     {
-        if constexpr (MODEL == MCSAS_CYLINDERS_ISOTROPIC && QPT > 1) {
+        if constexpr ((MODEL == MCSAS_CYLINDERS_ISOTROPIC || MODEL == MCSAS_ELLIPSOIDS_ISOTROPIC
+                       || MODEL == MCSAS_ELLIPSOIDAL_CORE_SHELL) && QPT > 1) {
             O::template evalV<QPT>(cc, nodes, qt, Q, d);       // q points interleaved in the node loop
             return;
         }

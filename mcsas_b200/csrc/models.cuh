@@ -89,6 +89,44 @@ __device__ __forceinline__ float sph_ff(const QRep<float> &Q, float r)
                 + x2 * 2.5052108e-7f)));
     return x < 1.f ? ser : big;
 }
+// sph_ff(float) for the M q points of a thread, stage by stage (M-way instruction-level
+// parallelism; same arithmetic as the scalar form)
+template <int M> __device__ __forceinline__ void sph_ff_vec(const QRep<float> (&Q)[M], float r, float (&f)[M])
+{
+    float x[M], t[M], fr[M], sn[M], cs[M], x2[M], big[M], ser[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) x[i] = Q[i].q * r;
+#pragma unroll
+    for (int i = 0; i < M; ++i) t[i] = Q[i].th * r;
+#pragma unroll
+    for (int i = 0; i < M; ++i) t[i] = (t[i] + 12582912.f) - 12582912.f;
+#pragma unroll
+    for (int i = 0; i < M; ++i) fr[i] = fmaf(Q[i].th, r, -t[i]);
+#pragma unroll
+    for (int i = 0; i < M; ++i) fr[i] = fmaf(Q[i].tl, r, fr[i]);
+#pragma unroll
+    for (int i = 0; i < M; ++i) fr[i] = fr[i] * 6.2831853071795865f;
+#pragma unroll
+    for (int i = 0; i < M; ++i) sn[i] = __sinf(fr[i]);
+#pragma unroll
+    for (int i = 0; i < M; ++i) cs[i] = __cosf(fr[i]);
+#pragma unroll
+    for (int i = 0; i < M; ++i) x2[i] = x[i] * x[i];
+#pragma unroll
+    for (int i = 0; i < M; ++i) big[i] = fast_rcp(x2[i] * x[i]);
+#pragma unroll
+    for (int i = 0; i < M; ++i) ser[i] = fmaf(x2[i], 2.5052108e-7f, -2.2045855e-5f);
+#pragma unroll
+    for (int i = 0; i < M; ++i) big[i] = fmaf(-x[i], cs[i], sn[i]) * big[i];
+#pragma unroll
+    for (int i = 0; i < M; ++i) ser[i] = fmaf(x2[i], ser[i], 1.1904762e-3f);
+#pragma unroll
+    for (int i = 0; i < M; ++i) ser[i] = fmaf(x2[i], ser[i], -0.033333333f);
+#pragma unroll
+    for (int i = 0; i < M; ++i) ser[i] = fmaf(x2[i], ser[i], 0.33333333f);
+#pragma unroll
+    for (int i = 0; i < M; ++i) f[i] = x[i] < 1.f ? ser[i] : big[i];
+}
 template <class Real> struct SphNorm;
 template <> struct SphNorm<double> { static constexpr double V = 1.0; };
 template <> struct SphNorm<float> { static constexpr double V = 9.0; };
@@ -309,6 +347,28 @@ template <class Real> struct Ops<MCSAS_ELLIPSOIDAL_CORE_SHELL, Real> {
         }
         return acc * cc.amp;                            // sqrt(mean)^2 * w  :90
     }
+    // fp32 production path: the thread's M q points together through the node loop
+    template <int M>
+    __device__ __forceinline__ static void evalV(const Contrib<float> &cc, const float *nodes,
+                                                 const QuadTab<float> &qt, const QRep<float> (&Q)[M],
+                                                 float (&out)[M])
+    {
+        float acc[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) acc[i] = 0.f;
+        for (int j = 0; j < qt.D; ++j) {
+            const float wj = qt.wt[j];
+            float f1[M], f2[M];
+            sph_ff_vec<M>(Q, nodes[j], f1);
+            sph_ff_vec<M>(Q, nodes[qt.D + j], f2);
+#pragma unroll
+            for (int i = 0; i < M; ++i) f1[i] = cc.c[0] * f1[i] + cc.c[1] * f2[i];
+#pragma unroll
+            for (int i = 0; i < M; ++i) acc[i] += wj * (f1[i] * f1[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < M; ++i) out[i] = acc[i] * cc.amp;
+    }
 };
 
 // ----------------------------------------------------- EllipsoidsIsotropic --
@@ -340,6 +400,25 @@ template <class Real> struct Ops<MCSAS_ELLIPSOIDS_ISOTROPIC, Real> {
             acc += qt.wt[j] * (f * f);                  // :71 (weights carry sin(alpha)/D)
         }
         return acc * cc.amp;
+    }
+    // fp32 production path: the thread's M q points together through the node loop
+    template <int M>
+    __device__ __forceinline__ static void evalV(const Contrib<float> &cc, const float *nodes,
+                                                 const QuadTab<float> &qt, const QRep<float> (&Q)[M],
+                                                 float (&out)[M])
+    {
+        float acc[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) acc[i] = 0.f;
+        for (int j = 0; j < qt.D; ++j) {
+            const float wj = qt.wt[j];
+            float f[M];
+            sph_ff_vec<M>(Q, nodes[j], f);
+#pragma unroll
+            for (int i = 0; i < M; ++i) acc[i] += wj * (f[i] * f[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < M; ++i) out[i] = acc[i] * cc.amp;
     }
 };
 

@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 from mcsas_b200 import Engine, synth, FP32, FP64  # noqa: E402
 from mcsas_b200.data import SASData  # noqa: E402
 from mcsas_b200.mcsas import McSAS  # noqa: E402
-from mcsas_b200.models import CylindersIsotropic, Kholodenko  # noqa: E402
+from mcsas_b200.models import CylindersIsotropic, EllipsoidsIsotropic, EllipsoidalCoreShell, Kholodenko  # noqa: E402
 
 NM = 1e-9
 
@@ -66,6 +66,21 @@ def config3(reps):
         m, q, I, sig, reps, max_iter=int(os.environ.get("CYL_MAXIT", "100000")))
 
 
+def config_ell(reps):
+    """Not a BASELINE config: the two other orientation-averaged models on the config-3 q grid."""
+    q = np.logspace(np.log10(0.03), np.log10(3.0), 500) * 1e9
+    rng = np.random.default_rng(6)
+    for cls in (EllipsoidsIsotropic, EllipsoidalCoreShell):
+        m = cls()
+        act = [p for p in m.params() if hasattr(p, "isActive") and p.isActive()]
+        act[0].setActiveRange((1 * NM, 50 * NM))
+        radii = np.clip(rng.normal(8., 1.5, 300), 0.5, None) * NM
+        it = m.calc(q, radii[:, None], 1.0).cumInt
+        I, sig = noisy(it, 5)
+        fit("%s (%s active), 500 q, reference %d-node rule" % (cls.__name__, act[0].name(), 100), m, q, I, sig, reps,
+            max_iter=int(os.environ.get("ELL_MAXIT", "100000")))
+
+
 def config4(reps):
     q = np.logspace(np.log10(0.01), np.log10(10.0), 500) * 1e9
     m = Kholodenko()
@@ -97,6 +112,8 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["3", "5"]
     if "3" in which:
         config3(int(os.environ.get("REPS", "100")))
+    if "ell" in which:
+        config_ell(int(os.environ.get("REPS", "100")))
     if "4" in which:
         config4(int(os.environ.get("REPS", "100")))
     if "5" in which:
