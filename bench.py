@@ -100,6 +100,28 @@ def oracle_cpu_steps_per_s(steps_per_chain, threads):
     return sum(done) / el, el
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout: libraries also write there (NCCL's version banner
+    on the first collective), so everything else is sent to stderr until emit()."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_JSON_FD, data)
+
+
 def host_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -133,10 +155,11 @@ def run_reference(args, rank, world):
             "e2e": {"value": value, "unit": "MC steps/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -289,7 +312,7 @@ def main():
                 "value": v, "unit": "MC steps/s", "cores": threads, "kind": "port",
                 "sample": "%d threads x 1 chain x 150000 MC steps of the same workload (%.1f s); "
                           "oracle/mcsas_oracle.c" % (threads, el)}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
