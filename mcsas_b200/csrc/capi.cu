@@ -697,7 +697,7 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     if (cfg->precision == MCSAS_FP32 && cfg->slice_steps == 0 && !env && a.slice_steps > 0) {
         // auto: a slice is a number of BATCHES (similar duration whether a chain is in its
         // move-rich early phase or late), the step limit stays as an upper bound
-        a.slice_batches = 384;
+        a.slice_batches = 256;                              // (tools/tune.py sched: 256 with backups from <= #SMs/4 live chains)
         if (const char *sb = getenv("MCSAS_B200_SLICE_BATCHES")) { if (atoi(sb) > 0) a.slice_batches = atoi(sb); }
         a.slice_steps = 16384;
     }
@@ -842,8 +842,8 @@ extern "C" int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms)
         }
         // ---- start backups: few chains alive, SMs idle, chain is late in its attempt -------------
         bool new_backups = false;
-        int bdiv = 8;
-        if (const char *bd = getenv("MCSAS_B200_BACKUP_DIV")) bdiv = atoi(bd) > 0 ? atoi(bd) : 8;
+        int bdiv = 4;
+        if (const char *bd = getenv("MCSAS_B200_BACKUP_DIV")) bdiv = atoi(bd) > 0 ? atoi(bd) : 4;
         if (ctx->backups && n_primary > 0 && n_primary * bdiv <= ctx->prop.multiProcessorCount) {
             for (int c = 0; c < NC; ++c) {
                 if (ctx->done[c] || ctx->bak[c] >= 0) continue;

@@ -53,6 +53,13 @@ if __name__ == "__main__":
     if "mixed" in which:
         for m in ("0", "1", "0", "1"):
             run("mixed=%s" % m, {"MCSAS_B200_MIXED": m}, seeds=(1, 2, 4, 7, 9, 11))
+    if "sched" in which:
+        for sb in os.environ.get("SCHED_SB", "256,384,576").split(","):
+            for bd in os.environ.get("SCHED_BD", "4,8,16").split(","):
+                os.environ["MCSAS_B200_SLICE_BATCHES"] = sb
+                os.environ["MCSAS_B200_BACKUP_DIV"] = bd
+                run("slice_batches=%s backup_div=%s" % (sb, bd), {}, seeds=(1, 2, 4, 7, 9, 11))
+        del os.environ["MCSAS_B200_SLICE_BATCHES"], os.environ["MCSAS_B200_BACKUP_DIV"]
     if "grid" in which:
         for c in (1, 2, 4, 8):
             for qpt in (1, 2, 4):
