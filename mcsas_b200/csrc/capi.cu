@@ -517,20 +517,24 @@ static int launch_slice(mcsas_ctx *ctx, int n_live, bool resume)
     int prc = plan_chain(ctx, ctx->nq_max, n_live, &pl);
     if (prc) return prc;
     a.resume = resume ? 1 : 0;
-    int n_up = 0;
+    int n_up = 0, up_f = 2;
     ChainPlan pu = pl;
     const char *mixed_env = getenv("MCSAS_B200_MIXED");
     const bool mixed_on = mixed_env ? atoi(mixed_env) != 0 : true;
     if (mixed_on && ctx->precision == MCSAS_FP32 && ctx->forced_cluster == 0 && !getenv("MCSAS_B200_CLUSTER")
         && a.slice_batches > 0 && pl.cluster < 4 && n_live <= pl.resident) {
         const int spare = ctx->prop.multiProcessorCount - n_live * pl.cluster;
-        n_up = spare / pl.cluster;
+        // up_f: the upgraded chains run on up_f * C CTAs (4: fewer chains, but the few that bound
+        // the time to solution go twice as fast; only from C = 1)
+        if (const char *fe = getenv("MCSAS_B200_MIXED_FACTOR")) up_f = atoi(fe) == 4 ? 4 : 2;
+        if (pl.cluster * up_f > 4) up_f = 2;
+        n_up = spare / ((up_f - 1) * pl.cluster);
         if (n_up > n_live) n_up = n_live;
         if (n_up >= 1) {
-            ctx->forced_cluster = 2 * pl.cluster;
+            ctx->forced_cluster = up_f * pl.cluster;
             prc = plan_chain(ctx, ctx->nq_max, n_up, &pu);
             ctx->forced_cluster = 0;
-            if (prc || pu.cluster != 2 * pl.cluster || pu.resident < n_up) n_up = 0;
+            if (prc || pu.cluster != up_f * pl.cluster || pu.resident < n_up) n_up = 0;
         } else n_up = 0;
     }
     ctx->last_threads = pl.threads; ctx->last_qpt = CHAIN_QPT[pl.layout]; ctx->last_resident = pl.resident;
@@ -554,8 +558,8 @@ static int launch_slice(mcsas_ctx *ctx, int n_live, bool resume)
         ChainArgs u = a;
         u.cluster = pu.cluster;
         u.warps_q = pu.warps_q;
-        u.slice_batches = a.slice_batches * 11 / 8;
-        u.slice_steps = a.slice_steps * 11 / 8;
+        u.slice_batches = up_f == 4 ? a.slice_batches * 2 : a.slice_batches * 11 / 8;
+        u.slice_steps = up_f == 4 ? a.slice_steps * 2 : a.slice_steps * 11 / 8;
         cudaError_t e = CHAIN_FN[a.mp.model_id](ctx->precision, pu.layout, n_up * pu.cluster, pu.threads + extra,
                                                 ctx->smem, ctx->stream, u);
         if (e != cudaSuccess) return fail(ctx, MCSAS_ERR_CUDA, "chain kernel launch (mixed slice): %s", cudaGetErrorString(e));

@@ -53,6 +53,9 @@ if __name__ == "__main__":
     if "mixed" in which:
         for m in ("0", "1", "0", "1"):
             run("mixed=%s" % m, {"MCSAS_B200_MIXED": m}, seeds=(1, 2, 4, 7, 9, 11))
+    if "factor" in which:
+        for f in ("2", "4", "2", "4"):
+            run("mixed factor=%s" % f, {"MCSAS_B200_MIXED_FACTOR": f}, seeds=(1, 2, 4, 7, 9, 11))
     if "sched" in which:
         for sb in os.environ.get("SCHED_SB", "256,384,576").split(","):
             for bd in os.environ.get("SCHED_BD", "4,8,16").split(","):
