@@ -558,8 +558,10 @@ static int launch_slice(mcsas_ctx *ctx, int n_live, bool resume)
         ChainArgs u = a;
         u.cluster = pu.cluster;
         u.warps_q = pu.warps_q;
-        u.slice_batches = up_f == 4 ? a.slice_batches * 2 : a.slice_batches * 11 / 8;
-        u.slice_steps = up_f == 4 ? a.slice_steps * 2 : a.slice_steps * 11 / 8;
+        int num8 = up_f == 4 ? 16 : 11;                      // batches of the upgraded chains, in eighths
+        if (const char *ne = getenv("MCSAS_B200_MIXED_EIGHTHS")) { if (atoi(ne) >= 8) num8 = atoi(ne); }
+        u.slice_batches = a.slice_batches * num8 / 8;
+        u.slice_steps = a.slice_steps * num8 / 8;
         cudaError_t e = CHAIN_FN[a.mp.model_id](ctx->precision, pu.layout, n_up * pu.cluster, pu.threads + extra,
                                                 ctx->smem, ctx->stream, u);
         if (e != cudaSuccess) return fail(ctx, MCSAS_ERR_CUDA, "chain kernel launch (mixed slice): %s", cudaGetErrorString(e));

@@ -56,6 +56,9 @@ if __name__ == "__main__":
     if "factor" in which:
         for f in ("2", "4", "2", "4"):
             run("mixed factor=%s" % f, {"MCSAS_B200_MIXED_FACTOR": f}, seeds=(1, 2, 4, 7, 9, 11))
+    if "eighths" in which:
+        for e in ("9", "10", "11", "12", "13", "14"):
+            run("mixed eighths=%s" % e, {"MCSAS_B200_MIXED_EIGHTHS": e}, seeds=(1, 2, 4, 7, 9, 11))
     if "sched" in which:
         for sb in os.environ.get("SCHED_SB", "256,384,576").split(","):
             for bd in os.environ.get("SCHED_BD", "4,8,16").split(","):
