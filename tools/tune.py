@@ -59,6 +59,9 @@ if __name__ == "__main__":
     if "eighths" in which:
         for e in ("9", "10", "11", "12", "13", "14"):
             run("mixed eighths=%s" % e, {"MCSAS_B200_MIXED_EIGHTHS": e}, seeds=(1, 2, 4, 7, 9, 11))
+    if "gram" in which:
+        for g in ("1", "0"):
+            run("gram=%s" % g, {"MCSAS_B200_GRAM": g}, seeds=(1, 2, 4, 7, 9, 11))
     if "sched" in which:
         for sb in os.environ.get("SCHED_SB", "256,384,576").split(","):
             for bd in os.environ.get("SCHED_BD", "4,8,16").split(","):
