@@ -67,7 +67,7 @@ struct mcsas_ctx {
     int *d_att = nullptr;
     unsigned char *d_tacc = nullptr;
     double *d_tchi = nullptr;
-    size_t out_cap = 0, trace_cap = 0;
+    size_t rset_cap = 0, fit_cap = 0, slot_cap = 0, trace_cap = 0;   // elements allocated per output buffer
     int *h_stop = nullptr;        // mapped pinned host int
     int *d_stop = nullptr;
     // time-sliced launch state
@@ -176,6 +176,7 @@ extern "C" int mcsas_upload_datasets(mcsas_ctx *ctx, int n_sets, const int *nq, 
                                      const double *intensity, const double *sigma)
 {
     if (!ctx) return MCSAS_ERR_ARG;
+    if (ctx->running) return fail(ctx, MCSAS_ERR_STATE, "upload_datasets: a run is in flight (call mcsas_wait first)");
     if (n_sets <= 0 || !nq || !q || !intensity || !sigma)
         return fail(ctx, MCSAS_ERR_ARG, "upload_datasets: null/empty input");
     CK(cudaSetDevice(ctx->device));
@@ -202,7 +203,10 @@ extern "C" int mcsas_upload_datasets(mcsas_ctx *ctx, int n_sets, const int *nq, 
             if (q[src + i] > qmax) qmax = q[src + i];
             if (q[src + i] > 0. && q[src + i] < qmin) qmin = q[src + i];
             if (fabs(intensity[src + i]) > imax) imax = fabs(intensity[src + i]);
-            if (!std::isfinite(q[src + i]) || !std::isfinite(intensity[src + i]) || !std::isfinite(sigma[src + i]))
+            // sigma = +inf is what DataObj._prepareUncertainty (dataobj.py:224-226) gives a point with an
+            // invalid uncertainty: weight 0 in the fit, the point still counts in chi^2 / nq
+            const bool sig_ok = std::isfinite(sigma[src + i]) || (std::isinf(sigma[src + i]) && sigma[src + i] > 0.);
+            if (!std::isfinite(q[src + i]) || !std::isfinite(intensity[src + i]) || !sig_ok)
                 return fail(ctx, MCSAS_ERR_ARG, "dataset %d: non-finite value at point %d", s, i);
         }
         sets[s].q_max = qmax;
@@ -260,6 +264,7 @@ extern "C" int mcsas_set_model(mcsas_ctx *ctx, int model_id, const double *param
                                int quad_nodes)
 {
     if (!ctx) return MCSAS_ERR_ARG;
+    if (ctx->running) return fail(ctx, MCSAS_ERR_STATE, "set_model: a run is in flight (call mcsas_wait first)");
     if (model_id < 0 || model_id >= MCSAS_N_MODELS) return fail(ctx, MCSAS_ERR_ARG, "unknown model id %d", model_id);
     if (n_params < 1 || n_params > MCSAS_MAX_PARAMS || !params) return fail(ctx, MCSAS_ERR_ARG, "bad n_params %d", n_params);
     if (n_active < 0 || n_active > MCSAS_MAX_ACTIVE) return fail(ctx, MCSAS_ERR_ARG, "n_active %d outside [0,%d]", n_active, MCSAS_MAX_ACTIVE);
@@ -321,6 +326,7 @@ extern "C" int mcsas_set_smearing(mcsas_ctx *ctx, int n_points, const double *q_
                                   int two_d_coll)
 {
     if (!ctx) return MCSAS_ERR_ARG;
+    if (ctx->running) return fail(ctx, MCSAS_ERR_STATE, "set_smearing: a run is in flight (call mcsas_wait first)");
     if (n_points == 0) { memset(&ctx->smear, 0, sizeof ctx->smear); ctx->have_run = false; return MCSAS_OK; }
     if (n_points < 2 || n_points > MCSAS_MAX_SMEAR || !q_offset || !weights)
         return fail(ctx, MCSAS_ERR_ARG, "set_smearing: n_points %d outside [2,%d] or null profile", n_points, MCSAS_MAX_SMEAR);
@@ -464,8 +470,9 @@ static int plan_chain_fp32(mcsas_ctx *ctx, int nq, int n_live, ChainPlan *out)
     if (forced_c > MAX_CLUSTER) forced_c = MAX_CLUSTER;
     ChainPlan best = {0, 0, 0, 0, 0};
     // preference order of cluster sizes: the planned one first, then smaller, then larger
-    int want_c = 1;
-    while (want_c < 4 && (long long)n_live * want_c * 2 <= sms) want_c *= 2;
+    int want_c = 1, max_c = 4;
+    if ((env = getenv("MCSAS_B200_MAXC")) && atoi(env) > 0) max_c = atoi(env);
+    while (want_c < max_c && (long long)n_live * want_c * 2 <= sms) want_c *= 2;
     int order[8], no = 0;
     if (forced_c > 0) order[no++] = forced_c;
     else {
@@ -654,15 +661,22 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     }
     // outputs
     const int n_slots = 2 * n_chains;
-    size_t need_out = (size_t)n_slots * ((size_t)N * P + ctx->nq_max + 8);
-    if (need_out > ctx->out_cap || n_chains > ctx->n_chains || (size_t)N * P > (size_t)ctx->n_contribs * ctx->n_active) {
+    // every output buffer has its own capacity: a context may be reused with more q points but
+    // fewer contributions (or the reverse) between fits
+    if ((size_t)n_slots * N * P > ctx->rset_cap) {
         CK(regrow(&ctx->d_rset, (size_t)n_slots * N * P));
+        ctx->rset_cap = (size_t)n_slots * N * P;
+    }
+    if ((size_t)n_slots * ctx->nq_max > ctx->fit_cap) {
         CK(regrow(&ctx->d_fit, (size_t)n_slots * ctx->nq_max));
+        ctx->fit_cap = (size_t)n_slots * ctx->nq_max;
+    }
+    if ((size_t)n_slots > ctx->slot_cap) {
         CK(regrow(&ctx->d_scal, (size_t)n_slots * 5));
         CK(regrow(&ctx->d_cnt, (size_t)n_slots * 4));
         CK(regrow(&ctx->d_att, (size_t)n_slots * 2));
         CK(regrow(&ctx->d_ids, (size_t)n_slots));
-        ctx->out_cap = need_out;
+        ctx->slot_cap = (size_t)n_slots;
     }
     CK(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(long long) * (size_t)n_slots * 4, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_scal, 0, sizeof(double) * (size_t)n_slots * 5, ctx->stream));

@@ -283,7 +283,7 @@ struct FastDec {
     int kstar;
     int wd;
     int accmask;
-    int pad_;
+    int used;                    // Gram batch: steps consumed (< FGRP when the criterion is reached inside it)
     double a, b, conval;
 };
 
@@ -992,7 +992,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     }
                 }
                 if (a.prof) pd[2] = clock64();
-                int ks = -1, accmask = 0;
+                int ks = -1, accmask = 0, gused = Kb;
                 double ca = a0, cb = b0, cc = conval;
                 if (!gram) {
                     double chi = 0., an = 0., bn = 0., e1, e2, rss;
@@ -1035,6 +1035,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     }
                     __syncwarp();
                     int pos = 0;
+                    gused = Kb;
                     double g1 = s1, g2 = s2, g3 = s3, g4 = s4;      // fp64 copies updated per accepted move
                     for (int it = 0; it <= FGRP && !wd; ++it) {
                         double rss = 0., an = 0., bn = 0., e1 = 0., e2 = 0.;
@@ -1064,6 +1065,9 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                         ca = ai; cb = bi; cc = ri * L.inv_nq;
                         accmask |= 1 << i;
                         pos = i + 1;
+                        // the reference tests the criterion before EVERY step (mcsas.py:354-357):
+                        // the steps behind the move that reaches it are not made
+                        if (cc <= a.conv_crit) { gused = i + 1; break; }
                     }
                     ks = accmask ? 0 : -1;
                 }
@@ -1071,6 +1075,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                 if (lane == 0) {
                     s_dec->kstar = ks;
                     s_dec->accmask = accmask;
+                    s_dec->used = gused;
                     s_dec->wd = wd ? 2 : 0;
                     s_dec->a = ca;                               // centre of the state after this batch
                     s_dec->b = cb;
@@ -1086,7 +1091,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             if (s_dec->wd == 2) { status = -2; break; }
             const int kstar = s_dec->kstar;
             const int accmask = s_dec->accmask;
-            const int used = gram ? Kb : (kstar >= 0 ? kstar + 1 : Kb);
+            const int used = gram ? s_dec->used : (kstar >= 0 ? kstar + 1 : Kb);
             conval = s_dec->conval;
             if (a.trace_accept && rank == 0) {
                 for (int k = tid; k < used; k += T) {

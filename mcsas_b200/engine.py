@@ -122,7 +122,9 @@ class Engine(object):
                          int(bool(record_trace)), int(first_chain), int(cluster_size),
                          int(slice_steps))
 
-    def run_async(self, cfg, stream=None):
+    def run_async(self, cfg, stream=None, stop_flag=None):
+        """stop_flag: a ctypes.c_int the caller owns (kept alive until wait()); non-zero stops the
+        fit at its next time-slice boundary (McSAS.stop)."""
         stride = 0
         sp = None
         if stream is not None:
@@ -132,7 +134,9 @@ class Engine(object):
             stride = stream.shape[1]
             sp = _dp(stream)
             self._stream_keepalive = stream
-        self._check(self._L.mcsas_run_async(self._ctx, C.byref(cfg), sp, C.c_longlong(stride), None),
+        self._stop_keepalive = stop_flag
+        fp = C.cast(C.pointer(stop_flag), C.POINTER(C.c_int)) if stop_flag is not None else None
+        self._check(self._L.mcsas_run_async(self._ctx, C.byref(cfg), sp, C.c_longlong(stride), fp),
                     "run_async")
         self._last = cfg
 

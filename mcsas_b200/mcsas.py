@@ -12,6 +12,7 @@ Differences that are deliberate and documented in DESIGN.md:
     the deterministic parity mode uploads a recorded stream (`proposalStream`);
   * scale/background is the closed-form weighted LSQ that scipy's leastsq converges to.
 """
+import ctypes
 import logging
 import time
 
@@ -49,7 +50,6 @@ class McSAS(object):
     data = None
     model = None
     result = None
-    stop = False
 
     @classmethod
     def factory(cls):
@@ -67,13 +67,23 @@ class McSAS(object):
         self.specMax = specMax
         self.proposalStream = None      # deterministic parity mode: [numReps][stream] in [0,1)
         self.result = []
-        self.stop = False
+        # McSAS.stop (mcsas.py:357, 238-243): a host int the kernel scheduler polls at every
+        # time-slice boundary; it may be set from another thread / a callback while a fit runs
+        self._stopFlag = ctypes.c_int(0)
         self.lastKernelMs = 0.0
         self.details = None
         self._engine = None
 
     def params(self):
         return self._params
+
+    @property
+    def stop(self):
+        return bool(self._stopFlag.value)
+
+    @stop.setter
+    def stop(self, value):
+        self._stopFlag.value = 1 if value else 0
 
     @property
     def engine(self):
@@ -136,9 +146,7 @@ class McSAS(object):
         self.model.configureEngine(eng)
         self._configureSmearing(eng)
         cfg = self._config(numContribs, numReps, record_trace)
-        eng.run_async(cfg, stream)
-        if self.stop:
-            eng.request_stop()
+        eng.run_async(cfg, stream, stop_flag=self._stopFlag)
         self.lastKernelMs = eng.wait()
         return eng.fetch()
 
@@ -161,7 +169,11 @@ class McSAS(object):
         conval = out["conval"][0]
         failed = conval > float(self.convergenceCriterion())
         self.details = out
-        if failed.any():
+        if self.stop:                                         # mcsas.py:238-243
+            logging.warning("Stop button pressed, exiting...")
+            if not self.showIncomplete():
+                return
+        elif failed.any():
             logging.warning("Could not reach optimization criterion within {0} attempts "
                             "({1} of {2} repetitions), exiting..."
                             .format(int(self.maxRetries()) + 2, int(failed.sum()), numReps))

@@ -194,8 +194,12 @@ def test_missing_device_or_bad_args_fail_loudly():
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["sphere_small", "sphere_nobg", "sphere_posbg", "sphcs_small", "cyl_small",
-                                  "gauss_small"])
+# all 8 models and every settings variant (findBackground off, positiveBackground, startFromMinimum)
+TRACK_CASES = ["sphere_small", "sphere_nobg", "sphere_posbg", "sphere_startmin", "lma_small", "sphcs_small",
+               "ellcs_small", "elliso_small", "cyl_small", "gauss_small", "kho_small"]
+
+
+@pytest.mark.parametrize("name", TRACK_CASES)
 @pytest.mark.parametrize("spec_max,cluster", [(1, 1), (32, 1), (64, 1), (32, 2), (8, 4)])
 def test_fp32_chain_tracks_fp64_chain(name, spec_max, cluster):
     """Production kernel (fp32 residual-delta sums, Gram batches, cached rows) against the
@@ -204,7 +208,9 @@ def test_fp32_chain_tracks_fp64_chain(name, spec_max, cluster):
     from mcsas_b200 import Engine
     g = common.load_chain(name)
     om = common.oracle_model(g)
-    max_iter = min(int(g["max_iter"]), 1500)
+    # the goldens' lengths are set by the reference's speed (Kholodenko: 40 steps); the Philox
+    # chains of both kernels can run longer on the same data
+    max_iter = min(max(int(g["max_iter"]), 400), 1500)
 
     def run(prec, spec, cl):
         eng = gpu_common.engine_for(om, [(g["q"], g["I"], g["sigma"])])
@@ -212,6 +218,7 @@ def test_fp32_chain_tracks_fp64_chain(name, spec_max, cluster):
                                  max_iter=max_iter, max_retries=-1, comp_exp=float(g["comp_exp"]),
                                  find_background=g["find_background"],
                                  positive_background=g["positive_background"],
+                                 start_from_minimum=g["start_from_minimum"],
                                  precision=prec, seed=424242, record_trace=True, spec_max=spec,
                                  cluster_size=cl)
         eng.run(cfg)
@@ -233,6 +240,45 @@ def test_fp32_chain_tracks_fp64_chain(name, spec_max, cluster):
         # gauss_small: 0.01 % uncertainties amplify the ~3e-7 error of the fp32 form factors
         np.testing.assert_allclose(chi[:first], rchi[:first], rtol=1e-2 if name == "gauss_small" else 1e-4)
         assert abs(out["conval0"][0, r] / ref["conval0"][0, r] - 1) < 1e-5
+
+
+@pytest.mark.parametrize("name,crit", [("sphere_small", 3000.), ("sphere_small", 800.), ("sphere_small", 150.),
+                                       ("sphcs_small", 1000.), ("lma_small", 400.), ("gauss_small", 300.),
+                                       ("gauss_small", 20.), ("gauss_small", 1.0), ("cyl_small", 900.)])
+@pytest.mark.parametrize("spec_max", [8, 64])
+def test_chain_stops_at_the_step_that_reaches_the_criterion(name, crit, spec_max):
+    """mcsas.py:354-357 tests `conval > convergenceCriterion` before EVERY step.  With a loose
+    criterion the chains converge while moves are still frequent, i.e. inside a Gram batch of the
+    production kernel (8 steps, several accepted): the steps behind the move that reaches the
+    criterion must not be made.  Same Philox stream in the fp64 parity kernel: numIter, numMoves,
+    the accept sequence and the contribution set are equal -- nothing is truncated."""
+    from mcsas_b200 import Engine
+    g = common.load_chain(name)
+    om = common.oracle_model(g)
+    R = 8
+    outs = []
+    for prec in (FP64, FP32):
+        eng = gpu_common.engine_for(om, [(g["q"], g["I"], g["sigma"])])
+        cfg = Engine.make_config(n_contribs=g["N"], n_reps=R, conv_crit=crit, max_iter=3000, max_retries=-1,
+                                 comp_exp=float(g["comp_exp"]), find_background=g["find_background"],
+                                 precision=prec, seed=90210, record_trace=True,
+                                 spec_max=spec_max if prec == FP32 else 32, cluster_size=1)
+        eng.run(cfg)
+        out = eng.fetch()
+        out["tr"] = [eng.fetch_trace(r, 3000)[0] for r in range(R)]
+        eng.close()
+        outs.append(out)
+    a, b = outs
+    assert (a["conval"] <= crit).all() and (a["num_iter"] < 3000).all()       # all converge early
+    np.testing.assert_array_equal(b["num_iter"], a["num_iter"])
+    np.testing.assert_array_equal(b["num_moves"], a["num_moves"])
+    for r in range(R):
+        n = int(a["num_iter"][0, r])
+        np.testing.assert_array_equal(b["tr"][r][:n], a["tr"][r][:n])
+        assert a["tr"][r][n - 1] == 1                      # the last step made is the converging move
+    np.testing.assert_array_equal(b["contribs"], a["contribs"])
+    # gauss_small: 0.01 % uncertainties amplify the ~3e-7 error of the fp32 form factors
+    np.testing.assert_allclose(b["conval"], a["conval"], rtol=1e-2 if name == "gauss_small" else 1e-4)
 
 
 def test_many_chains_run_in_waves_and_do_not_depend_on_packing():
