@@ -28,7 +28,7 @@ extern "C" {
 #define MCSAS_MAX_PARAMS 16
 #define MCSAS_MAX_ACTIVE 4
 #define MCSAS_MAX_NQ 4096
-#define MCSAS_MAX_SPEC 32
+#define MCSAS_MAX_SPEC 32        /* speculative proposals per batch, fp64 parity kernel (fp32 production kernel: 64) */
 
 typedef struct mcsas_ctx mcsas_ctx;
 
@@ -79,20 +79,36 @@ typedef struct mcsas_run_config {
     int n_reps;                /* numReps: chains per dataset */
     double conv_crit;          /* convergenceCriterion */
     long long max_iter;        /* maxIterations */
-    int max_retries;           /* maxRetries: up to max_retries+2 attempts (mcsas.py:220-246) */
+    int max_retries;           /* maxRetries: up to max_retries+1 attempts (mcsas.py:220-246); < 0: one attempt */
     double comp_exp;           /* compensationExponent */
     int find_background;       /* findBackground */
     int positive_background;   /* positiveBackground */
     int start_from_minimum;    /* startFromMinimum */
     int precision;             /* mcsas_precision */
     unsigned long long seed;   /* Philox key (production proposals) */
-    int spec_max;              /* max speculative proposals per batch, 0 = default (32), 1 = none */
+    int spec_max;              /* max speculative proposals per batch: 0 = default (fp64 kernel 32, fp32 kernel 64),
+                                  1 = none (sequential).  The fp64 kernel's results do not depend on it; in the
+                                  fp32 kernel it decides which batches are Gram batches (different rounding) */
     int record_trace;          /* 1: keep per-step accept flag + chi-squared (parity tests) */
     int first_chain;           /* global index of this context's first chain (multi-GPU partition) */
     int cluster_size;          /* CTAs per chain (q split over a thread-block cluster): 0 = auto, 1/2/4/8 */
     long long slice_steps;     /* MC steps per chain and launch before the live chains are re-packed:
-                                  0 = auto, -1 = one launch */
+                                  0 = auto (fp32 kernel: a time budget per launch), -1 = one launch */
 } mcsas_run_config;
+
+/* Scheduler / kernel knobs for experiments (tools/, tests): no counterpart in the reference and no
+ * influence on a chain's result (the fp32 kernel's results are independent of cluster size and time
+ * slicing).  All 0 = defaults. */
+typedef struct mcsas_tuning {
+    int max_cluster;   /* largest cluster the scheduler may give a chain: 0 = default (8), 1, 2, 4, 8 */
+    int slice_us;      /* time budget of one launch per chain in microseconds, 0 = default */
+    int backups;       /* speculative next attempts on idle SMs: 0 = default (on), -1 = off */
+    int backup_div;    /* start them when live chains * backup_div <= SMs, 0 = default (4) */
+    int gram;          /* Gram batches: 0 = default (on), -1 = off */
+    int qpt;           /* force q points per thread (1, 2, 4), 0 = auto */
+    int profile;       /* 1: in-kernel phase cycle counters, printed to stderr by mcsas_wait */
+    int verbose;       /* 1: one stderr line per time slice */
+} mcsas_tuning;
 
 /* -- context ------------------------------------------------------------- */
 int mcsas_ctx_create(int device, mcsas_ctx **out);
@@ -144,7 +160,9 @@ int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
 int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms);
 /* Ask a running fit to stop at its next time-slice boundary (McSAS.stop). */
 int mcsas_request_stop(mcsas_ctx *ctx);
-/* Facts about the last run: kernel launches (time slices), last cluster size, summed kernel ms. */
+/* Experiment knobs (NULL: back to the defaults). */
+int mcsas_set_tuning(mcsas_ctx *ctx, const mcsas_tuning *tuning);
+/* Facts about the last run: kernel launches, last cluster size, summed kernel ms. */
 int mcsas_run_info(mcsas_ctx *ctx, int *n_launches, int *last_cluster, float *kernel_ms);
 /* Scheduler facts of the last run: backup attempts (the next retry of a late chain, mcsas.py:220-246,
  * started ahead of time on idle SMs) started and promoted to the chain's current attempt. */

@@ -18,7 +18,7 @@ EXPORTS = [
     "mcsas_ctx_create", "mcsas_ctx_destroy", "mcsas_last_error", "mcsas_device_info",
     "mcsas_upload_datasets", "mcsas_set_model", "mcsas_set_smearing", "mcsas_eval", "mcsas_run", "mcsas_run_async",
     "mcsas_wait", "mcsas_request_stop", "mcsas_run_info", "mcsas_scheduler_info", "mcsas_fetch", "mcsas_fetch_trace", "mcsas_fractions",
-    "mcsas_measure_peaks",
+    "mcsas_measure_peaks", "mcsas_set_tuning",
 ]
 
 
@@ -34,6 +34,13 @@ class RunConfig(C.Structure):
                 ("start_from_minimum", C.c_int), ("precision", C.c_int),
                 ("seed", C.c_ulonglong), ("spec_max", C.c_int), ("record_trace", C.c_int),
                 ("first_chain", C.c_int), ("cluster_size", C.c_int), ("slice_steps", C.c_longlong)]
+
+
+class Tuning(C.Structure):
+    """struct mcsas_tuning (experiment knobs, all 0 = defaults)"""
+    _fields_ = [("max_cluster", C.c_int), ("slice_us", C.c_int), ("backups", C.c_int),
+                ("backup_div", C.c_int), ("gram", C.c_int), ("qpt", C.c_int), ("profile", C.c_int),
+                ("verbose", C.c_int)]
 
 
 _lib = None
@@ -72,5 +79,6 @@ def lib():
     L.mcsas_fetch_trace.argtypes = [vp, C.c_int, C.POINTER(C.c_ubyte), dp, C.c_longlong]
     L.mcsas_fractions.argtypes = [vp, C.POINTER(RunConfig)] + [dp] * 11
     L.mcsas_measure_peaks.argtypes = [vp, dp, dp]
+    L.mcsas_set_tuning.argtypes = [vp, C.POINTER(Tuning)]
     _lib = L
     return L

@@ -32,8 +32,10 @@ static const eval_launch_fn EVAL_FN[MCSAS_N_MODELS] = {
 
 struct mcsas_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr, stream2 = nullptr;     // stream2: the larger-cluster half of a mixed slice
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_begin = nullptr, ev_mix = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaStream_t side[3] = {nullptr, nullptr, nullptr};   // concurrent launches of a slice, one per cluster size
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_begin = nullptr;
+    cudaEvent_t ev_side[3] = {nullptr, nullptr, nullptr};
     float span_ms = 0.f;          // first launch start -> last slice end (host gaps between slices included)
     cudaDeviceProp prop;
     std::string err;
@@ -62,9 +64,15 @@ struct mcsas_ctx {
     bool have_run = false, have_trace = false, running = false;
     double *d_stream = nullptr;
     size_t stream_cap = 0;
-    double *d_rset = nullptr, *d_fit = nullptr, *d_scal = nullptr;   // scal: 5 doubles per chain
-    long long *d_cnt = nullptr;                                       // 3 per chain
-    int *d_att = nullptr;
+    double *d_rset = nullptr, *d_fit = nullptr, *d_scal = nullptr;   // scal: SCAL_N doubles per slot
+    double *d_ftsave = nullptr;                                       // fp64 master intensity of unfinished chains
+    long long *d_cnt = nullptr;                                       // 4 per slot
+    int *d_att = nullptr;                                             // ATT_N ints per slot: attempts | status | batch size
+    // pinned mirrors read back once per time slice (one async copy each, one synchronisation)
+    int *h_att = nullptr;
+    long long *h_cnt = nullptr;
+    double *h_cv = nullptr;
+    size_t pin_cap = 0;
     unsigned char *d_tacc = nullptr;
     double *d_tchi = nullptr;
     size_t rset_cap = 0, fit_cap = 0, slot_cap = 0, trace_cap = 0;   // elements allocated per output buffer
@@ -81,7 +89,10 @@ struct mcsas_ctx {
     float *d_cache = nullptr;
     int *d_cache_lock = nullptr;
     size_t cache_cap = 0;
-    int n_live = 0, n_launches = 0, last_up = 0, last_cluster = 1, last_threads = 0, last_qpt = 0, last_resident = 0;
+    int n_live = 0, n_launches = 0, n_slices = 0, last_cluster = 1, last_threads = 0, last_qpt = 0, last_resident = 0;
+    int last_sizes[4] = {0, 0, 0, 0};   // chains launched with cluster size 1, 2, 4, 8 in the last slice
+    int max_cluster = 8, forced_qpt = 0;
+    mcsas_tuning tune;                  // experiment knobs (mcsas_set_tuning), all 0 = defaults
     float kernel_ms = 0.f;
     volatile int *stop_flag = nullptr;
     std::map<long long, int> occ_cache;
@@ -98,6 +109,8 @@ static int fail(mcsas_ctx *ctx, int code, const char *fmt, ...)
     return code;
 }
 
+#define SCAL_N 9
+#define ATT_N 3
 #define CK(call)                                                                             \
     do {                                                                                     \
         cudaError_t e_ = (call);                                                             \
@@ -123,12 +136,17 @@ extern "C" int mcsas_ctx_create(int device, mcsas_ctx **out)
     mcsas_ctx *ctx = new mcsas_ctx();
     ctx->device = device;
     memset(&ctx->smear, 0, sizeof ctx->smear);
+    memset(&ctx->tune, 0, sizeof ctx->tune);
     if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess
         || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess
         || cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess
         || cudaEventCreate(&ctx->ev_begin) != cudaSuccess
-        || cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess
-        || cudaEventCreateWithFlags(&ctx->ev_mix, cudaEventDisableTiming) != cudaSuccess
+        || cudaStreamCreateWithFlags(&ctx->side[0], cudaStreamNonBlocking) != cudaSuccess
+        || cudaStreamCreateWithFlags(&ctx->side[1], cudaStreamNonBlocking) != cudaSuccess
+        || cudaStreamCreateWithFlags(&ctx->side[2], cudaStreamNonBlocking) != cudaSuccess
+        || cudaEventCreateWithFlags(&ctx->ev_side[0], cudaEventDisableTiming) != cudaSuccess
+        || cudaEventCreateWithFlags(&ctx->ev_side[1], cudaEventDisableTiming) != cudaSuccess
+        || cudaEventCreateWithFlags(&ctx->ev_side[2], cudaEventDisableTiming) != cudaSuccess
         || cudaHostAlloc((void **)&ctx->h_stop, sizeof(int), cudaHostAllocMapped) != cudaSuccess
         || cudaHostGetDevicePointer((void **)&ctx->d_stop, ctx->h_stop, 0) != cudaSuccess) {
         g_create_err = std::string("CUDA context setup failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -147,10 +165,12 @@ extern "C" void mcsas_ctx_destroy(mcsas_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_sets); cudaFree(ctx->d_data); cudaFree(ctx->d_quad); cudaFree(ctx->d_stream);
     cudaFree(ctx->d_rset); cudaFree(ctx->d_fit); cudaFree(ctx->d_scal); cudaFree(ctx->d_cnt);
+    cudaFree(ctx->d_ftsave); cudaFreeHost(ctx->h_att); cudaFreeHost(ctx->h_cnt); cudaFreeHost(ctx->h_cv);
     cudaFree(ctx->d_att); cudaFree(ctx->d_tacc); cudaFree(ctx->d_tchi); cudaFree(ctx->d_ids); cudaFree(ctx->d_prof); cudaFree(ctx->d_cache); cudaFree(ctx->d_cache_lock);
     cudaFreeHost(ctx->h_stop);
-    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_begin); cudaEventDestroy(ctx->ev_mix);
-    cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->stream2);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_begin);
+    for (int i = 0; i < 3; ++i) { cudaEventDestroy(ctx->ev_side[i]); cudaStreamDestroy(ctx->side[i]); }
+    cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
@@ -415,11 +435,7 @@ static int query_resident(mcsas_ctx *ctx, int c, int layout, int block_threads, 
 static int plan_chain_fp64(mcsas_ctx *ctx, int nq, int n_live, ChainPlan *out)
 {
     const int sms = ctx->prop.multiProcessorCount;
-    int forced_c = ctx->forced_cluster, forced_t = 0, forced_q = 0;
-    const char *env;
-    if ((env = getenv("MCSAS_B200_CLUSTER")) && atoi(env) > 0) forced_c = atoi(env);
-    if ((env = getenv("MCSAS_B200_T")) && atoi(env) > 0) forced_t = atoi(env);
-    if ((env = getenv("MCSAS_B200_QPT")) && atoi(env) > 0) forced_q = atoi(env);
+    const int forced_c = ctx->forced_cluster, forced_t = 0, forced_q = ctx->forced_qpt;
     ChainPlan best = {0, 0, 0, 0, 0};
     double best_score = -1.;
     for (int c = 1; c <= MAX_CLUSTER; c *= 2) {
@@ -454,144 +470,155 @@ static int plan_chain_fp64(mcsas_ctx *ctx, int nq, int n_live, ChainPlan *out)
     return MCSAS_OK;
 }
 
-// Layout of the fp32 production kernel: cluster size C (q split) x q points per thread
-// (1,2,4) x proposal groups PS (1,2,4); eval threads = warps_q * PS * 32.
+// Layout of the fp32 production kernel for ONE cluster size C (q split over the cluster) at
+// q points per thread QPT = 4 (fewer only when forced): proposal groups PS = spare warps of the
+// 8-warp CTA; eval threads = warps_q * PS * 32.
 // Measured on B200 (tools/tune.py fast, nq = 1000): 8 eval warps with 4 q points per thread
-// are the sweet spot at every cluster size; a cluster pays for its per-batch exchange only
-// when its CTAs get SMs of their own, so C = largest of {1,2,4} with n_live * C <= #SMs.
-static int plan_chain_fp32(mcsas_ctx *ctx, int nq, int n_live, ChainPlan *out)
+// are the sweet spot at every cluster size.
+static bool plan_fast_layout(mcsas_ctx *ctx, int nq, int c, ChainPlan *out)
 {
-    const int sms = ctx->prop.multiProcessorCount;
-    int forced_c = ctx->forced_cluster, forced_q = 0, forced_ps = 0;
-    const char *env;
-    if ((env = getenv("MCSAS_B200_CLUSTER")) && atoi(env) > 0) forced_c = atoi(env);
-    if ((env = getenv("MCSAS_B200_QPT")) && atoi(env) > 0) forced_q = atoi(env);
-    if ((env = getenv("MCSAS_B200_PS")) && atoi(env) > 0) forced_ps = atoi(env);
-    if (forced_c > MAX_CLUSTER) forced_c = MAX_CLUSTER;
-    ChainPlan best = {0, 0, 0, 0, 0};
-    // preference order of cluster sizes: the planned one first, then smaller, then larger
-    int want_c = 1, max_c = 4;
-    if ((env = getenv("MCSAS_B200_MAXC")) && atoi(env) > 0) max_c = atoi(env);
-    while (want_c < max_c && (long long)n_live * want_c * 2 <= sms) want_c *= 2;
-    int order[8], no = 0;
-    if (forced_c > 0) order[no++] = forced_c;
-    else {
-        for (int c = want_c; c >= 1; c /= 2) order[no++] = c;
-        for (int c = want_c * 2; c <= MAX_CLUSTER; c *= 2) order[no++] = c;
-    }
     const int grp_of[3] = {4, 8, 8};                        // proposals per chunk of layout QPT = 1,2,4
-    for (int oi = 0; oi < no && best.cluster == 0; ++oi) {
-        const int c = order[oi];
-        const int n = (nq + c - 1) / c;
-        for (int l = N_CHAIN_LAYOUTS - 1; l >= 0 && best.cluster == 0; --l) {       // QPT = 4 first
-            const int qpt = CHAIN_QPT[l];
-            if (forced_q > 0 && qpt != forced_q) continue;
-            const int wq = (n + 32 * qpt - 1) / (32 * qpt);
-            if (wq * 32 > FAST_MAX_EVAL_THREADS[l]) continue;
-            int ps = 1;
-            while (ps < 4 && wq * ps * 2 <= 8 && wq * ps * 2 * 32 <= FAST_MAX_EVAL_THREADS[l]
-                   && ps * 2 * grp_of[l] <= ctx->args.spec_max) ps *= 2;
-            if (forced_ps > 0) ps = forced_ps;
-            const int threads = wq * ps * 32;
-            if (threads > FAST_MAX_EVAL_THREADS[l] || threads / 32 > FAST_MAX_WARPS) continue;
-            int resident = 0;
-            query_resident(ctx, c, l, threads, &resident);
-            if (resident < 1) continue;                                            // more chains than fit: waves
-            best.cluster = c; best.layout = l; best.threads = threads; best.resident = resident; best.warps_q = wq;
-        }
+    const int n = (nq + c - 1) / c;
+    for (int l = N_CHAIN_LAYOUTS - 1; l >= 0; --l) {        // QPT = 4 first
+        const int qpt = CHAIN_QPT[l];
+        if (ctx->forced_qpt > 0 && qpt != ctx->forced_qpt) continue;
+        const int wq = (n + 32 * qpt - 1) / (32 * qpt);
+        if (wq * 32 > FAST_MAX_EVAL_THREADS[l]) continue;
+        int ps = 1;
+        while (wq * ps * 2 <= 8 && wq * ps * 2 * 32 <= FAST_MAX_EVAL_THREADS[l]
+               && ps * 2 * grp_of[l] <= ctx->args.spec_max) ps *= 2;
+        const int threads = wq * ps * 32;
+        if (threads > FAST_MAX_EVAL_THREADS[l] || threads / 32 > FAST_MAX_WARPS) continue;
+        if (c * wq > ctx->args.gw_cap) continue;
+        int resident = 0;
+        query_resident(ctx, c, l, threads, &resident);
+        if (resident < 1) continue;
+        out->cluster = c; out->layout = l; out->threads = threads; out->resident = resident; out->warps_q = wq;
+        return true;
     }
-    if (best.cluster == 0) return fail(ctx, MCSAS_ERR_ARG, "no launchable fp32 chain layout for nq=%d", nq);
-    *out = best;
+    return false;
+}
+
+static int launch_one_size(mcsas_ctx *ctx, const ChainArgs &base, const ChainPlan &pl, const int *d_ids, int n,
+                           cudaStream_t st)
+{
+    ChainArgs a = base;
+    a.cluster = pl.cluster;
+    a.warps_q = pl.warps_q;
+    a.chain_ids = d_ids;
+    const int extra = ctx->precision == MCSAS_FP64 ? 32 : 0;                          // fp64: + producer warp
+    cudaError_t e = CHAIN_FN[a.mp.model_id](ctx->precision, pl.layout, n * pl.cluster, pl.threads + extra,
+                                            ctx->smem, st, a);
+    if (e != cudaSuccess) return fail(ctx, MCSAS_ERR_CUDA, "chain kernel launch (cluster %d): %s", pl.cluster, cudaGetErrorString(e));
+    ctx->n_launches++;
     return MCSAS_OK;
 }
 
-static int plan_chain(mcsas_ctx *ctx, int nq, int n_live, ChainPlan *out)
-{
-    return ctx->precision == MCSAS_FP64 ? plan_chain_fp64(ctx, nq, n_live, out)
-                                        : plan_chain_fp32(ctx, nq, n_live, out);
-}
-
-// Launch one time slice for the chains listed in ctx->h_ids[0..n_live).
+// Launch one time slice for the state slots listed in ctx->h_ids[0..n_live).
 //
-// Mixed slices (fp32 production kernel, automatic layout): when the planned cluster size C
-// leaves SMs idle (config 2: 100 chains x 1 CTA on 148 SMs), n_up = idle / C chains run this
-// slice as 2C-CTA clusters in a second, concurrent launch: those with the largest chi-squared.  Their slice is 11/8 as many batches (a 2C cluster runs a batch ~1.4x faster,
-// tools/tune.py), so both launches end together.
+// fp32 production kernel: a chain's result does not depend on the cluster size it runs with
+// (chain_fast.cuh), so every slice re-packs the machine.  Fewer live chains than SMs: the
+// chains furthest from the criterion (largest chi-squared: the likely critical path of the fit)
+// are upgraded 1 -> 2 -> 4 -> 8 CTAs until no SM is left; the up to four cluster sizes run as
+// concurrent launches, largest clusters first so that they find empty GPCs.  At least as many
+// chains as SMs: one launch of 1-CTA chains, the hardware's CTA scheduler fills the SMs.
 static int launch_slice(mcsas_ctx *ctx, int n_live, bool resume)
 {
     ChainArgs a = ctx->args;
-    ChainPlan pl;
-    int prc = plan_chain(ctx, ctx->nq_max, n_live, &pl);
-    if (prc) return prc;
     a.resume = resume ? 1 : 0;
-    int n_up = 0, up_f = 2;
-    ChainPlan pu = pl;
-    const char *mixed_env = getenv("MCSAS_B200_MIXED");
-    const bool mixed_on = mixed_env ? atoi(mixed_env) != 0 : true;
-    if (mixed_on && ctx->precision == MCSAS_FP32 && ctx->forced_cluster == 0 && !getenv("MCSAS_B200_CLUSTER")
-        && a.slice_batches > 0 && pl.cluster < 4 && n_live <= pl.resident) {
-        const int spare = ctx->prop.multiProcessorCount - n_live * pl.cluster;
-        // up_f: the upgraded chains run on up_f * C CTAs (4: fewer chains, but the few that bound
-        // the time to solution go twice as fast; only from C = 1)
-        if (const char *fe = getenv("MCSAS_B200_MIXED_FACTOR")) up_f = atoi(fe) == 4 ? 4 : 2;
-        if (pl.cluster * up_f > 4) up_f = 2;
-        n_up = spare / ((up_f - 1) * pl.cluster);
-        if (n_up > n_live) n_up = n_live;
-        if (n_up >= 1) {
-            ctx->forced_cluster = up_f * pl.cluster;
-            prc = plan_chain(ctx, ctx->nq_max, n_up, &pu);
-            ctx->forced_cluster = 0;
-            if (prc || pu.cluster != up_f * pl.cluster || pu.resident < n_up) n_up = 0;
-        } else n_up = 0;
+    const int sms = ctx->prop.multiProcessorCount;
+    for (int i = 0; i < 4; ++i) ctx->last_sizes[i] = 0;
+    if (ctx->precision == MCSAS_FP64) {
+        ChainPlan pl;
+        int prc = plan_chain_fp64(ctx, ctx->nq_max, n_live, &pl);
+        if (prc) return prc;
+        ctx->last_threads = pl.threads; ctx->last_qpt = CHAIN_QPT[pl.layout]; ctx->last_resident = pl.resident;
+        const int *ids = nullptr;
+        if (n_live != ctx->n_chains || resume) {
+            CK(cudaMemcpyAsync(ctx->d_ids, ctx->h_ids.data(), sizeof(int) * n_live, cudaMemcpyHostToDevice, ctx->stream));
+            ids = ctx->d_ids;
+        }
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        int rc = launch_one_size(ctx, a, pl, ids, n_live, ctx->stream);
+        if (rc) return rc;
+        ctx->last_cluster = pl.cluster;
+        ctx->n_slices++;
+        return MCSAS_OK;
     }
-    ctx->last_threads = pl.threads; ctx->last_qpt = CHAIN_QPT[pl.layout]; ctx->last_resident = pl.resident;
-    a.chain_ids = nullptr;
-    if (n_up > 0 && n_up < n_live && (int)ctx->h_conval.size() == ctx->n_slots) {
-        // the chains that are furthest from the criterion get the larger clusters: they are the
-        // likely critical path of the fit (deterministic: a function of the chains' states only)
+    // ---- cluster size per chain --------------------------------------------------------------
+    ChainPlan plans[4];
+    bool have[4] = {false, false, false, false};
+    int maxc = ctx->forced_cluster > 0 ? ctx->forced_cluster : ctx->max_cluster;
+    if (maxc > MAX_CLUSTER) maxc = MAX_CLUSTER;
+    for (int li = 0, c = 1; li < 4; ++li, c *= 2)
+        if (c <= maxc && (ctx->forced_cluster <= 0 || c == ctx->forced_cluster))
+            have[li] = plan_fast_layout(ctx, ctx->nq_max, c, &plans[li]);
+    int lowest = -1;
+    for (int li = 0; li < 4; ++li) if (have[li]) { lowest = li; break; }
+    if (lowest < 0) return fail(ctx, MCSAS_ERR_ARG, "no launchable fp32 chain layout for nq=%d", ctx->nq_max);
+    std::vector<int> level(n_live, lowest);
+    if ((int)ctx->h_conval.size() == ctx->n_slots && n_live > 1) {
+        // primaries before backup attempts, then by distance from the criterion
         const std::vector<double> &cv = ctx->h_conval;
-        std::stable_sort(ctx->h_ids.begin(), ctx->h_ids.begin() + n_live,
-                         [&cv](int x, int y) { return cv[x] > cv[y]; });
+        const int NC = ctx->n_chains;
+        const std::vector<int> &curv = ctx->cur;
+        std::stable_sort(ctx->h_ids.begin(), ctx->h_ids.begin() + n_live, [&](int x, int y) {
+            const bool px = curv[x % NC] == x, py = curv[y % NC] == y;
+            if (px != py) return px;
+            return cv[x] > cv[y];
+        });
     }
-    if (n_live != ctx->n_chains || resume || n_up > 0) {
-        CK(cudaMemcpyAsync(ctx->d_ids, ctx->h_ids.data(), sizeof(int) * n_live, cudaMemcpyHostToDevice, ctx->stream));
-        a.chain_ids = ctx->d_ids;
-    }
-    CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    const int extra = ctx->precision == MCSAS_FP64 ? 32 : 0;                          // fp64: + producer warp
-    if (n_up > 0) {
-        // the clusters go first, on the main stream, so that they are placed while the SMs are
-        // still empty; the single-size CTAs follow on stream2 (behind ev0 only) and fill the rest
-        ChainArgs u = a;
-        u.cluster = pu.cluster;
-        u.warps_q = pu.warps_q;
-        int num8 = up_f == 4 ? 16 : 11;                      // batches of the upgraded chains, in eighths
-        if (const char *ne = getenv("MCSAS_B200_MIXED_EIGHTHS")) { if (atoi(ne) >= 8) num8 = atoi(ne); }
-        u.slice_batches = a.slice_batches * num8 / 8;
-        u.slice_steps = a.slice_steps * num8 / 8;
-        cudaError_t e = CHAIN_FN[a.mp.model_id](ctx->precision, pu.layout, n_up * pu.cluster, pu.threads + extra,
-                                                ctx->smem, ctx->stream, u);
-        if (e != cudaSuccess) return fail(ctx, MCSAS_ERR_CUDA, "chain kernel launch (mixed slice): %s", cudaGetErrorString(e));
-        ctx->n_launches++;
-        a.chain_ids = ctx->d_ids + n_up;
-    }
-    if (n_live - n_up > 0) {
-        cudaStream_t st = ctx->stream;
-        if (n_up > 0) { st = ctx->stream2; CK(cudaStreamWaitEvent(st, ctx->ev0, 0)); }
-        a.cluster = pl.cluster;
-        a.warps_q = pl.warps_q;
-        cudaError_t e = CHAIN_FN[a.mp.model_id](ctx->precision, pl.layout, (n_live - n_up) * pl.cluster,
-                                                pl.threads + extra, ctx->smem, st, a);
-        if (e != cudaSuccess) return fail(ctx, MCSAS_ERR_CUDA, "chain kernel launch: %s", cudaGetErrorString(e));
-        ctx->n_launches++;
-        if (n_up > 0) {
-            CK(cudaEventRecord(ctx->ev_mix, st));
-            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_mix, 0));
+    if (ctx->forced_cluster <= 0) {
+        long long used = (long long)n_live << lowest;
+        int cnt_at[4] = {0, 0, 0, 0};
+        cnt_at[lowest] = n_live;
+        for (int li = lowest + 1; li < 4 && used < sms; ++li) {
+            if (!have[li]) break;
+            const int step_cost = (1 << li) / 2;
+            for (int i = 0; i < n_live && used + step_cost <= sms; ++i) {
+                if (level[i] >= li) continue;
+                if (level[i] != li - 1) break;                   // (sorted: upgrades form a prefix)
+                if (cnt_at[li] + 1 > plans[li].resident) break;  // co-resident clusters of this size
+                level[i] = li; cnt_at[li]++; cnt_at[li - 1]--;
+                used += step_cost;
+            }
         }
     }
+    CK(cudaMemcpyAsync(ctx->d_ids, ctx->h_ids.data(), sizeof(int) * n_live, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    // chains are sorted by level descending (upgrades are prefixes of the priority order)
+    int pos = 0, nside = 0;
+    for (int li = 3; li >= 0; --li) {
+        int n = 0;
+        while (pos + n < n_live && level[pos + n] == li) ++n;
+        if (!n) continue;
+        const bool last_group = pos + n == n_live;
+        cudaStream_t st = ctx->stream;
+        if (!last_group) { st = ctx->side[nside]; CK(cudaStreamWaitEvent(st, ctx->ev0, 0)); }
+        int rc = launch_one_size(ctx, a, plans[li], ctx->d_ids + pos, n, st);
+        if (rc) return rc;
+        if (!last_group) { CK(cudaEventRecord(ctx->ev_side[nside], st)); ++nside; }
+        ctx->last_sizes[li] = n;
+        ctx->last_cluster = 1 << li;
+        ctx->last_threads = plans[li].threads; ctx->last_qpt = CHAIN_QPT[plans[li].layout]; ctx->last_resident = plans[li].resident;
+        pos += n;
+    }
+    for (int i = 0; i < nside; ++i) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_side[i], 0));
+    ctx->n_slices++;
+    return MCSAS_OK;
+}
+
+// what the scheduler needs to know about every state slot after a slice: one async copy each into
+// pinned memory behind the slice's launches, then the end-of-slice event
+static int enqueue_readback(mcsas_ctx *ctx)
+{
+    const size_t NS = (size_t)ctx->n_slots;
+    if (ctx->args.slice_steps > 0 || ctx->args.slice_ns > 0) {
+        CK(cudaMemcpyAsync(ctx->h_att, ctx->d_att, sizeof(int) * ATT_N * NS, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_cnt, ctx->d_cnt, sizeof(long long) * 4 * NS, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->h_cv, ctx->d_scal + 2 * NS, sizeof(double) * NS, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    ctx->last_cluster = n_live - n_up > 0 ? pl.cluster : pu.cluster;
-    ctx->last_up = n_up;
     return MCSAS_OK;
 }
 
@@ -622,9 +649,10 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
         ring = p2;
         if (cfg->max_iter >= (1LL << 31)) return fail(ctx, MCSAS_ERR_ARG, "run: max_iter must be < 2^31");
     }
+    const int gw_cap = fast_gw_cap(ctx->nq_max);
     auto smem_of = [&](int rg) {
         return cfg->precision == MCSAS_FP64 ? chain_smem_bytes(nq_pad_max, N, P, D, narr, real, rg)
-                                            : fast_smem_bytes(nq_pad_max, N, P, D, narr, rg);
+                                            : fast_smem_bytes(nq_pad_max, N, P, D, narr, rg, gw_cap);
     };
     while (ring > 4 && smem_of(ring) > smem_limit) ring /= 2;
     size_t smem = smem_of(ring);
@@ -636,7 +664,6 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
         return fail(ctx, MCSAS_ERR_ARG, "run: configuration needs %zu B shared memory (> %zu)", smem, smem_limit);
     const int kcap_max = cfg->precision == MCSAS_FP32 ? FAST_KCAP : MCSAS_MAX_SPEC;
     int kcap = cfg->spec_max <= 0 ? kcap_max : (cfg->spec_max > kcap_max ? kcap_max : cfg->spec_max);
-    if (const char *ke = getenv("MCSAS_B200_KMAX")) { if (atoi(ke) > 0 && atoi(ke) < kcap) kcap = atoi(ke); }
     if (kcap > ring / 4) kcap = ring / 4;
     if (kcap < 1) kcap = 1;
     if (cfg->precision == MCSAS_FP32) {                  // fp32 kernel: batches are powers of two
@@ -669,18 +696,28 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     }
     if ((size_t)n_slots * ctx->nq_max > ctx->fit_cap) {
         CK(regrow(&ctx->d_fit, (size_t)n_slots * ctx->nq_max));
+        CK(regrow(&ctx->d_ftsave, (size_t)n_slots * ctx->nq_max));
         ctx->fit_cap = (size_t)n_slots * ctx->nq_max;
     }
     if ((size_t)n_slots > ctx->slot_cap) {
-        CK(regrow(&ctx->d_scal, (size_t)n_slots * 5));
+        CK(regrow(&ctx->d_scal, (size_t)n_slots * SCAL_N));
         CK(regrow(&ctx->d_cnt, (size_t)n_slots * 4));
-        CK(regrow(&ctx->d_att, (size_t)n_slots * 2));
+        CK(regrow(&ctx->d_att, (size_t)n_slots * ATT_N));
         CK(regrow(&ctx->d_ids, (size_t)n_slots));
         ctx->slot_cap = (size_t)n_slots;
     }
+    if ((size_t)n_slots > ctx->pin_cap) {
+        cudaFreeHost(ctx->h_att); cudaFreeHost(ctx->h_cnt); cudaFreeHost(ctx->h_cv);
+        ctx->h_att = nullptr; ctx->h_cnt = nullptr; ctx->h_cv = nullptr;
+        ctx->pin_cap = 0;
+        CK(cudaHostAlloc((void **)&ctx->h_att, sizeof(int) * ATT_N * n_slots, cudaHostAllocDefault));
+        CK(cudaHostAlloc((void **)&ctx->h_cnt, sizeof(long long) * 4 * n_slots, cudaHostAllocDefault));
+        CK(cudaHostAlloc((void **)&ctx->h_cv, sizeof(double) * n_slots, cudaHostAllocDefault));
+        ctx->pin_cap = (size_t)n_slots;
+    }
     CK(cudaMemsetAsync(ctx->d_cnt, 0, sizeof(long long) * (size_t)n_slots * 4, ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_scal, 0, sizeof(double) * (size_t)n_slots * 5, ctx->stream));
-    CK(cudaMemsetAsync(ctx->d_att, 0, sizeof(int) * (size_t)n_slots * 2, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_scal, 0, sizeof(double) * (size_t)n_slots * SCAL_N, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_att, 0, sizeof(int) * (size_t)n_slots * ATT_N, ctx->stream));
     ctx->have_trace = false;
     if (cfg->record_trace) {
         size_t n = (size_t)n_chains * (size_t)cfg->max_iter;
@@ -696,44 +733,50 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     a.mp = mp;
     a.smear = ctx->smear;
     a.n_contribs = N; a.n_reps = cfg->n_reps; a.n_chains = n_chains;
-    a.max_attempts = proposal_stream ? 1 : (cfg->max_retries < 0 ? 1 : cfg->max_retries + 2);
+    // mcsas.py:220-246: `if nt > maxRetries: give up` is tested BEFORE each mcFit and nt counts the
+    // finished ones, so a repetition makes at most maxRetries + 1 attempts (the "+ 2" of the reference's
+    // log message over-counts; measured on the unmodified reference: 6 attempts for maxRetries = 5)
+    a.max_attempts = proposal_stream ? 1 : (cfg->max_retries < 0 ? 1 : cfg->max_retries + 1);
     a.max_iter = cfg->max_iter; a.conv_crit = cfg->conv_crit; a.comp_exp = cfg->comp_exp;
     a.find_bg = cfg->find_background != 0; a.pos_bg = cfg->positive_background != 0;
     a.start_min = cfg->start_from_minimum != 0;
     a.spec_max = kcap; a.ring = ring;
-    {
-        const char *ge = getenv("MCSAS_B200_GRAM");
-        a.gram = ge ? atoi(ge) != 0 : 1;
-    }
+    a.gw_cap = gw_cap;
+    a.gram = ctx->tune.gram < 0 ? 0 : 1;
     a.first_chain = cfg->first_chain; a.record_trace = cfg->record_trace;
     a.seed = cfg->seed;
-    // time slicing: deterministic (uploaded stream / traced) runs are one launch
+    // Time slicing.  Deterministic (uploaded stream / traced) runs are one launch.  fp32 production
+    // kernel, automatic: a launch gives every chain a TIME budget (the chain stops at the first batch
+    // boundary behind it; results do not depend on where -- chain_fast.cuh), so all CTAs of a slice
+    // end together whatever phase their chains are in.  More chains than twice the SMs run in waves
+    // and get a long budget: the hardware's CTA scheduler balances them.
     long long slice = cfg->slice_steps;
-    if (slice == 0) slice = (proposal_stream || cfg->record_trace) ? -1 : 8192;
-    const char *env = getenv("MCSAS_B200_SLICE");
-    if (env && !(proposal_stream || cfg->record_trace)) slice = atoll(env);
-    a.slice_steps = slice > 0 ? slice : 0;
-    a.slice_batches = 0;
-    if (cfg->precision == MCSAS_FP32 && cfg->slice_steps == 0 && !env && a.slice_steps > 0) {
-        // auto: a slice is a number of BATCHES (similar duration whether a chain is in its
-        // move-rich early phase or late), the step limit stays as an upper bound
-        a.slice_batches = 256;                              // (tools/tune.py sched: 256 with backups from <= #SMs/4 live chains)
-        if (const char *sb = getenv("MCSAS_B200_SLICE_BATCHES")) { if (atoi(sb) > 0) a.slice_batches = atoi(sb); }
-        a.slice_steps = 16384;
+    const bool one_launch = proposal_stream || cfg->record_trace || slice < 0;
+    a.slice_steps = 0; a.slice_batches = 0; a.slice_ns = 0;
+    if (!one_launch) {
+        if (slice > 0) a.slice_steps = slice;                 // explicit step budget per launch
+        else if (cfg->precision == MCSAS_FP32) {
+            const int us = ctx->tune.slice_us > 0 ? ctx->tune.slice_us
+                                                  : (n_chains > 2 * ctx->prop.multiProcessorCount ? 8000 : 2000);
+            a.slice_ns = 1000LL * us;
+        } else a.slice_steps = 8192;
     }
     a.sets = ctx->d_sets; a.data = ctx->d_data;
     a.quad_x = ctx->d_quad; a.quad_w = ctx->d_quad + D;
     a.stream = d_stream; a.stream_stride = stream_stride;
     a.rset = ctx->d_rset; a.fit_meas = ctx->d_fit; a.nq_stride = ctx->nq_max;
+    a.ft_save = ctx->d_ftsave;
     a.scaling = ctx->d_scal; a.background = ctx->d_scal + n_slots; a.conval = ctx->d_scal + 2 * n_slots;
     a.conval0 = ctx->d_scal + 3 * n_slots; a.elapsed_s = ctx->d_scal + 4 * n_slots;
+    a.cen_a = ctx->d_scal + 5 * (size_t)n_slots; a.cen_b = ctx->d_scal + 6 * (size_t)n_slots;
+    a.cv_run = ctx->d_scal + 7 * (size_t)n_slots; a.last_acc = ctx->d_scal + 8 * (size_t)n_slots;
     a.num_iter = ctx->d_cnt; a.num_moves = ctx->d_cnt + n_slots; a.evals = ctx->d_cnt + 2 * n_slots;
     a.steps_all = ctx->d_cnt + 3 * (size_t)n_slots;
-    a.attempts = ctx->d_att; a.status = ctx->d_att + n_slots;
+    a.attempts = ctx->d_att; a.status = ctx->d_att + n_slots; a.batch_k = ctx->d_att + 2 * (size_t)n_slots;
     a.trace_accept = cfg->record_trace ? ctx->d_tacc : nullptr;
     a.trace_chi = cfg->record_trace ? ctx->d_tchi : nullptr;
     a.cache = nullptr;
-    if (cfg->precision == MCSAS_FP32 && !(getenv("MCSAS_B200_CACHE") && atoi(getenv("MCSAS_B200_CACHE")) == 0)) {
+    if (cfg->precision == MCSAS_FP32) {
         // contribution-row cache: n_contribs rows of FAST_QCAP floats per SM (a CTA owns its SM)
         const size_t stride = (size_t)N * FAST_QCAP;
         const size_t need = stride * FAST_CACHE_SMS;
@@ -744,7 +787,7 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
         a.cache_stride = (long long)stride;
         a.cache_lock = ctx->d_cache_lock;
     }
-    if (getenv("MCSAS_B200_PROF") && cfg->precision == MCSAS_FP32) {
+    if (ctx->tune.profile && cfg->precision == MCSAS_FP32) {
         cudaFree(ctx->d_prof);
         ctx->d_prof = nullptr;
         CK(cudaMalloc(&ctx->d_prof, sizeof(long long) * 48 * n_slots));
@@ -755,14 +798,12 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     ctx->precision = cfg->precision;
     ctx->smem = smem;
     ctx->forced_cluster = cfg->cluster_size;
+    ctx->forced_qpt = ctx->tune.qpt;
+    ctx->max_cluster = ctx->tune.max_cluster > 0 ? ctx->tune.max_cluster : 8;
     ctx->n_chains = n_chains; ctx->n_contribs = N; ctx->n_reps = cfg->n_reps; ctx->n_active = P;
     ctx->n_slots = n_slots;
     ctx->max_attempts = a.max_attempts;
-    {
-        const char *be = getenv("MCSAS_B200_BACKUP");
-        ctx->backups = cfg->precision == MCSAS_FP32 && !proposal_stream && !cfg->record_trace && a.slice_steps > 0
-                       && a.max_attempts > 1 && !(be && atoi(be) == 0);
-    }
+    ctx->backups = cfg->precision == MCSAS_FP32 && !one_launch && a.max_attempts > 1 && ctx->tune.backups >= 0;
     ctx->cur.assign(n_chains, 0);
     for (int i = 0; i < n_chains; ++i) ctx->cur[i] = i;
     ctx->bak.assign(n_chains, -1);
@@ -777,11 +818,14 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     ctx->n_live = n_chains;
     ctx->h_conval.clear();
     ctx->n_launches = 0;
+    ctx->n_slices = 0;
     ctx->kernel_ms = 0.f;
     ctx->stop_flag = stop_flag;
     *ctx->h_stop = 0;
     CK(cudaEventRecord(ctx->ev_begin, ctx->stream));
     int rc = launch_slice(ctx, n_chains, false);
+    if (rc) return rc;
+    rc = enqueue_readback(ctx);
     if (rc) return rc;
     ctx->running = true;
     ctx->have_run = false;
@@ -804,31 +848,27 @@ extern "C" int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms)
     if (!ctx->running) return fail(ctx, MCSAS_ERR_STATE, "wait: nothing running");
     ctx->running = false;
     const int NC = ctx->n_chains, NS = ctx->n_slots;
-    std::vector<int> att(2 * (size_t)NS);                 // attempts | status
-    std::vector<long long> cnt(4 * (size_t)NS);           // num_iter | num_moves | evals | steps_all
+    const bool sliced = ctx->args.slice_steps > 0 || ctx->args.slice_ns > 0;
     for (;;) {
         CK(cudaStreamSynchronize(ctx->stream));
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         ctx->kernel_ms += ms;
-        if (getenv("MCSAS_B200_DEBUG"))
-            fprintf(stderr, "[mcsas_b200] slice %d: live %d cluster %d (%d chains at twice that) T %d qpt %d resident %d  %.3f ms\n",
-                    ctx->n_launches, ctx->n_live, ctx->last_cluster, ctx->last_up, ctx->last_threads, ctx->last_qpt,
-                    ctx->last_resident, ms);
-        if (ctx->args.slice_steps <= 0) break;
-        CK(cudaMemcpy(att.data(), ctx->d_att, sizeof(int) * att.size(), cudaMemcpyDeviceToHost));
-        int *attempts = att.data(), *status = att.data() + NS;
+        if (ctx->tune.verbose)
+            fprintf(stderr, "[mcsas_b200] slice %d: live %d  chains at cluster 1/2/4/8: %d/%d/%d/%d  %.3f ms\n",
+                    ctx->n_slices, ctx->n_live, ctx->last_sizes[0], ctx->last_sizes[1], ctx->last_sizes[2],
+                    ctx->last_sizes[3], ms);
+        if (!sliced) break;
+        int *att = ctx->h_att;
+        long long *cnt = ctx->h_cnt;
+        int *attempts = att, *status = att + NS;
         for (int i = 0; i < ctx->n_live; ++i) {
             int s = ctx->h_ids[i];
             if (status[s] < 0)
                 return fail(ctx, MCSAS_ERR_CUDA, "chain %d: kernel watchdog fired (status %d)", s % NC, status[s]);
         }
-        if (ctx->backups) CK(cudaMemcpy(cnt.data(), ctx->d_cnt, sizeof(long long) * cnt.size(), cudaMemcpyDeviceToHost));
-        if (ctx->precision == MCSAS_FP32 && ctx->args.slice_batches > 0) {
-            ctx->h_conval.resize(NS);
-            CK(cudaMemcpy(ctx->h_conval.data(), ctx->d_scal + 2 * (size_t)NS, sizeof(double) * NS, cudaMemcpyDeviceToHost));
-        }
-        const long long *num_iter = cnt.data(), *evals = cnt.data() + 2 * (size_t)NS, *steps_all = cnt.data() + 3 * (size_t)NS;
+        ctx->h_conval.assign(ctx->h_cv, ctx->h_cv + NS);
+        const long long *num_iter = cnt, *evals = cnt + 2 * (size_t)NS, *steps_all = cnt + 3 * (size_t)NS;
         // ---- per chain: current attempt finished / failed / continues; backup bookkeeping --------
         int n = 0, n_primary = 0;
         for (int c = 0; c < NC; ++c) {
@@ -862,8 +902,7 @@ extern "C" int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms)
         }
         // ---- start backups: few chains alive, SMs idle, chain is late in its attempt -------------
         bool new_backups = false;
-        int bdiv = 4;
-        if (const char *bd = getenv("MCSAS_B200_BACKUP_DIV")) bdiv = atoi(bd) > 0 ? atoi(bd) : 4;
+        const int bdiv = ctx->tune.backup_div > 0 ? ctx->tune.backup_div : 4;
         if (ctx->backups && n_primary > 0 && n_primary * bdiv <= ctx->prop.multiProcessorCount) {
             for (int c = 0; c < NC; ++c) {
                 if (ctx->done[c] || ctx->bak[c] >= 0) continue;
@@ -874,6 +913,7 @@ extern "C" int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms)
                 // fresh state of the backup slot, uploaded below with the host copies
                 att[b] = attempts[pslot] + 1; att[(size_t)NS + b] = 2;
                 for (int k = 0; k < 4; ++k) cnt[(size_t)k * NS + b] = 0;
+                ctx->h_conval[b] = 1e300;
                 new_backups = true;
                 CK(cudaMemsetAsync(ctx->d_scal + 4 * (size_t)NS + b, 0, sizeof(double), ctx->stream));   // elapsed
                 ctx->bak[c] = b; ctx->bak_state[c] = 1;
@@ -882,17 +922,19 @@ extern "C" int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms)
             }
         }
         if (new_backups) {                                  // nothing runs between slices: whole arrays
-            CK(cudaMemcpyAsync(ctx->d_att, att.data(), sizeof(int) * att.size(), cudaMemcpyHostToDevice, ctx->stream));
-            CK(cudaMemcpyAsync(ctx->d_cnt, cnt.data(), sizeof(long long) * cnt.size(), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->d_att, att, sizeof(int) * ATT_N * (size_t)NS, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->d_cnt, cnt, sizeof(long long) * 4 * (size_t)NS, cudaMemcpyHostToDevice, ctx->stream));
         }
-        if (ctx->n_launches > 100000) return fail(ctx, MCSAS_ERR_CUDA, "time-slice loop did not terminate");
+        if (ctx->n_slices > 1000000) return fail(ctx, MCSAS_ERR_CUDA, "time-slice loop did not terminate");
         ctx->n_live = n;
         bool stop = *(volatile int *)ctx->h_stop != 0 || (ctx->stop_flag && *ctx->stop_flag);
         if (n_primary == 0 || stop) break;
         int rc = launch_slice(ctx, n, true);
         if (rc) return rc;
+        rc = enqueue_readback(ctx);
+        if (rc) return rc;
     }
-    if (getenv("MCSAS_B200_DEBUG") && ctx->backups)
+    if (ctx->tune.verbose && ctx->backups)
         fprintf(stderr, "[mcsas_b200] backup attempts started %d, used %d\n", ctx->n_backups_started, ctx->n_backups_used);
     if (ctx->args.prof) {                                 // phase profile (experiments only)
         std::vector<long long> h((size_t)48 * ctx->n_slots);
@@ -936,6 +978,19 @@ extern "C" int mcsas_run_info(mcsas_ctx *ctx, int *n_launches, int *last_cluster
     if (n_launches) *n_launches = ctx->n_launches;
     if (last_cluster) *last_cluster = ctx->last_cluster;
     if (kernel_ms) *kernel_ms = ctx->kernel_ms;
+    return MCSAS_OK;
+}
+
+extern "C" int mcsas_set_tuning(mcsas_ctx *ctx, const mcsas_tuning *t)
+{
+    if (!ctx) return MCSAS_ERR_ARG;
+    if (ctx->running) return fail(ctx, MCSAS_ERR_STATE, "set_tuning: a run is in flight");
+    if (t) ctx->tune = *t; else memset(&ctx->tune, 0, sizeof ctx->tune);
+    if (ctx->tune.max_cluster != 0 && ctx->tune.max_cluster != 1 && ctx->tune.max_cluster != 2
+        && ctx->tune.max_cluster != 4 && ctx->tune.max_cluster != 8)
+        return fail(ctx, MCSAS_ERR_ARG, "set_tuning: max_cluster must be 0, 1, 2, 4 or 8");
+    if (ctx->tune.qpt != 0 && ctx->tune.qpt != 1 && ctx->tune.qpt != 2 && ctx->tune.qpt != 4)
+        return fail(ctx, MCSAS_ERR_ARG, "set_tuning: qpt must be 0, 1, 2 or 4");
     return MCSAS_OK;
 }
 

@@ -28,6 +28,12 @@
 //  * no dedicated producer warp: all 8 warps evaluate; while warp 0 solves the batch, the
 //    last warp prepares the ring entries of the next one.  When the q slice of a CTA needs
 //    fewer warps, the spare warps form PROPOSAL GROUPS that evaluate other chunks.
+//  * SCHEDULE-INDEPENDENT RESULTS: every warp's partial sums reach every CTA of the chain's
+//    cluster directly (st.async + mbarrier transaction count, no CTA barrier in between) and
+//    are added in one fixed order, and a launch that ends mid-chain saves everything the loop
+//    carries (fp64 master intensity, centre of the expansion, running chi-squared, batch
+//    size).  A chain's result is therefore a function of (seed, chain id) alone -- the same
+//    bits for every cluster size, time slicing and GPU count.
 #pragma once
 #include "chain_kernel.cuh"
 
@@ -340,10 +346,41 @@ template <int NG> __device__ __forceinline__ int grp_perm(int lane)
     return NG == 8 ? ((lane >> 2) & 7) : ((lane >> 3) & 3);
 }
 
+// ---- exchange of per-warp partial sums -------------------------------------------------------
+// Every CTA of a chain's cluster receives the partial sums of EVERY warp of the chain (global
+// warp gw = rank * warps_q + wq covers the q points [32 QPT gw, 32 QPT (gw + 1))) and adds
+// them in ascending gw order, so the totals -- and with them every accept decision -- are
+// bit-identical for every cluster size (a chain's result does not depend on how the host
+// scheduler packs it).  C > 1: st.async into all ranks (own CTA included), completion counted
+// in bytes on the receiver's mbarrier; C == 1: plain shared-memory stores and one mbarrier
+// arrival per warp.  No CTA-wide barrier between the evaluation and the decision.
+__device__ __forceinline__ void xsend16(float4 *dst, uint64_t *bar, int C, const float4 v)
+{
+    if (C == 1) { *dst = v; return; }
+    const uint32_t la = smem_u32(dst), lb = smem_u32(bar);
+    for (int r = 0; r < C; ++r) {
+        uint32_t ra, rb;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(r));
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(lb), "r"(r));
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                     ::"r"(ra), "r"(__float_as_int(v.x)), "r"(__float_as_int(v.y)), "r"(__float_as_int(v.z)),
+                       "r"(__float_as_int(v.w)), "r"(rb) : "memory");
+    }
+}
+__device__ __forceinline__ void xsend8(double *dst, uint64_t *bar, int C, const double v)
+{
+    if (C == 1) { *dst = v; return; }
+    for (int r = 0; r < C; ++r) dsmem_store_async(dst, bar, (uint32_t)r, v);
+}
+__device__ __forceinline__ void mbar_arrive_release(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // CACHE: the scaled intensity rows D_i(q) of the N current contributions live in global
 // memory (L2 resident: N x nq floats per chain), so the "old" half of every evaluation
-// (mcsas.py:362 recomputes it) is one coalesced load; rows are rebuilt with the initial sum
-// of every launch and rewritten when a move is accepted.
+// (mcsas.py:362 recomputes it) is one coalesced load; rows are rebuilt at the start of every
+// launch and rewritten when a move is accepted.
 // SMEAR: instantiation for data with a smearing profile (sasmodel.py:56-73); the unsmeared
 // instantiation folds every smearing branch away at compile time.
 template <int MODEL, int QPT, bool CACHE, bool SMEAR>
@@ -355,7 +392,6 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     constexpr int NARR = O::NARR;
     constexpr int FGRP = QPT == 1 ? 4 : 8;         // proposals per reduce-scatter chunk
     constexpr int NGP = FGRP * (FGRP - 1) / 2;     // pairs of a chunk (Gram matrix, off diagonal)
-    constexpr int NGU = (NGP + 1) / 2;             // ... in 64-bit exchange units
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T = blockDim.x;                      // all warps evaluate; the last one also fills the ring
     const int W = T >> 5;
@@ -365,6 +401,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     const int TQ = WQ * 32, qtid = wq * 32 + lane;
     const int C = a.cluster;
     const int rank = C > 1 ? (int)cluster_ctarank() : 0;
+    const int GW = C * WQ, gw = rank * WQ + wq;    // warps of the whole chain / this warp's place among them
     const int slot = blockIdx.x / C;
     const int chain = a.chain_ids ? a.chain_ids[slot] : slot;
     // `chain` is a state slot: slots >= n_chains hold a chain's other attempt (retry prepared or
@@ -391,22 +428,20 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char *sp = smem_raw;
     auto carve = [&](size_t bytes) { unsigned char *p = sp; sp += (bytes + 15) & ~size_t(15); return p; };
+    const int GWC = a.gw_cap;                      // >= GW of every layout the host may pick for this nq
     uint64_t *s_bar = (uint64_t *)carve(16);
     double *s_data = (double *)carve(sizeof(double) * 3 * ds.nq_pad);
     double *s_rset = (double *)carve(sizeof(double) * N * (P > 0 ? P : 1));
     carve(64);
     RingEntry<float> *s_ring = (RingEntry<float> *)carve((size_t)RING * sizeof(RingEntry<float>));
-    float4 *s_wsum = (float4 *)carve(16 * (size_t)FAST_MAX_WARPS * FAST_KCAP);
-    double *s_bsum = (double *)carve(8 * (size_t)(FAST_MAX_WARPS + 1) * 6);
-    constexpr int XU = FAST_XU;                    // b64 units per rank in an exchange buffer
-    double *s_part = (double *)carve(8 * 2 * (size_t)MAX_CLUSTER * XU);
+    float4 *s_xp = (float4 *)carve(16 * 2 * (size_t)GWC * FAST_KCAP);   // [buf][gw][proposal] (s1..s4)
+    double *s_xb = (double *)carve(8 * 2 * (size_t)GWC * 8);            // [buf][gw][5 base sums, flags]
+    float *s_xg = (float *)carve(4 * 2 * (size_t)GWC * 32);             // [buf][gw][Gram pairs]
     uint64_t *s_xbar = (uint64_t *)carve(16);
-    float *s_gram = (float *)carve(4 * (size_t)FAST_MAX_WARPS * 28);  // per-warp Gram pairs
     float *s_gtot = (float *)carve(4 * 32);
     double *s_chi = (double *)carve(8 * (size_t)FAST_KCAP + 128);
     FastDec *s_dec = (FastDec *)(s_chi + FAST_KCAP);
-    double *s_asum = (double *)carve(8 * (size_t)(FAST_MAX_WARPS + 2) * 3 + 8 * 2 * MAX_CLUSTER * 3);
-    double *s_apart = s_asum + (FAST_MAX_WARPS + 2) * 3;
+    double *s_apart = (double *)carve(8 * 2 * (size_t)GWC * 3);         // [buf][gw][3] full-LSQ all-sum
     double *s_ft = (double *)carve(8 * 2 * FAST_QCAP);            // model intensity, double buffered
     double *s_In = (double *)carve(8 * FAST_QCAP);                // I / i_scale
     double *s_sw = (double *)carve(8 * FAST_QCAP);                // i_scale / sigma (0: padding)
@@ -421,7 +456,11 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         __threadfence();
     }
     // ---- stage the dataset once: TMA bulk copy global -> shared ---------------------------
-    if (tid == 0) { mbar_init(s_bar, 1); mbar_init(s_xbar, 1); mbar_init(s_xbar + 1, 1); s_dec->wd = 0; }
+    if (tid == 0) {
+        mbar_init(s_bar, 1);
+        mbar_init(s_xbar, C > 1 ? 1 : W);
+        mbar_init(s_xbar + 1, C > 1 ? 1 : W);
+    }
     unsigned xphase = 0;
     __syncthreads();
     if (tid == 0) {
@@ -434,7 +473,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         s_qw[j] = (float)a.quad_w[j];
     }
     mbar_wait(s_bar, 0);
-    __syncthreads();
+    if (C > 1) cluster_sync_all(); else __syncthreads();         // every rank's mbarriers are initialised
     const QuadTab<float> qt = { D, a.mp.quad_rule, s_qx, s_qw, &a.smear, SMEAR ? a.smear.n : 0 };
     const float qref = (float)(ds.q_ref * 1e-9);   // 1/nm
 
@@ -473,28 +512,26 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         }
     }
 
-    // Sum three per-thread partials over the whole cluster (fixed order; all threads call it)
-    int abuf = 0;
+    // Sum three per-thread partials (group 0 holds them) over the whole chain, in ascending
+    // global-warp order on every rank (all threads call it)
+    int sbuf = 0;
     auto cluster_allsum3 = [&](double (&v)[3]) {
 #pragma unroll
         for (int i = 0; i < 3; ++i) v[i] = warp_sum(v[i]);
-        if (lane == 0) { s_asum[warp * 3] = v[0]; s_asum[warp * 3 + 1] = v[1]; s_asum[warp * 3 + 2] = v[2]; }
-        __syncthreads();
-        double *part = s_apart + (size_t)abuf * MAX_CLUSTER * 3;
-        if (tid < 3) {
-            double x = 0.;
-            for (int wv = 0; wv < W; ++wv) x += s_asum[wv * 3 + tid];
-            if (C > 1) { for (int r = 0; r < C; ++r) dsmem_store(part + rank * 3 + tid, (uint32_t)r, x); }
-            else part[tid] = x;
+        double *part = s_apart + (size_t)sbuf * GWC * 3;
+        if (grp == 0 && lane < 3) {
+            const double x = lane == 0 ? v[0] : (lane == 1 ? v[1] : v[2]);
+            if (C > 1) { for (int r = 0; r < C; ++r) dsmem_store(part + gw * 3 + lane, (uint32_t)r, x); }
+            else part[gw * 3 + lane] = x;
         }
         if (C > 1) cluster_sync_all(); else __syncthreads();
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             double x = 0.;
-            for (int r = 0; r < C; ++r) x += part[r * 3 + i];
+            for (int g = 0; g < GW; ++g) x += part[g * 3 + i];
             v[i] = x;
         }
-        abuf ^= 1;
+        sbuf ^= 1;
     };
 
     cluster_allsum3(v3);
@@ -570,6 +607,16 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     const unsigned long long t_start = globaltimer_ns();
     long long step = 0, moves = 0, evals = 0, steps_all = 0;
     double conval = 0., conval0 = 0., sc_a = 1., sc_b = 0.;
+    double a0 = 1., b0 = 0.;                       // centre of the quadratic expansion (fit of the last accepted state)
+    double cv_run = 0.;                            // chi-squared the accept test compares against
+    // Batch kind and size.  Which batches are Gram batches follows from the positions of the
+    // accepted steps alone (a chain-intrinsic rule: results must not depend on the schedule):
+    // a move less than FGRP steps behind the previous one switches to Gram batches, a Gram batch
+    // without a move switches back.  The size K of a speculative batch is free (it never changes
+    // a result) and adapts to the distance between moves.
+    long long last_acc = -(1LL << 40);             // step of the last accepted move
+    bool gmode = true;
+    int K = max(1, kmax / 2);
     int attempt = 0, status = 1;
     bool resume = a.resume != 0 && a.status[chain] == 0;
     if (a.resume) {
@@ -606,7 +653,8 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         for (int j = 0; j < QPT; ++j) ft0[j] = 0.;
         cur = 0;
         __syncthreads();
-        // ---- ft = sum of all contributions, in contribution order (mcsas.py:319) -----------
+        // ---- ft = sum of all contributions, in contribution order (mcsas.py:319); the cached
+        //      rows of this launch ------------------------------------------------------------
         for (int i0 = 0; i0 < N; i0 += RING) {
             int nb = min(RING, N - i0);
             for (int e = tid; e < nb; e += blockDim.x) {
@@ -627,16 +675,37 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             }
             __syncthreads();
         }
-        evals += N;
+        if (!resume) evals += N;                                 // (rebuilding the rows of a resumed chain is not counted)
+        if (resume) {
+            // continue exactly where the previous launch stopped: the fp64 master intensity, the
+            // centre of the expansion, the running chi-squared and the batch size are part of the
+            // saved state, so a slice boundary leaves no trace in the chain
+#pragma unroll
+            for (int j = 0; j < QPT; ++j) {
+                const int i = (rank * TQ + qtid) * QPT + j;
+                ft0[j] = i < nq ? a.ft_save[(long long)chain * a.nq_stride + i] : 0.;
+            }
+        }
         if (grp == 0) {
 #pragma unroll
             for (int j = 0; j < QPT; ++j) s_ft[qtid * QPT + j] = ft0[j];
         }
-        lsq_all(sc_a, sc_b, conval);                             // mcsas.py:339-344
-        if (!resume) { conval0 = conval; step = 0; moves = 0; }
+        if (resume) {
+            a0 = a.cen_a[chain]; b0 = a.cen_b[chain]; cv_run = a.cv_run[chain];
+            last_acc = (long long)a.last_acc[chain];
+            K = a.batch_k[chain] & 0xffff;
+            gmode = (a.batch_k[chain] >> 16) != 0;
+            sc_a = a0; sc_b = b0;
+            __syncthreads();
+        } else {
+            lsq_all(sc_a, sc_b, conval);                         // mcsas.py:339-344
+            conval0 = conval; step = 0; moves = 0;
+            a0 = sc_a; b0 = sc_b; cv_run = conval;
+            K = max(1, kmax / 2);
+            gmode = true; last_acc = -(1LL << 40);
+        }
         resume = false;
-        // centre of the quadratic expansion = this fit; residual / model in units of sigma
-        double a0 = sc_a, b0 = sc_b;
+        // residual / model in units of sigma around the centre
 #pragma unroll
         for (int j = 0; j < QPT; ++j) {
             const int ql = qtid * QPT + j;
@@ -650,57 +719,69 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         long long filled = min(step + 2LL * kmax, a.max_iter);   // ring holds steps [.., filled)
         for (long long t = step + tid; t < filled; t += blockDim.x) fill_entry(t, attempt, sbase);
         __syncthreads();
-        int K = max(1, kmax / 2);
         int batch = 0;
         const int wd_batches = (int)min((long long)0x3fffffff, 2 * (min(a.max_iter, slice_end) - step) + 64);
         const int batch_end = a.slice_batches > 0 ? a.slice_batches : 0x7fffffff;
+        bool slice_over = false;                                 // this launch's budget (steps, batches, time) is used up
+        conval = cv_run;
         bool live = N > 1 && conval > a.conv_crit && step < a.max_iter && step < slice_end;
 
-        {
         // ---- the MC loop (mcsas.py:354-404) ---------------------------------------------------
-        // Two kinds of batches: SPECULATIVE (Kb <= 32 steps evaluated against the current state,
+        // Two kinds of batches: SPECULATIVE (Kb <= 64 steps evaluated against the current state,
         // committed up to the first accepted one) when moves are rare, and GRAM (exactly FGRP
-        // steps, all of them consumed: the Gram matrix of the proposals' changes lets warp 0
-        // re-derive the sums of later proposals after each accepted one) when moves are frequent.
+        // steps: the Gram matrix of the proposals' changes lets warp 0 re-derive the sums of
+        // later proposals after each accepted one) when moves are frequent.
         FastBase B;                                              // meaningful in warp 0 only
         B.S = L.S; B.Sm = 0.; B.Smm = 0.; B.E0 = 0.; B.E1 = 0.; B.E2 = 0.; B.a0 = a0; B.b0 = b0;
+        int xb_ = 0;                                             // exchange buffer of the next batch
+        for (;;) {
         while (live) {
             const long long pt0 = a.prof ? clock64() : 0;
-            int Kb = min(K, kmax);
-            bool gram = a.gram && Kb <= FGRP && kmax >= FGRP;
+            // a speculative batch smaller than one chunk per proposal group would take as long
+            int Kb = min(max(K, PS * FGRP), kmax);
+            bool gram = a.gram && gmode && kmax >= FGRP;
             if (gram) Kb = FGRP;
             {
                 long long rem = a.max_iter - step;
                 if (rem < Kb) { Kb = rem >= 1 ? (1 << (31 - __clz((int)rem))) : 0; gram = false; }   // power of two
             }
             ++batch;
-            bool wd = Kb < 1 || batch > wd_batches;               // watchdog: never loop forever
+            if (Kb < 1 || batch > wd_batches) { status = -2; break; }   // watchdog (uniform over the cluster)
             const int ri0 = (int)((uint32_t)step % (uint32_t)N);  // contribution replaced by the batch's first step
+            const int xb = xb_;
+            float4 *const xp = s_xp + (size_t)xb * GWC * FAST_KCAP + (size_t)gw * FAST_KCAP;
+            double *const xbs = s_xb + (size_t)xb * GWC * 8 + (size_t)gw * 8;
+            uint64_t *const xbar = s_xbar + xb;
             const long long pt1 = a.prof ? clock64() : 0;
-            // ---- exact base sums of the current state (after an accepted move) ---------------
-            if (dirty && grp == 0) {
-                double b5[5] = {0., 0., 0., 0., 0.};
+            // ---- exact base sums of the current state (after an accepted move) + this rank's flags
+            if (grp == 0) {
+                double x = 0.;
+                if (dirty) {
+                    double b5[5] = {0., 0., 0., 0., 0.};
 #pragma unroll
-                for (int j = 0; j < QPT; ++j) {
-                    const int ql = qtid * QPT + j;
-                    const double sq = s_sw[ql];
-                    double m = sq * s_ft[cur * FAST_QCAP + ql];
-                    double r = sq * s_In[ql] - (a0 * m + b0 * sq);
-                    b5[0] = fma(r, r, b5[0]);                    // E0 = sum w e^2
-                    b5[1] = fma(r, m, b5[1]);                    // E1 = sum w e ft
-                    b5[2] = fma(r, sq, b5[2]);                   // E2 = sum w e
-                    b5[3] = fma(m, sq, b5[3]);                   // Sm
-                    b5[4] = fma(m, m, b5[4]);                    // Smm
-                }
+                    for (int j = 0; j < QPT; ++j) {
+                        const int ql = qtid * QPT + j;
+                        const double sq = s_sw[ql];
+                        double m = sq * s_ft[cur * FAST_QCAP + ql];
+                        double r = sq * s_In[ql] - (a0 * m + b0 * sq);
+                        b5[0] = fma(r, r, b5[0]);                    // E0 = sum w e^2
+                        b5[1] = fma(r, m, b5[1]);                    // E1 = sum w e ft
+                        b5[2] = fma(r, sq, b5[2]);                   // E2 = sum w e
+                        b5[3] = fma(m, sq, b5[3]);                   // Sm
+                        b5[4] = fma(m, m, b5[4]);                    // Smm
+                    }
 #pragma unroll
-                for (int i = 0; i < 5; ++i) b5[i] = warp_sum(b5[i]);
-                if (lane < 5) {
-                    double x = b5[0];
+                    for (int i = 0; i < 5; ++i) b5[i] = warp_sum(b5[i]);
+                    x = b5[0];
                     if (lane == 1) x = b5[1];
                     if (lane == 2) x = b5[2];
                     if (lane == 3) x = b5[3];
                     if (lane == 4) x = b5[4];
-                    s_bsum[wq * 6 + lane] = x;
+                    if (lane < 5) xsend8(xbs + lane, xbar, C, x);
+                }
+                if (lane == 5) {                                 // time budget of this launch (any warp may end it)
+                    const bool over = a.slice_ns > 0 && globaltimer_ns() - t_start > (unsigned long long)a.slice_ns;
+                    xsend8(xbs + 5, xbar, C, over ? 1. : 0.);
                 }
             }
             const long long pt1a = a.prof ? clock64() : 0;
@@ -711,187 +792,193 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             asm volatile("mov.b32 %0, %0;" : "+r"(perm));
             float uu[FGRP][QPT];                                 // GRAM: (new - old)/sigma of slot s
             float dnk[CACHE ? FGRP : 1][QPT];                    // GRAM + CACHE: new row of slot s
-            if (!wd) {
-                if (gram) {
-                    // every group evaluates the chunk (all need uu for the update); group 0 reports
-                    const int e0 = (int)step & (RING - 1);
-                    float acc[FGRP][4], gq[NGP];
-                    float od[CACHE ? FGRP : 1][QPT];
+            if (gram) {
+                // every group evaluates the chunk (all need uu for the update); group 0 reports
+                const int e0 = (int)step & (RING - 1);
+                float acc[FGRP][4], gq[NGP];
+                float od[CACHE ? FGRP : 1][QPT];
+                if (CACHE) {
+#pragma unroll
+                    for (int s = 0; s < FGRP; ++s) {
+                        int ri = ri0 + (s ^ perm);
+                        if (ri >= N) ri -= N;
+                        row_load<QPT>(crow + (size_t)ri * RL, od[CACHE ? s : 0]);
+                    }
+                    int ent[FGRP];
+#pragma unroll
+                    for (int s = 0; s < FGRP; ++s) ent[s] = (e0 + (s ^ perm)) & (RING - 1);
+                    FO::template evalChunk<QPT, CACHE ? FGRP : 1>(s_ring, (const int (&)[CACHE ? FGRP : 1])ent,
+                                                                  s_nodes, NSTR, qt, Q, dnk);
+                }
+#pragma unroll
+                for (int i = 0; i < NGP; ++i) gq[i] = 0.f;
+#pragma unroll
+                for (int s = 0; s < FGRP; ++s) {
+                    acc[s][0] = 0.f; acc[s][1] = 0.f; acc[s][2] = 0.f; acc[s][3] = 0.f;
+                    const int e = (e0 + (s ^ perm)) & (RING - 1);
+                    const Contrib<float> cn = s_ring[e].cn, co = s_ring[e].co;
+                    const float *nn = s_nodes + (size_t)(e * 2) * NSTR, *no = nn + NSTR;
+                    float dd[QPT];
                     if (CACHE) {
 #pragma unroll
+                        for (int j = 0; j < QPT; ++j) dd[j] = dnk[CACHE ? s : 0][j] - od[CACHE ? s : 0][j];
+                    } else {
+                        FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd);
+                    }
+#pragma unroll
+                    for (int j = 0; j < QPT; ++j) {
+                        const float u = cq[j] * dd[j];
+                        uu[s][j] = u;
+                        acc[s][0] = fmaf(rho[j], u, acc[s][0]);
+                        acc[s][1] = fmaf(u, u, acc[s][1]);
+                        acc[s][2] = fmaf(mu[j], u, acc[s][2]);
+                        acc[s][3] = fmaf(om[j], u, acc[s][3]);
+#pragma unroll
+                        for (int t = 0; t < s; ++t)
+                            gq[tri_idx<FGRP>(t, s)] = fmaf(uu[t][j], u, gq[tri_idx<FGRP>(t, s)]);
+                    }
+                }
+                if (grp == 0) {
+#pragma unroll
+                    for (int h = FGRP / 2, off = 16; h >= 1; h >>= 1, off >>= 1) {
+#pragma unroll
+                        for (int s = 0; s < h; ++s)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                acc[s][i] += __shfl_xor_sync(0xffffffffu, acc[s + h][i], off);
+                        // Gram: all-reduce with the slot permutation of the partner lane
+                        float tmp[NGP];
+#pragma unroll
+                        for (int t = 0; t < FGRP; ++t)
+#pragma unroll
+                            for (int s2 = t + 1; s2 < FGRP; ++s2)
+                                tmp[tri_idx<FGRP>(t, s2)] =
+                                    __shfl_xor_sync(0xffffffffu, gq[tri_idx<FGRP>(t ^ h, s2 ^ h)], off);
+#pragma unroll
+                        for (int i = 0; i < NGP; ++i) gq[i] += tmp[i];
+                    }
+#pragma unroll
+                    for (int off = 32 / FGRP / 2; off >= 1; off >>= 1) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            acc[0][i] += __shfl_xor_sync(0xffffffffu, acc[0][i], off);
+#pragma unroll
+                        for (int i = 0; i < NGP; ++i) gq[i] += __shfl_xor_sync(0xffffffffu, gq[i], off);
+                    }
+                    if ((lane & (32 / FGRP - 1)) == 0)
+                        xsend16(xp + perm, xbar, C, make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]));
+                    // every lane holds the warp's Gram pairs in natural proposal order only where
+                    // perm == 0 (lanes 0..3): lane 0 publishes them, two pairs per 8-byte unit
+                    if (lane == 0) {
+                        double *xg = (double *)(s_xg + (size_t)xb * GWC * 32 + (size_t)gw * 32);
+#pragma unroll
+                        for (int i = 0; i < NGP; i += 2) {
+                            const float g1 = i + 1 < NGP ? gq[(i + 1) % NGP] : 0.f;
+                            xsend8(xg + (i >> 1), xbar, C, __hiloint2double(__float_as_int(g1), __float_as_int(gq[i])));
+                        }
+                    }
+                }
+            } else if (Kb >= FGRP) {
+                const int e0 = (int)step & (RING - 1);
+                for (int k0 = grp * FGRP; k0 < Kb; k0 += PS * FGRP) {
+                    const long long ptk = a.prof ? clock64() : 0;
+                    float acc[FGRP][4];
+                    float dn[CACHE ? FGRP : 1][QPT], od[CACHE ? FGRP : 1][QPT];
+                    if (CACHE) {
+                        // old rows first (L2 latency hides behind the new evaluations)
+#pragma unroll
                         for (int s = 0; s < FGRP; ++s) {
-                            int ri = ri0 + (s ^ perm);
+                            int ri = ri0 + k0 + (s ^ perm);
                             if (ri >= N) ri -= N;
                             row_load<QPT>(crow + (size_t)ri * RL, od[CACHE ? s : 0]);
                         }
                         int ent[FGRP];
 #pragma unroll
-                        for (int s = 0; s < FGRP; ++s) ent[s] = (e0 + (s ^ perm)) & (RING - 1);
+                        for (int s = 0; s < FGRP; ++s) ent[s] = (e0 + k0 + (s ^ perm)) & (RING - 1);
                         FO::template evalChunk<QPT, CACHE ? FGRP : 1>(s_ring, (const int (&)[CACHE ? FGRP : 1])ent,
-                                                                      s_nodes, NSTR, qt, Q, dnk);
+                                                                      s_nodes, NSTR, qt, Q, dn);
                     }
-#pragma unroll
-                    for (int i = 0; i < NGP; ++i) gq[i] = 0.f;
 #pragma unroll
                     for (int s = 0; s < FGRP; ++s) {
                         acc[s][0] = 0.f; acc[s][1] = 0.f; acc[s][2] = 0.f; acc[s][3] = 0.f;
-                        const int e = (e0 + (s ^ perm)) & (RING - 1);
-                        const Contrib<float> cn = s_ring[e].cn, co = s_ring[e].co;
-                        const float *nn = s_nodes + (size_t)(e * 2) * NSTR, *no = nn + NSTR;
                         float dd[QPT];
                         if (CACHE) {
 #pragma unroll
-                            for (int j = 0; j < QPT; ++j) dd[j] = dnk[CACHE ? s : 0][j] - od[CACHE ? s : 0][j];
+                            for (int j = 0; j < QPT; ++j) dd[j] = dn[CACHE ? s : 0][j] - od[CACHE ? s : 0][j];
                         } else {
-                            FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd);
+                            const int k = k0 + (s ^ perm);
+                            const int e = (e0 + k) & (RING - 1);
+                            const Contrib<float> cn = s_ring[e].cn, co = s_ring[e].co;
+                            const float *nn = s_nodes + (size_t)(e * 2) * NSTR, *no = nn + NSTR;
+                            FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd);  // mcsas.py:360-362
                         }
 #pragma unroll
                         for (int j = 0; j < QPT; ++j) {
-                            const float u = cq[j] * dd[j];
-                            uu[s][j] = u;
+                            float u = cq[j] * dd[j];                     // (new - old)/sigma, :366
                             acc[s][0] = fmaf(rho[j], u, acc[s][0]);
                             acc[s][1] = fmaf(u, u, acc[s][1]);
                             acc[s][2] = fmaf(mu[j], u, acc[s][2]);
                             acc[s][3] = fmaf(om[j], u, acc[s][3]);
-#pragma unroll
-                            for (int t = 0; t < s; ++t)
-                                gq[tri_idx<FGRP>(t, s)] = fmaf(uu[t][j], u, gq[tri_idx<FGRP>(t, s)]);
                         }
                     }
-                    if (grp == 0) {
+                    // select-free reduce-scatter: slot s of lane l holds proposal s ^ perm(l)
 #pragma unroll
-                        for (int h = FGRP / 2, off = 16; h >= 1; h >>= 1, off >>= 1) {
+                    for (int h = FGRP / 2, off = 16; h >= 1; h >>= 1, off >>= 1) {
 #pragma unroll
-                            for (int s = 0; s < h; ++s)
-#pragma unroll
-                                for (int i = 0; i < 4; ++i)
-                                    acc[s][i] += __shfl_xor_sync(0xffffffffu, acc[s + h][i], off);
-                            // Gram: all-reduce with the slot permutation of the partner lane
-                            float tmp[NGP];
-#pragma unroll
-                            for (int t = 0; t < FGRP; ++t)
-#pragma unroll
-                                for (int s2 = t + 1; s2 < FGRP; ++s2)
-                                    tmp[tri_idx<FGRP>(t, s2)] =
-                                        __shfl_xor_sync(0xffffffffu, gq[tri_idx<FGRP>(t ^ h, s2 ^ h)], off);
-#pragma unroll
-                            for (int i = 0; i < NGP; ++i) gq[i] += tmp[i];
-                        }
-#pragma unroll
-                        for (int off = 32 / FGRP / 2; off >= 1; off >>= 1) {
+                        for (int s = 0; s < h; ++s)
 #pragma unroll
                             for (int i = 0; i < 4; ++i)
-                                acc[0][i] += __shfl_xor_sync(0xffffffffu, acc[0][i], off);
-#pragma unroll
-                            for (int i = 0; i < NGP; ++i) gq[i] += __shfl_xor_sync(0xffffffffu, gq[i], off);
-                        }
-                        if ((lane & (32 / FGRP - 1)) == 0)
-                            s_wsum[wq * FAST_KCAP + perm] = make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
-                        if (lane == 0) {                          // perm == 0: natural proposal order
-#pragma unroll
-                            for (int i = 0; i < NGP; ++i) s_gram[wq * NGP + i] = gq[i];
-                        }
+                                acc[s][i] += __shfl_xor_sync(0xffffffffu, acc[s + h][i], off);
                     }
-                } else if (Kb >= FGRP) {
-                    const int e0 = (int)step & (RING - 1);
-                    for (int k0 = grp * FGRP; k0 < Kb; k0 += PS * FGRP) {
-                        const long long ptk = a.prof ? clock64() : 0;
-                        float acc[FGRP][4];
-                        float dn[CACHE ? FGRP : 1][QPT], od[CACHE ? FGRP : 1][QPT];
-                        if (CACHE) {
-                            // old rows first (L2 latency hides behind the new evaluations)
 #pragma unroll
-                            for (int s = 0; s < FGRP; ++s) {
-                                int ri = ri0 + k0 + (s ^ perm);
-                                if (ri >= N) ri -= N;
-                                row_load<QPT>(crow + (size_t)ri * RL, od[CACHE ? s : 0]);
-                            }
-                            int ent[FGRP];
+                    for (int off = 32 / FGRP / 2; off >= 1; off >>= 1)
 #pragma unroll
-                            for (int s = 0; s < FGRP; ++s) ent[s] = (e0 + k0 + (s ^ perm)) & (RING - 1);
-                            FO::template evalChunk<QPT, CACHE ? FGRP : 1>(s_ring, (const int (&)[CACHE ? FGRP : 1])ent,
-                                                                          s_nodes, NSTR, qt, Q, dn);
-                        }
+                        for (int i = 0; i < 4; ++i)
+                            acc[0][i] += __shfl_xor_sync(0xffffffffu, acc[0][i], off);
+                    if ((lane & (32 / FGRP - 1)) == 0)
+                        xsend16(xp + k0 + perm, xbar, C, make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]));
+                    if (a.prof) { ptc[k0 == 0 ? 0 : 1] += clock64() - ptk; ptc[k0 == 0 ? 2 : 3] += 1; }
+                }
+            } else if (grp == 0) {
+                for (int k = 0; k < Kb; ++k) {
+                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                    const int e = ((int)step + k) & (RING - 1);
+                    const Contrib<float> cn = s_ring[e].cn, co = s_ring[e].co;
+                    const float *nn = s_nodes + (size_t)(e * 2) * NSTR, *no = nn + NSTR;
+                    float dd[QPT];
+                    if (CACHE) {
+                        int ri = ri0 + k;
+                        if (ri >= N) ri -= N;
+                        FO::template evalN<QPT>(cn, nn, qt, Q, dd);
+                        float ov[QPT];
+                        row_load<QPT>(crow + (size_t)ri * RL, ov);
 #pragma unroll
-                        for (int s = 0; s < FGRP; ++s) {
-                            acc[s][0] = 0.f; acc[s][1] = 0.f; acc[s][2] = 0.f; acc[s][3] = 0.f;
-                            float dd[QPT];
-                            if (CACHE) {
-#pragma unroll
-                                for (int j = 0; j < QPT; ++j) dd[j] = dn[CACHE ? s : 0][j] - od[CACHE ? s : 0][j];
-                            } else {
-                                const int k = k0 + (s ^ perm);
-                                const int e = (e0 + k) & (RING - 1);
-                                const Contrib<float> cn = s_ring[e].cn, co = s_ring[e].co;
-                                const float *nn = s_nodes + (size_t)(e * 2) * NSTR, *no = nn + NSTR;
-                                FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd);  // mcsas.py:360-362
-                            }
-#pragma unroll
-                            for (int j = 0; j < QPT; ++j) {
-                                float u = cq[j] * dd[j];                     // (new - old)/sigma, :366
-                                acc[s][0] = fmaf(rho[j], u, acc[s][0]);
-                                acc[s][1] = fmaf(u, u, acc[s][1]);
-                                acc[s][2] = fmaf(mu[j], u, acc[s][2]);
-                                acc[s][3] = fmaf(om[j], u, acc[s][3]);
-                            }
-                        }
-                        // select-free reduce-scatter: slot s of lane l holds proposal s ^ perm(l)
-#pragma unroll
-                        for (int h = FGRP / 2, off = 16; h >= 1; h >>= 1, off >>= 1) {
-#pragma unroll
-                            for (int s = 0; s < h; ++s)
-#pragma unroll
-                                for (int i = 0; i < 4; ++i)
-                                    acc[s][i] += __shfl_xor_sync(0xffffffffu, acc[s + h][i], off);
-                        }
-#pragma unroll
-                        for (int off = 32 / FGRP / 2; off >= 1; off >>= 1)
-#pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                acc[0][i] += __shfl_xor_sync(0xffffffffu, acc[0][i], off);
-                        if ((lane & (32 / FGRP - 1)) == 0)
-                            s_wsum[wq * FAST_KCAP + k0 + perm] = make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]);
-                        if (a.prof) { ptc[k0 == 0 ? 0 : 1] += clock64() - ptk; ptc[k0 == 0 ? 2 : 3] += 1; }
+                        for (int j = 0; j < QPT; ++j) dd[j] -= ov[j];
+                    } else {
+                        FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd);
                     }
-                } else if (grp == 0) {
-                    for (int k = 0; k < Kb; ++k) {
-                        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                        const int e = ((int)step + k) & (RING - 1);
-                        const Contrib<float> cn = s_ring[e].cn, co = s_ring[e].co;
-                        const float *nn = s_nodes + (size_t)(e * 2) * NSTR, *no = nn + NSTR;
-                        float dd[QPT];
-                        if (CACHE) {
-                            int ri = ri0 + k;
-                            if (ri >= N) ri -= N;
-                            FO::template evalN<QPT>(cn, nn, qt, Q, dd);
-                            float ov[QPT];
-                            row_load<QPT>(crow + (size_t)ri * RL, ov);
 #pragma unroll
-                            for (int j = 0; j < QPT; ++j) dd[j] -= ov[j];
-                        } else {
-                            FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd);
-                        }
-#pragma unroll
-                        for (int j = 0; j < QPT; ++j) {
-                            float u = cq[j] * dd[j];
-                            acc[0] = fmaf(rho[j], u, acc[0]);
-                            acc[1] = fmaf(u, u, acc[1]);
-                            acc[2] = fmaf(mu[j], u, acc[2]);
-                            acc[3] = fmaf(om[j], u, acc[3]);
-                        }
-#pragma unroll
-                        for (int off = 16; off >= 1; off >>= 1)
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
-                        if (lane == 0) s_wsum[wq * FAST_KCAP + k] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+                    for (int j = 0; j < QPT; ++j) {
+                        float u = cq[j] * dd[j];
+                        acc[0] = fmaf(rho[j], u, acc[0]);
+                        acc[1] = fmaf(u, u, acc[1]);
+                        acc[2] = fmaf(mu[j], u, acc[2]);
+                        acc[3] = fmaf(om[j], u, acc[3]);
                     }
+                    // the same shuffle tree as the chunk evaluator's (lane bits 4..0), so that a
+                    // proposal's sums do not depend on the size of the batch it was evaluated in
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+                    if (lane == 0) xsend16(xp + k, xbar, C, make_float4(acc[0], acc[1], acc[2], acc[3]));
                 }
             }
-            if (wd && lane == 0) s_dec->wd = 1;                  // any warp may raise it
+            if (C == 1) {                                        // this warp's part of the batch is in shared memory
+                __syncwarp();
+                if (lane == 0) mbar_arrive_release(xbar);
+            }
             const long long pt2 = a.prof ? clock64() : 0;
-            named_bar_sync(1, T);                                // B1: eval warps only
-            const long long pt3 = a.prof ? clock64() : 0;
-            wd = s_dec->wd != 0;
             // ---- the last warp prepares the ring entries of the NEXT batch while warp 0 decides:
             // steps [filled, step + Kb + kmax); their slots held steps <= step - RING/2 (consumed),
             // and the contributions they replace are not touched by this batch (Kb + kmax < N)
@@ -899,96 +986,49 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             if (warp == W - 1 && W > 1)
                 for (long long t = fill_from + lane; t < fill_to; t += 32) fill_entry(t, attempt, sbase);
             filled = max(filled, fill_to);
-            // ---- exchange the partial sums over the cluster (st.async + mbarrier) -------------
-            // units of a rank's exchange row: [0, 2K) two floats each of the proposal sums,
-            // [2 FAST_KCAP, +5) base sums, [2 FAST_KCAP + 5] watchdog flag, [2 FAST_KCAP + 8, +NGU) Gram pairs
-            double *part = s_part + (size_t)abuf * MAX_CLUSTER * XU;
-            const int nb5 = dirty ? 5 : 0;
-            if (C > 1) {
-                const int nprop = 2 * Kb, ngu = gram ? NGU : 0, nval = nprop + nb5 + 1 + ngu;
-                if (tid == 0) mbar_expect_tx(s_xbar + abuf, (uint32_t)(C * nval * 8));
-                for (int i = tid; i < nval; i += T) {
-                    double x;
-                    int du;
-                    if (i < nprop) {                             // two floats of proposal i/2
-                        const float *src = (const float *)s_wsum + (size_t)(i >> 1) * 4 + (i & 1) * 2;
-                        float x0 = 0.f, x1 = 0.f;
-                        for (int wv = 0; wv < WQ; ++wv) { x0 += src[(size_t)wv * FAST_KCAP * 4]; x1 += src[(size_t)wv * FAST_KCAP * 4 + 1]; }
-                        x = __hiloint2double(__float_as_int(x1), __float_as_int(x0));
-                        du = i;
-                    } else if (i < nprop + nb5) {
-                        x = 0.;
-                        for (int wv = 0; wv < WQ; ++wv) x += s_bsum[wv * 6 + (i - nprop)];
-                        du = 2 * FAST_KCAP + (i - nprop);
-                    } else if (i == nprop + nb5) {
-                        x = wd ? 1. : 0.;
-                        du = 2 * FAST_KCAP + 5;
-                    } else {                                     // two Gram pairs
-                        const int g = 2 * (i - nprop - nb5 - 1);
-                        float x0 = 0.f, x1 = 0.f;
-                        for (int wv = 0; wv < WQ; ++wv) {
-                            x0 += s_gram[wv * NGP + g];
-                            if (g + 1 < NGP) x1 += s_gram[wv * NGP + g + 1];
-                        }
-                        x = __hiloint2double(__float_as_int(x1), __float_as_int(x0));
-                        du = 2 * FAST_KCAP + 8 + (g >> 1);
-                    }
-                    double *dst = part + (size_t)rank * XU + du;
-                    for (int r = 0; r < C; ++r) dsmem_store_async(dst, s_xbar + abuf, (uint32_t)r, x);
-                }
-                if (warp == 0) {
-                    mbar_wait(s_xbar + abuf, (xphase >> abuf) & 1);
-                    bool anywd = false;
-                    for (int r = 0; r < C; ++r) anywd |= part[(size_t)r * XU + 2 * FAST_KCAP + 5] != 0.;
-                    wd = anywd;
-                }
-                xphase ^= 1u << abuf;
-            }
             long long pd[4] = {0, 0, 0, 0};
+            const long long pt3 = a.prof ? clock64() : 0;
             if (warp == 0) {
+                if (C > 1 && lane == 0) {                        // bytes this rank receives per batch
+                    const uint32_t per_gw = (uint32_t)(Kb * 16 + 8 + (dirty ? 40 : 0) + (gram ? ((NGP + 1) / 2) * 8 : 0));
+                    mbar_expect_tx(xbar, (uint32_t)GW * per_gw);
+                }
+                mbar_wait(xbar, (xphase >> xb) & 1);             // every warp's partial sums have landed
                 if (a.prof) pd[0] = clock64();
-                if (dirty) {                                     // fresh base sums: lane i < 5 adds quantity i
+                const double *allb = s_xb + (size_t)xb * GWC * 8;
+                {
+                    // lane i < 5: base sum i (fresh only after a move), lane 5: launch budget flag;
+                    // ascending global-warp order
                     double x = 0.;
-                    if (lane < 5) {
-                        if (C > 1) { for (int r = 0; r < C; ++r) x += part[(size_t)r * XU + 2 * FAST_KCAP + lane]; }
-                        else { for (int wv = 0; wv < WQ; ++wv) x += s_bsum[wv * 6 + lane]; }
+                    if (lane < 6 && (dirty || lane == 5))
+                        for (int g = 0; g < GW; ++g) x += allb[g * 8 + lane];
+                    const double fl = __shfl_sync(0xffffffffu, x, 5);
+                    if (fl != 0.) slice_over = true;
+                    if (dirty) {
+                        B.E0 = __shfl_sync(0xffffffffu, x, 0); B.E1 = __shfl_sync(0xffffffffu, x, 1);
+                        B.E2 = __shfl_sync(0xffffffffu, x, 2); B.Sm = __shfl_sync(0xffffffffu, x, 3);
+                        B.Smm = __shfl_sync(0xffffffffu, x, 4);
+                        B.a0 = a0; B.b0 = b0;
+                        // the centre is the fit of this state up to the fp32 error of the delta sums:
+                        // chi2 at the centre exceeds the minimum by O(1e-14) relative
+                        conval = B.E0 * L.inv_nq;
                     }
-                    B.E0 = __shfl_sync(0xffffffffu, x, 0); B.E1 = __shfl_sync(0xffffffffu, x, 1);
-                    B.E2 = __shfl_sync(0xffffffffu, x, 2); B.Sm = __shfl_sync(0xffffffffu, x, 3);
-                    B.Smm = __shfl_sync(0xffffffffu, x, 4);
-                    B.a0 = a0; B.b0 = b0;
-                    // the centre is the fit of this state up to the fp32 error of the delta sums:
-                    // chi2 at the centre exceeds the minimum by O(1e-14) relative
-                    conval = B.E0 * L.inv_nq;
                 }
                 if (a.prof) pd[1] = clock64();
                 // lane l owns proposals l and l + 32 (second round only for batches of 64)
                 float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, t4 = 0.f;
-                const bool mine = lane < Kb && !wd, mine2 = lane + 32 < Kb && !wd;
+                const bool mine = lane < Kb, mine2 = lane + 32 < Kb;
+                const float4 *allp = s_xp + (size_t)xb * GWC * FAST_KCAP;
                 if (mine) {
-                    if (C > 1) {
-                        for (int r = 0; r < C; ++r) {
-                            const float4 v = *(const float4 *)(part + (size_t)r * XU + 2 * lane);
-                            s1 += v.x; s2 += v.y; s3 += v.z; s4 += v.w;
-                        }
-                    } else {
-                        for (int wv = 0; wv < WQ; ++wv) {
-                            const float4 v = s_wsum[wv * FAST_KCAP + lane];
-                            s1 += v.x; s2 += v.y; s3 += v.z; s4 += v.w;
-                        }
+                    for (int g = 0; g < GW; ++g) {
+                        const float4 v = allp[(size_t)g * FAST_KCAP + lane];
+                        s1 += v.x; s2 += v.y; s3 += v.z; s4 += v.w;
                     }
                 }
                 if (mine2) {
-                    if (C > 1) {
-                        for (int r = 0; r < C; ++r) {
-                            const float4 v = *(const float4 *)(part + (size_t)r * XU + 2 * (lane + 32));
-                            t1 += v.x; t2 += v.y; t3 += v.z; t4 += v.w;
-                        }
-                    } else {
-                        for (int wv = 0; wv < WQ; ++wv) {
-                            const float4 v = s_wsum[wv * FAST_KCAP + lane + 32];
-                            t1 += v.x; t2 += v.y; t3 += v.z; t4 += v.w;
-                        }
+                    for (int g = 0; g < GW; ++g) {
+                        const float4 v = allp[(size_t)g * FAST_KCAP + lane + 32];
+                        t1 += v.x; t2 += v.y; t3 += v.z; t4 += v.w;
                     }
                 }
                 if (a.prof) pd[2] = clock64();
@@ -1023,21 +1063,17 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                         cc = __shfl_sync(0xffffffffu, chi, kl);
                     }
                 } else {
-                    // Gram totals over warps / ranks
+                    // Gram totals over the chain's warps (ascending global-warp order)
+                    const float *allg = s_xg + (size_t)xb * GWC * 32;
                     for (int i = lane; i < NGP; i += 32) {
                         float v = 0.f;
-                        if (C > 1) {
-                            for (int r = 0; r < C; ++r) v += ((const float *)(part + (size_t)r * XU + 2 * FAST_KCAP + 8))[i];
-                        } else {
-                            for (int wv = 0; wv < WQ; ++wv) v += s_gram[wv * NGP + i];
-                        }
+                        for (int g = 0; g < GW; ++g) v += allg[g * 32 + i];
                         s_gtot[i] = v;
                     }
                     __syncwarp();
                     int pos = 0;
-                    gused = Kb;
                     double g1 = s1, g2 = s2, g3 = s3, g4 = s4;      // fp64 copies updated per accepted move
-                    for (int it = 0; it <= FGRP && !wd; ++it) {
+                    for (int it = 0; it <= FGRP; ++it) {
                         double rss = 0., an = 0., bn = 0., e1 = 0., e2 = 0.;
                         bool better = false;
                         if (mine && lane >= pos) {
@@ -1056,9 +1092,9 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                         const double s4i = __shfl_sync(0xffffffffu, g4, i);
                         const double da = ai - B.a0, db = bi - B.b0;
                         if (mine && lane > i) {                  // sums of later proposals w.r.t. the new state
-                            const double G = (double)s_gtot[tri_idx_rt(FGRP, i, lane)];
-                            g1 = g1 - da * g3 - ai * G - db * g4;
-                            g3 += G;
+                            const double Gp = (double)s_gtot[tri_idx_rt(FGRP, i, lane)];
+                            g1 = g1 - da * g3 - ai * Gp - db * g4;
+                            g3 += Gp;
                         }
                         B.Sm += s4i; B.Smm += 2. * s3i + s2i;
                         B.E0 = ri; B.E1 = e1i; B.E2 = e2i; B.a0 = ai; B.b0 = bi;
@@ -1076,7 +1112,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     s_dec->kstar = ks;
                     s_dec->accmask = accmask;
                     s_dec->used = gused;
-                    s_dec->wd = wd ? 2 : 0;
+                    s_dec->wd = slice_over ? 1 : 0;
                     s_dec->a = ca;                               // centre of the state after this batch
                     s_dec->b = cb;
                     s_dec->conval = cc;
@@ -1084,15 +1120,16 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             }
             if (W == 1)                                          // one-warp CTA: fill after deciding
                 for (long long t = fill_from + lane; t < fill_to; t += 32) fill_entry(t, attempt, sbase);
-            abuf ^= 1;
+            xphase ^= 1u << xb;
+            xb_ = xb ^ 1;
             const long long pt4 = a.prof ? clock64() : 0;
-            named_bar_sync(1, T);                                // B2
+            named_bar_sync(1, T);                                // B2: the decision is published
             const long long pt5 = a.prof ? clock64() : 0;
-            if (s_dec->wd == 2) { status = -2; break; }
             const int kstar = s_dec->kstar;
             const int accmask = s_dec->accmask;
             const int used = gram ? s_dec->used : (kstar >= 0 ? kstar + 1 : Kb);
             conval = s_dec->conval;
+            slice_over = s_dec->wd != 0;
             if (a.trace_accept && rank == 0) {
                 for (int k = tid; k < used; k += T) {
                     a.trace_accept[(long long)chain * a.max_iter + step + k] = gram ? ((accmask >> k) & 1) : (k == kstar);
@@ -1138,9 +1175,10 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     }
                     moves += __popc(accmask);
                     dirty = true;
-                    K = FGRP;
+                    last_acc = step + (31 - __clz(accmask));
                 } else {
-                    K = min(kmax, 2 * FGRP);                     // no move in a whole chunk: speculate
+                    gmode = false;                               // no move in a whole chunk: speculate
+                    K = min(kmax, 2 * FGRP);
                 }
             } else if (kstar >= 0) {                             // mcsas.py:381-384
                 a0 = s_dec->a; b0 = s_dec->b;
@@ -1175,6 +1213,8 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                 ++moves;
                 evals += 2;
                 dirty = true;
+                gmode = step + kstar - last_acc <= FGRP;
+                last_acc = step + kstar;
                 K = max(1, min(kmax, 1 << (31 - __clz(kstar + 1))));
             } else {
                 K = min(kmax, K * 2);
@@ -1185,24 +1225,35 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             if (a.prof && tid == 0 && rank == 0) {               // phase cycles of warp 0 (tools/prof)
                 long long *pp = a.prof + ((long long)chain * 2 + (gram ? 1 : 0)) * 24;
                 pp[16] += pd[3] - pd[2]; pp[17] += pt4 - pd[3];
-                pp[13] += pd[0] - pt3; pp[14] += pd[1] - pd[0]; pp[15] += pd[2] - pd[1]; pp[5] += 0;
+                pp[13] += pd[0] - pt3; pp[14] += pd[1] - pd[0]; pp[15] += pd[2] - pd[1];
                 pp[8] += pt1a - pt1; pp[9] += ptc[0]; pp[10] += ptc[1]; pp[11] += ptc[2]; pp[12] += ptc[3];
                 pp[0] += pt1 - pt0; pp[1] += pt2 - pt1; pp[2] += pt3 - pt2; pp[3] += pt4 - pt3;
                 pp[4] += pt5 - pt4; pp[5] += clock64() - pt5; pp[6] += 1; pp[7] += used;
             }
-            live = conval > a.conv_crit && step < a.max_iter && step < slice_end && batch < batch_end;
-        }
+            slice_over = slice_over || step >= slice_end || batch >= batch_end;
+            live = conval > a.conv_crit && step < a.max_iter && !slice_over;
         }
         __syncthreads();
-        // ---- final fit of the accepted state (mcsas.py:424-425) --------------------------------
+        // ---- exact fit of the accepted state (mcsas.py:424-425) --------------------------------
+        cv_run = conval;                                         // what the accept test compares against
         lsq_all(sc_a, sc_b, conval);
         if (status == -2) break;
+        // the running chi-squared crossed the criterion on fp32 delta sums but the exact fit has
+        // not: the chain goes on from the exact value (whether or not a launch ends here)
+        if (N > 1 && cv_run <= a.conv_crit && conval > a.conv_crit && step < a.max_iter) {
+            cv_run = conval;
+            dirty = true;
+            if (!slice_over) { live = true; continue; }
+        }
+        break;
+        }
+        if (status == -2) break;
         const bool running = (N > 1 && conval > a.conv_crit && step < a.max_iter);
-        if (running) { status = 0; break; }                      // slice ended: resume later
+        if (running) { status = 0; break; }                      // this launch's budget ended: resume later
         status = 1;
         if (conval <= a.conv_crit || a.stream || attempt + 1 >= a.max_attempts || N <= 1)
             break;
-        if (a.slice_steps > 0) {                                 // retry (mcsas.py:220-246) in a later slice
+        if (a.slice_steps > 0 || a.slice_ns > 0) {               // retry (mcsas.py:220-246) in a later launch
             status = 2; ++attempt; step = 0; moves = 0;
             break;
         }
@@ -1216,9 +1267,11 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
 #pragma unroll
         for (int j = 0; j < QPT; ++j) {
             int i = (rank * TQ + qtid) * QPT + j;
-            if (i < nq)
-                a.fit_meas[(long long)chain * a.nq_stride + i] =
-                    (s_ft[cur * FAST_QCAP + qtid * QPT + j] * sc_a + sc_b) * ds.i_scale;                 // mcsas.py:429
+            if (i < nq) {
+                const double f = s_ft[cur * FAST_QCAP + qtid * QPT + j];
+                a.fit_meas[(long long)chain * a.nq_stride + i] = (f * sc_a + sc_b) * ds.i_scale;         // mcsas.py:429
+                if (status == 0) a.ft_save[(long long)chain * a.nq_stride + i] = f;
+            }
         }
     }
     if (tid == 0 && rank == 0) {
@@ -1227,6 +1280,9 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         a.background[chain] = sc_b * ds.i_scale;
         a.conval[chain] = conval;
         a.conval0[chain] = conval0;
+        a.cen_a[chain] = a0; a.cen_b[chain] = b0; a.cv_run[chain] = cv_run;
+        a.batch_k[chain] = K | (gmode ? 1 << 16 : 0);
+        a.last_acc[chain] = (double)last_acc;
         a.num_iter[chain] = step;
         a.num_moves[chain] = moves;
         a.evals[chain] = evals;

@@ -64,6 +64,8 @@ struct ChainArgs {
     int resume;                  // 1: continue from the saved state (rset, counters)
     long long slice_steps;       // MC steps per chain in this launch, 0 = run to the end
     int slice_batches;           // fp32 kernel: batches per chain in this launch (0 = no limit)
+    long long slice_ns;          // fp32 kernel: time budget of this launch per chain in ns (0 = no limit)
+    int gw_cap;                  // fp32 kernel: capacity (in warps of a whole chain) of the exchange buffers
     const int *chain_ids;        // chains of this launch (grid = n * cluster) or NULL
     int *status;                 // per chain: 1 finished, 0 needs another slice
     int first_chain;
@@ -83,6 +85,12 @@ struct ChainArgs {
     double *scaling, *background, *conval, *conval0, *elapsed_s;
     long long *num_iter, *num_moves, *evals, *steps_all;
     int *attempts;
+    // fp32 kernel: what a chain carries across launches besides rset and the counters
+    double *ft_save;             // [chain][nq_stride] fp64 master copy of the model intensity
+    double *cen_a, *cen_b;       // centre of the quadratic expansion (fit of the last accepted state)
+    double *cv_run;              // chi-squared the accept test compares against
+    double *last_acc;            // step of the last accepted move (decides which batches are Gram batches)
+    int *batch_k;                // speculative batch size | Gram mode << 16
     unsigned char *trace_accept; // [chain][max_iter] or NULL
     double *trace_chi;           // [chain][max_iter] or NULL
     float *cache;                // fp32 kernel: NULL or [SM id][cache_stride] contribution rows
@@ -144,10 +152,20 @@ __host__ __device__ inline size_t chain_smem_bytes(int nq_pad, int N, int P, int
 #define FAST_MAX_WARPS 32
 #define FAST_KCAP 64               // fp32 kernel: speculative proposals per batch (2 per decision lane)
 #define FAST_RING_MAX 256          // ... ring entries (>= 4 * FAST_KCAP)
-#define FAST_XU (2 * FAST_KCAP + 8 + 16) // 64-bit units per rank in a cluster exchange buffer
 #define FAST_CACHE_SMS 256         // row regions allocated (>= %nsmid of a B200)
 #define FAST_QCAP 1024            // q points per CTA (QPT * 32 * warps_q)
-__host__ __device__ inline size_t fast_smem_bytes(int nq_pad, int N, int P, int D, int narr, int ring)
+// warps of a whole chain (cluster size x warps per CTA slice) for the largest layout the planner
+// may choose: the q slice of a CTA is a whole number of warps of 32 * 4 q points
+__host__ __device__ inline int fast_gw_cap(int nq)
+{
+    int cap = 1;
+    for (int c = 1; c <= MAX_CLUSTER; c *= 2) {
+        const int n = (nq + c - 1) / c, wq = (n + 127) / 128;
+        if (c * wq > cap) cap = c * wq;
+    }
+    return cap;
+}
+__host__ __device__ inline size_t fast_smem_bytes(int nq_pad, int N, int P, int D, int narr, int ring, int gw_cap)
 {
 #define AL16(b) ((((size_t)(b)) + 15) & ~size_t(15))
     size_t s = 16;                                               // mbarrier
@@ -155,17 +173,16 @@ __host__ __device__ inline size_t fast_smem_bytes(int nq_pad, int N, int P, int 
     s += AL16(8 * (size_t)N * (P > 0 ? P : 1));                  // rset
     s += AL16(64);                                               // ctrl
     s += AL16((size_t)ring * (8 * MCSAS_MAX_ACTIVE + 2 * 4 * 8));// ring entries
-    s += AL16(16 * (size_t)FAST_MAX_WARPS * FAST_KCAP);          // per-warp proposal sums (float4)
-    s += AL16(8 * (size_t)(FAST_MAX_WARPS + 1) * 6);             // per-warp base sums
-    s += AL16(8 * 2 * (size_t)MAX_CLUSTER * FAST_XU);            // cluster exchange, 2 buffers
-    s += AL16(4 * (size_t)FAST_MAX_WARPS * 28) + AL16(4 * 32);   // Gram pairs per warp + totals
+    s += AL16(16 * 2 * (size_t)gw_cap * FAST_KCAP);              // exchange: per-warp proposal sums (float4), 2 buffers
+    s += AL16(8 * 2 * (size_t)gw_cap * 8);                       // exchange: per-warp base sums + flags
+    s += AL16(4 * 2 * (size_t)gw_cap * 32);                      // exchange: per-warp Gram pairs
     s += 16;                                                     // exchange mbarriers
+    s += AL16(4 * 32);                                           // Gram totals
     s += AL16(8 * (size_t)FAST_KCAP + 128);                      // chi per proposal + decision
-    s += AL16(8 * (size_t)(FAST_MAX_WARPS + 2) * 3 + 8 * 2 * MAX_CLUSTER * 3);   // full-LSQ all-sum
+    s += AL16(8 * 2 * (size_t)gw_cap * 3);                       // full-LSQ all-sum
     s += AL16(8 * 2 * FAST_QCAP) + 2 * AL16(8 * FAST_QCAP) + AL16(4 * FAST_QCAP);   // ft (x2), I, 1/sigma, q scale
     s += 2 * AL16(4 * (size_t)(D + 1));                          // quadrature table
     s += AL16(4 * (size_t)ring * 2 * narr * D) + 16;             // node arrays
     return s;
 #undef AL16
 }
-

@@ -15,9 +15,6 @@
 template <class Real, int QPT, bool SMEAR> struct KernelOf {
     static auto get() { return chain_kernel<MODEL_ID, Real, QPT>; }
 };
-template <int QPT, bool SMEAR> struct KernelOf<float, QPT, SMEAR> {
-    static auto get() { return chain_fast_kernel<MODEL_ID, QPT, false, SMEAR && CanSmear<MODEL_ID>::value>; }
-};
 struct CachedF {};            // tag: fp32 production kernel with the contribution-row cache
 template <int QPT, bool SMEAR> struct KernelOf<CachedF, QPT, SMEAR> {
     static auto get() { return chain_fast_kernel<MODEL_ID, QPT, true, SMEAR && CanSmear<MODEL_ID>::value>; }
@@ -106,10 +103,8 @@ cudaError_t CAT(mcsas_launch_chain_, MODEL_ID)(int prec, int layout, int grid, i
 {
     if (prec == MCSAS_FP64) return launch_prec<double, false>(layout, grid, threads, smem, st, a);
     if (a.smear.n > 0)
-        return a.cache ? launch_prec<CachedF, true>(layout, grid, threads, smem, st, a)
-                       : launch_prec<float, true>(layout, grid, threads, smem, st, a);
-    return a.cache ? launch_prec<CachedF, false>(layout, grid, threads, smem, st, a)
-                   : launch_prec<float, false>(layout, grid, threads, smem, st, a);
+            return launch_prec<CachedF, true>(layout, grid, threads, smem, st, a);
+    return launch_prec<CachedF, false>(layout, grid, threads, smem, st, a);
 }
 
 cudaError_t CAT(mcsas_launch_eval_, MODEL_ID)(int prec, int grid, size_t smem, cudaStream_t st,

@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import McSASB200Error, RunConfig
+from ._lib import McSASB200Error, RunConfig, Tuning
 
 
 def _dp(a):
@@ -121,6 +121,15 @@ class Engine(object):
                          int(precision), int(seed) & 0xFFFFFFFFFFFFFFFF, int(spec_max),
                          int(bool(record_trace)), int(first_chain), int(cluster_size),
                          int(slice_steps))
+
+    def set_tuning(self, **kw):
+        """Experiment knobs of the scheduler / kernel (struct mcsas_tuning); no arguments: defaults."""
+        t = Tuning()
+        for k, v in kw.items():
+            if not hasattr(t, k):
+                raise McSASB200Error("unknown tuning knob %r" % k)
+            setattr(t, k, int(v))
+        self._check(self._L.mcsas_set_tuning(self._ctx, C.byref(t)), "set_tuning")
 
     def run_async(self, cfg, stream=None, stop_flag=None):
         """stop_flag: a ctypes.c_int the caller owns (kept alive until wait()); non-zero stops the

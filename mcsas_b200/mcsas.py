@@ -160,7 +160,7 @@ class McSAS(object):
             eng.set_smearing(*prof)
 
     def analyse(self):
-        """mcsas.py:191-285: numReps independent chains, retried up to maxRetries+2 times
+        """mcsas.py:191-285: numReps independent chains, retried up to maxRetries+1 attempts
         each; on failure the reference returns without results unless showIncomplete."""
         if not any(isActiveFitParam(p) for p in self.model.params()):
             raise ValueError("no active fit parameter: nothing to fit (mcsas.py:198-199)")
@@ -176,7 +176,7 @@ class McSAS(object):
         elif failed.any():
             logging.warning("Could not reach optimization criterion within {0} attempts "
                             "({1} of {2} repetitions), exiting..."
-                            .format(int(self.maxRetries()) + 2, int(failed.sum()), numReps))
+                            .format(int(self.maxRetries()) + 2, int(failed.sum()), numReps))   # (the reference's text)
             if not self.showIncomplete():
                 return
         contributions = out["contribs"][0]                    # [N, P, R]

@@ -86,10 +86,10 @@ def test_non_convergence_returns_no_result_unless_show_incomplete():
     algo.data = data
     algo.numReps.setValue(3)
     algo.maxIterations.setValue(200)          # cannot converge in 200 steps
-    algo.maxRetries.setValue(1)
+    algo.maxRetries.setValue(2)
     algo.calc()
     assert algo.result == []                  # mcsas.py:221-230
-    assert (algo.details["attempts"] == 3).all()      # maxRetries + 2 attempts
+    assert (algo.details["attempts"] == 3).all()      # maxRetries + 1 attempts (measured on the reference)
     algo.showIncomplete.setValue(True)
     algo.calc()
     assert len(algo.result) == 1 and (algo.result[0]["conval"] > 1.0).all()
