@@ -103,11 +103,14 @@ typedef struct mcsas_tuning {
     int max_cluster;   /* largest cluster the scheduler may give a chain: 0 = default (8), 1, 2, 4, 8 */
     int slice_us;      /* time budget of one launch per chain in microseconds, 0 = default */
     int backups;       /* speculative next attempts on idle SMs: 0 = default (on), -1 = off */
-    int backup_div;    /* start them when live chains * backup_div <= SMs, 0 = default (4) */
+    int backup_div;    /* start them when live chains * backup_div <= SMs, 0 = default (2) */
     int gram;          /* Gram batches: 0 = default (on), -1 = off */
     int qpt;           /* force q points per thread (1, 2, 4), 0 = auto */
     int profile;       /* 1: in-kernel phase cycle counters, printed to stderr by mcsas_wait */
     int verbose;       /* 1: one stderr line per time slice */
+    int backup_pct;    /* a chain gets a backup attempt from this percentage of maxIterations on, 0 = default (40) */
+    int late_steps;    /* chains with at least this many steps take the largest clusters first, by chi-squared:
+                          0 = default (never) */
 } mcsas_tuning;
 
 /* -- context ------------------------------------------------------------- */

@@ -572,17 +572,36 @@ static int launch_slice(mcsas_ctx *ctx, int n_live, bool resume)
         long long used = (long long)n_live << lowest;
         int cnt_at[4] = {0, 0, 0, 0};
         cnt_at[lowest] = n_live;
+        // Late chains first, as far as they can go: the chi-squared of a chain says little about its
+        // length before ~20 000 steps (tools/predict_len.py: rank correlation 0.0 at 10 000, 0.4 at
+        // 20 000, 0.7 at 40 000 steps); from then on the chains furthest from the criterion are the
+        // likely critical path (the ones that will use all maxIterations and need another attempt)
+        const long long late = ctx->tune.late_steps > 0 ? ctx->tune.late_steps : (1LL << 60);   // (measured: no gain on config 2, off by default)
+        if (ctx->pin_cap >= (size_t)ctx->n_slots && !ctx->h_conval.empty()) {
+            for (int i = 0; i < n_live; ++i) {
+                if (ctx->h_cnt[ctx->h_ids[i]] < late) continue;
+                for (int li = level[i] + 1; li < 4 && have[li]; ++li) {
+                    const int cost = (1 << li) / 2;
+                    if (used + cost > sms || cnt_at[li] + 1 > plans[li].resident) break;
+                    cnt_at[li]++; cnt_at[level[i]]--; level[i] = li; used += cost;
+                }
+            }
+        }
         for (int li = lowest + 1; li < 4 && used < sms; ++li) {
             if (!have[li]) break;
             const int step_cost = (1 << li) / 2;
             for (int i = 0; i < n_live && used + step_cost <= sms; ++i) {
-                if (level[i] >= li) continue;
-                if (level[i] != li - 1) break;                   // (sorted: upgrades form a prefix)
+                if (level[i] != li - 1) continue;
                 if (cnt_at[li] + 1 > plans[li].resident) break;  // co-resident clusters of this size
                 level[i] = li; cnt_at[li]++; cnt_at[li - 1]--;
                 used += step_cost;
             }
         }
+        // launches take contiguous id ranges: order by cluster size (stable: priority order within a size)
+        std::vector<int> idx(n_live), ids(ctx->h_ids.begin(), ctx->h_ids.begin() + n_live), lv(level);
+        for (int i = 0; i < n_live; ++i) idx[i] = i;
+        std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return lv[x] > lv[y]; });
+        for (int i = 0; i < n_live; ++i) { ctx->h_ids[i] = ids[idx[i]]; level[i] = lv[idx[i]]; }
     }
     CK(cudaMemcpyAsync(ctx->d_ids, ctx->h_ids.data(), sizeof(int) * n_live, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -902,13 +921,14 @@ extern "C" int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms)
         }
         // ---- start backups: few chains alive, SMs idle, chain is late in its attempt -------------
         bool new_backups = false;
-        const int bdiv = ctx->tune.backup_div > 0 ? ctx->tune.backup_div : 4;
+        const int bdiv = ctx->tune.backup_div > 0 ? ctx->tune.backup_div : 2;
         if (ctx->backups && n_primary > 0 && n_primary * bdiv <= ctx->prop.multiProcessorCount) {
             for (int c = 0; c < NC; ++c) {
                 if (ctx->done[c] || ctx->bak[c] >= 0) continue;
                 const int pslot = ctx->cur[c];
                 if (status[pslot] != 0 || attempts[pslot] >= ctx->max_attempts) continue;
-                if (2 * num_iter[pslot] < ctx->max_iter) continue;
+                const int bpct = ctx->tune.backup_pct > 0 ? ctx->tune.backup_pct : 40;
+                if (100 * num_iter[pslot] < (long long)bpct * ctx->max_iter) continue;
                 const int b = pslot < NC ? pslot + NC : pslot - NC;
                 // fresh state of the backup slot, uploaded below with the host copies
                 att[b] = attempts[pslot] + 1; att[(size_t)NS + b] = 2;

@@ -625,6 +625,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         if (resume) { step = a.num_iter[chain]; moves = a.num_moves[chain]; conval0 = a.conval0[chain]; }
     }
     const long long slice_end = a.slice_steps > 0 ? step + a.slice_steps : (1LL << 62);
+    unsigned long long budget_ns = 0;              // this launch's time budget (set once the rows are built)
 
     for (;; ++attempt) {
         // ---- contribution set: fresh draws (mcsas.py:310-317) or saved state ---------------
@@ -676,6 +677,12 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             __syncthreads();
         }
         if (!resume) evals += N;                                 // (rebuilding the rows of a resumed chain is not counted)
+        // a launch's time budget is at least 16 x what building the rows cost it (orientation-averaged
+        // and integral models: N evaluations are many MC steps' worth), so re-packing stays cheap
+        if (a.slice_ns > 0 && budget_ns == 0) {
+            const unsigned long long t_rows = globaltimer_ns() - t_start;
+            budget_ns = max((unsigned long long)a.slice_ns, 16ULL * t_rows);
+        }
         if (resume) {
             // continue exactly where the previous launch stopped: the fp64 master intensity, the
             // centre of the expansion, the running chi-squared and the batch size are part of the
@@ -780,7 +787,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     if (lane < 5) xsend8(xbs + lane, xbar, C, x);
                 }
                 if (lane == 5) {                                 // time budget of this launch (any warp may end it)
-                    const bool over = a.slice_ns > 0 && globaltimer_ns() - t_start > (unsigned long long)a.slice_ns;
+                    const bool over = a.slice_ns > 0 && globaltimer_ns() - t_start > budget_ns;
                     xsend8(xbs + 5, xbar, C, over ? 1. : 0.);
                 }
             }

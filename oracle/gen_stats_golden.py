@@ -139,6 +139,7 @@ def run_case(name, reps, procs):
                model=np.array(case["model"]), active=np.array([a[0] for a in case["active"]]),
                lo=np.array([a[1] for a in case["active"]]), hi=np.array([a[2] for a in case["active"]]),
                conv_crit=float(algo.convergenceCriterion()), comp_exp=float(algo.compensationExponent()),
+               seed0=case["seed0"],
                scaling=np.array([o["scaling"] for o in outs]),
                background=np.array([o["background"] for o in outs]),
                num_iter=np.array([o["num_iter"] for o in outs]),

@@ -21,8 +21,20 @@ from unittest.mock import MagicMock
 
 import numpy as np
 
-REFERENCE_SRC = "/root/reference/src"
-REFERENCE_TESTDATA = "/root/reference/testdata"
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_reference():
+    """/root/reference (build container) or the verbatim copy __graft_entry__.build() leaves in the
+    git-ignored oracle/_ref/ so that the reference arm of bench.py can time the UNMODIFIED reference on
+    the GPU box's host cores (it travels with gpurun like the built .so files; never committed)."""
+    for root in ("/root/reference", os.path.join(_HERE, "_ref")):
+        if os.path.isdir(os.path.join(root, "src", "mcsas")):
+            return os.path.join(root, "src"), os.path.join(root, "testdata")
+    return "/root/reference/src", "/root/reference/testdata"
+
+
+REFERENCE_SRC, REFERENCE_TESTDATA = _find_reference()
 
 
 def available():

@@ -55,6 +55,13 @@ if __name__ == "__main__":
     if "slice" in which:
         for us in [int(x) for x in os.environ.get("SLICE_US", "500,1000,1500,2000,3000").split(",")]:
             run("slice_us=%d" % us, {"slice_us": us}, seeds=(1, 2, 4, 7, 9, 11))
+    if "late" in which:
+        for d in (-1, 20000, 30000, 40000, 50000, -1):
+            run("late_steps=%d" % d, {"late_steps": d}, seeds=(1, 2, 4, 7, 9, 11))
+    if "backup" in which:
+        for pct in (30, 40, 50, 60):
+            for bd in (2, 4):
+                run("backup_pct=%d div=%d" % (pct, bd), {"backup_pct": pct, "backup_div": bd}, seeds=(1, 2, 4, 7, 9, 11))
     if "gram" in which:
         for g in (0, -1):
             run("gram=%d" % g, {"gram": g}, seeds=(1, 2, 4, 7, 9, 11))
