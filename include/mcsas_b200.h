@@ -192,6 +192,22 @@ int mcsas_fractions(mcsas_ctx *ctx, const mcsas_run_config *cfg, const double *c
                     double *min_vol, double *min_num, double *min_volsqr, double *min_surf,
                     double *totals, double *sc);
 
+/* -- data preparation of a BATCH of raw 1-D tables: replaces, per dataset,
+ *    DataObj._prepareUncertainty (dataobj/dataobj.py:204-226: sigma <- max(sigma, fu_min * I), invalid -> inf),
+ *    _initMask/_applyFMasks/_applyLimits (:239-269: finite I, fMaskZero / fMaskNeg, x0Low <= q <= x0High) and
+ *    DataObj._reBin (:288-345: log-spaced bins; one row: kept; several: means and max(SEM, propagated sigma);
+ *    empty bins dropped) -- bit-identical to the reference's numpy arithmetic (pairwise sums, row order).
+ *    q / intensity / sigma: the n_raw[s] rows of all tables concatenated, q in 1/m; sigma NULL = no uncertainty
+ *    column.  n_bin <= 0: no rebinning (DataConfig.nBin = 0).  edges [n_sets][n_bin + 1]: the bin edges in 1/m as
+ *    the reference computes them (numpy.logspace(log10(min q), log10(max q + last step / 100), n_bin + 1) over
+ *    the masked rows, :308-311) -- computed by the caller so that they are numpy's bits.
+ *    Outputs: nq_out[n_sets], and q_out / i_out / sigma_out [n_sets][cap] (cap >= n_bin, or >= the longest
+ *    table when n_bin <= 0); feed them to mcsas_upload_datasets. */
+int mcsas_prepare_datasets(mcsas_ctx *ctx, int n_sets, const int *n_raw, const double *q,
+                           const double *intensity, const double *sigma, double fu_min, double x0_low,
+                           double x0_high, int mask_zero, int mask_neg, int n_bin, const double *edges,
+                           int cap, int *nq_out, double *q_out, double *i_out, double *sigma_out);
+
 /* -- measured pipe peaks of this GPU for the FP32/SFU roofline (bench.py):
  *    MUFU (sin+cos+rcp mix) Gop/s and FP32 FMA TFLOP/s, whole chip. */
 int mcsas_measure_peaks(mcsas_ctx *ctx, double *mufu_gops, double *ffma_tflops);

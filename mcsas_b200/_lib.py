@@ -18,7 +18,7 @@ EXPORTS = [
     "mcsas_ctx_create", "mcsas_ctx_destroy", "mcsas_last_error", "mcsas_device_info",
     "mcsas_upload_datasets", "mcsas_set_model", "mcsas_set_smearing", "mcsas_eval", "mcsas_run", "mcsas_run_async",
     "mcsas_wait", "mcsas_request_stop", "mcsas_run_info", "mcsas_scheduler_info", "mcsas_fetch", "mcsas_fetch_trace", "mcsas_fractions",
-    "mcsas_measure_peaks", "mcsas_set_tuning",
+    "mcsas_measure_peaks", "mcsas_set_tuning", "mcsas_prepare_datasets",
 ]
 
 
@@ -80,5 +80,7 @@ def lib():
     L.mcsas_fractions.argtypes = [vp, C.POINTER(RunConfig)] + [dp] * 11
     L.mcsas_measure_peaks.argtypes = [vp, dp, dp]
     L.mcsas_set_tuning.argtypes = [vp, C.POINTER(Tuning)]
+    L.mcsas_prepare_datasets.argtypes = [vp, C.c_int, ip, dp, dp, dp, C.c_double, C.c_double, C.c_double,
+                                         C.c_int, C.c_int, C.c_int, dp, C.c_int, ip, dp, dp, dp]
     _lib = L
     return L

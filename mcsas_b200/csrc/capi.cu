@@ -19,6 +19,18 @@ cudaError_t mcsas_launch_fractions(int prec, int model, int grid, size_t smem, c
                                    const FractionArgs &a);
 cudaError_t mcsas_launch_peaks(int which, int grid, int threads, int iters, float *out,
                                cudaStream_t st);
+struct PrepArgs {                 // dataprep.cu
+    int n_sets, n_bin, cap, has_sigma;
+    const long long *raw_off;
+    const double *q, *I, *sigma;
+    const double *edges;
+    double fu_min, x0_low, x0_high;
+    int mask_zero, mask_neg;
+    int *scratch;
+    int *nq_out;
+    double *q_out, *I_out, *s_out;
+};
+cudaError_t mcsas_launch_prepare(const PrepArgs &a, cudaStream_t st);
 
 static const chain_launch_fn CHAIN_FN[MCSAS_N_MODELS] = {
     mcsas_launch_chain_0, mcsas_launch_chain_1, mcsas_launch_chain_2, mcsas_launch_chain_3,
@@ -1140,6 +1152,64 @@ extern "C" int mcsas_fractions(mcsas_ctx *ctx, const mcsas_run_config *cfg, cons
         if (totals) for (int k = 0; k < 4; ++k) totals[((size_t)s * 4 + k) * R + r] = tot[(size_t)c * 4 + k];
         if (sc) for (int k = 0; k < 2; ++k) sc[((size_t)s * 2 + k) * R + r] = scv[(size_t)c * 2 + k];
     }
+    return MCSAS_OK;
+}
+
+// Data preparation of a batch of raw tables on the device (dataprep.cu); host buffers in and out.
+extern "C" int mcsas_prepare_datasets(mcsas_ctx *ctx, int n_sets, const int *n_raw, const double *q,
+                                      const double *intensity, const double *sigma, double fu_min, double x0_low,
+                                      double x0_high, int mask_zero, int mask_neg, int n_bin, const double *edges,
+                                      int cap, int *nq_out, double *q_out, double *i_out, double *sigma_out)
+{
+    if (!ctx) return MCSAS_ERR_ARG;
+    if (n_sets < 1 || !n_raw || !q || !intensity || !nq_out || !q_out || !i_out || !sigma_out || cap < 1)
+        return fail(ctx, MCSAS_ERR_ARG, "prepare_datasets: null/empty argument");
+    if (n_bin > 0 && !edges) return fail(ctx, MCSAS_ERR_ARG, "prepare_datasets: n_bin > 0 needs the bin edges");
+    if (n_bin > cap) return fail(ctx, MCSAS_ERR_ARG, "prepare_datasets: capacity %d < n_bin %d", cap, n_bin);
+    CK(cudaSetDevice(ctx->device));
+    std::vector<long long> off((size_t)n_sets + 1, 0);
+    for (int s = 0; s < n_sets; ++s) {
+        if (n_raw[s] < 0) return fail(ctx, MCSAS_ERR_ARG, "prepare_datasets: negative row count");
+        if (n_bin <= 0 && n_raw[s] > cap) return fail(ctx, MCSAS_ERR_ARG, "prepare_datasets: capacity %d < %d rows", cap, n_raw[s]);
+        off[s + 1] = off[s] + n_raw[s];
+    }
+    const size_t rows = (size_t)off[n_sets], nout = (size_t)n_sets * cap;
+    double *d_in = nullptr, *d_edges = nullptr, *d_out = nullptr;
+    long long *d_off = nullptr;
+    int *d_scr = nullptr, *d_nq = nullptr;
+    const int ncol = sigma ? 3 : 2;
+    cudaError_t e = cudaMalloc(&d_in, sizeof(double) * (rows ? rows : 1) * ncol);
+    if (e == cudaSuccess) e = cudaMalloc(&d_off, sizeof(long long) * (n_sets + 1));
+    if (e == cudaSuccess) e = cudaMalloc(&d_scr, sizeof(int) * (rows ? rows : 1));
+    if (e == cudaSuccess) e = cudaMalloc(&d_nq, sizeof(int) * n_sets);
+    if (e == cudaSuccess) e = cudaMalloc(&d_out, sizeof(double) * 3 * nout);
+    if (e == cudaSuccess && n_bin > 0) e = cudaMalloc(&d_edges, sizeof(double) * (size_t)n_sets * (n_bin + 1));
+    cudaStream_t st = ctx->stream;
+    if (e == cudaSuccess && rows) {
+        e = cudaMemcpyAsync(d_in, q, sizeof(double) * rows, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_in + rows, intensity, sizeof(double) * rows, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess && sigma) e = cudaMemcpyAsync(d_in + 2 * rows, sigma, sizeof(double) * rows, cudaMemcpyHostToDevice, st);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, off.data(), sizeof(long long) * (n_sets + 1), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && n_bin > 0)
+        e = cudaMemcpyAsync(d_edges, edges, sizeof(double) * (size_t)n_sets * (n_bin + 1), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        PrepArgs a;
+        a.n_sets = n_sets; a.n_bin = n_bin; a.cap = cap; a.has_sigma = sigma != nullptr;
+        a.raw_off = d_off; a.q = d_in; a.I = d_in + rows; a.sigma = sigma ? d_in + 2 * rows : nullptr;
+        a.edges = d_edges; a.fu_min = fu_min; a.x0_low = x0_low; a.x0_high = x0_high;
+        a.mask_zero = mask_zero != 0; a.mask_neg = mask_neg != 0;
+        a.scratch = d_scr; a.nq_out = d_nq;
+        a.q_out = d_out; a.I_out = d_out + nout; a.s_out = d_out + 2 * nout;
+        e = mcsas_launch_prepare(a, st);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(nq_out, d_nq, sizeof(int) * n_sets, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(q_out, d_out, sizeof(double) * nout, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(i_out, d_out + nout, sizeof(double) * nout, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sigma_out, d_out + 2 * nout, sizeof(double) * nout, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_in); cudaFree(d_off); cudaFree(d_scr); cudaFree(d_nq); cudaFree(d_out); cudaFree(d_edges);
+    if (e != cudaSuccess) return fail(ctx, MCSAS_ERR_CUDA, "prepare_datasets: %s", cudaGetErrorString(e));
     return MCSAS_OK;
 }
 

@@ -84,3 +84,59 @@ def prepare(q_nm, intensity, sigma=None, n_bin=100, fu_min=0.01, x0_low=0., x0_h
     m = valid_mask(q, intensity, x0_low, x0_high, mask_zero, mask_neg)
     qb, ib, sb = rebin(q[m], intensity[m], sig[m], n_bin)
     return SASData(qb, ib, sb, title=title)
+
+
+def batch_edges(n_raw, q, intensity, n_bin, x0_low=0., x0_high=np.inf, mask_zero=False, mask_neg=False):
+    """Bin edges of every table of a batch exactly as DataObj._reBin computes them
+    (dataobj.py:308-311: numpy.logspace(log10(min), log10(max + diff[-1] / 100), nBin + 1) over the
+    masked rows), vectorised over the concatenated tables -- numpy's own log10 / power, so the bits
+    are the reference's.  Returns [n_sets, n_bin + 1]; a table with fewer than two valid rows gets
+    the degenerate edges of its only row (or NaN when it has none)."""
+    n_raw = np.asarray(n_raw, dtype=np.int64)
+    q = np.asarray(q, dtype=np.float64)
+    m = valid_mask(q, intensity, x0_low, x0_high, mask_zero, mask_neg)
+    start = np.concatenate([[0], np.cumsum(n_raw)[:-1]])
+    nonempty = n_raw > 0
+    idx = np.arange(q.size)
+    seg = np.repeat(np.arange(n_raw.size), n_raw)
+
+    def seg_reduce(ufunc, values, fill):
+        out = np.full(n_raw.size, fill, dtype=values.dtype)
+        if values.size:
+            red = ufunc.reduceat(values, start[nonempty])
+            out[nonempty] = red
+        return out
+    qmin = seg_reduce(np.minimum, np.where(m, q, np.inf), np.inf)
+    qmax = seg_reduce(np.maximum, np.where(m, q, -np.inf), -np.inf)
+    last = seg_reduce(np.maximum, np.where(m, idx, -1), -1)              # last valid row of each table
+    m2 = m.copy()
+    m2[last[last >= 0]] = False
+    prev = seg_reduce(np.maximum, np.where(m2, idx, -1), -1)             # the valid row before it
+    have2 = prev >= 0
+    step = np.zeros(n_raw.size)
+    step[have2] = (q[last[have2]] - q[prev[have2]]) / 100.               # numpy.diff(sanX)[-1] / 100.
+    with np.errstate(invalid="ignore", divide="ignore"):
+        edges = np.logspace(np.log10(qmin), np.log10(qmax + step), int(n_bin) + 1, axis=1)
+    return np.ascontiguousarray(edges)
+
+
+def prepare_batch(tables, engine, n_bin=100, fu_min=0.01, x0_low=0., x0_high=np.inf,
+                  mask_zero=False, mask_neg=False):
+    """Data preparation of MANY raw tables in one device call (mcsas_prepare_datasets):
+    no per-dataset objects, bit-identical to `prepare` / the reference.  `tables`: sequence of
+    (q [1/nm], I, sigma or None) -- all with or all without an uncertainty column.
+    Returns a list of (q [1/m], I, sigma) array triples (views of one buffer), ready for
+    Engine.upload_datasets."""
+    n_raw = np.array([np.size(t[0]) for t in tables], dtype=np.int32)
+    q = np.concatenate([np.asarray(t[0], dtype=np.float64).ravel() for t in tables]) * NM_TO_SI
+    intensity = np.concatenate([np.asarray(t[1], dtype=np.float64).ravel() for t in tables])
+    has_sigma = [t[2] is not None for t in tables]
+    if any(has_sigma) and not all(has_sigma):
+        raise ValueError("prepare_batch: either every table has an uncertainty column or none")
+    sigma = np.concatenate([np.asarray(t[2], dtype=np.float64).ravel() for t in tables]) if all(has_sigma) else None
+    n_bin = int(n_bin) if n_bin and n_bin > 0 else 0
+    edges = batch_edges(n_raw, q, intensity, n_bin, x0_low, x0_high, mask_zero, mask_neg) if n_bin else None
+    cap = n_bin if n_bin else int(n_raw.max())
+    nq, qo, io, so = engine.prepare_datasets(n_raw, q, intensity, sigma, fu_min, x0_low, x0_high, mask_zero,
+                                             mask_neg, n_bin, edges, cap)
+    return [(qo[s, :nq[s]], io[s, :nq[s]], so[s, :nq[s]]) for s in range(n_raw.size)]

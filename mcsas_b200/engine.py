@@ -222,6 +222,24 @@ class Engine(object):
         d["sc"] = sc
         return d
 
+    def prepare_datasets(self, n_raw, q, intensity, sigma, fu_min, x0_low, x0_high, mask_zero, mask_neg,
+                         n_bin, edges, cap):
+        """mcsas_prepare_datasets: batched uncertainty floor / masks / log rebinning on the device.
+        Returns (nq[S], q[S,cap], I[S,cap], sigma[S,cap])."""
+        n_raw = np.ascontiguousarray(n_raw, dtype=np.int32)
+        S = n_raw.size
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        intensity = np.ascontiguousarray(intensity, dtype=np.float64)
+        sigma = None if sigma is None else np.ascontiguousarray(sigma, dtype=np.float64)
+        edges = None if edges is None else np.ascontiguousarray(edges, dtype=np.float64)
+        nq = np.zeros(S, dtype=np.int32)
+        qo, io, so = (np.zeros((S, int(cap))) for _ in range(3))
+        self._check(self._L.mcsas_prepare_datasets(
+            self._ctx, S, _ip(n_raw), _dp(q), _dp(intensity), _dp(sigma), float(fu_min), float(x0_low),
+            float(x0_high), int(bool(mask_zero)), int(bool(mask_neg)), int(n_bin), _dp(edges), int(cap),
+            _ip(nq), _dp(qo), _dp(io), _dp(so)), "prepare_datasets")
+        return nq, qo, io, so
+
     def measure_peaks(self):
         a, b = C.c_double(), C.c_double()
         self._check(self._L.mcsas_measure_peaks(self._ctx, C.byref(a), C.byref(b)), "measure_peaks")

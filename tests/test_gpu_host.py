@@ -259,3 +259,57 @@ def test_smearing_profile_on_the_data_reaches_the_kernels():
     algo.maxIterations.setValue(1500)
     rset, conval, details = algo.mcFit(40, False, True, nRun=0)
     assert np.isfinite(conval) and details["numMoves"] > 10
+
+
+# ---- batched data preparation on the device -------------------------------------
+@pytest.mark.parametrize("tag", ["sphere10_default", "quick_default", "quick_nbin50_lim", "quick_nobin"])
+def test_batched_dataprep_matches_reference(tag):
+    """mcsas_prepare_datasets against the vectors the unmodified reference hands to mcFit after
+    loaddatafile -> updateFuMin -> setConfig (tests/golden/dataprep.npz) and, bit for bit, against
+    the host mirror (mcsas_b200.dataprep.prepare, itself pinned to the same golden on CPU)."""
+    from mcsas_b200 import Engine, dataprep
+    g = np.load(os.path.join(common.GOLDEN, "dataprep.npz"))
+    raw, cfg = g[tag + "_raw"], g[tag + "_cfg"]
+    kw = dict(n_bin=cfg[0], fu_min=cfg[1], x0_low=cfg[2], x0_high=cfg[3], mask_zero=bool(cfg[4]),
+              mask_neg=bool(cfg[5]))
+    eng = Engine(0)
+    (q, I, s), = dataprep.prepare_batch([(raw[:, 0], raw[:, 1], raw[:, 2])], eng, **kw)
+    eng.close()
+    assert q.size == g[tag + "_q"].size
+    np.testing.assert_allclose(q, g[tag + "_q"], rtol=1e-14)
+    np.testing.assert_allclose(I, g[tag + "_I"], rtol=1e-14)
+    np.testing.assert_allclose(s, g[tag + "_sigma"], rtol=1e-13)
+    d = dataprep.prepare(raw[:, 0], raw[:, 1], raw[:, 2], **kw)
+    np.testing.assert_array_equal(q, d.q)
+    np.testing.assert_array_equal(I, d.f.binnedData)
+    np.testing.assert_array_equal(s, d.f.binnedDataU)
+
+
+@pytest.mark.parametrize("n_bin,with_sigma", [(100, True), (37, False), (0, True), (6, True)])
+def test_batched_dataprep_ragged_batch_is_bit_identical_to_the_host_mirror(n_bin, with_sigma):
+    """One device call for 60 raw tables of 3 .. 6000 rows with NaN / zero / negative intensities,
+    invalid uncertainties, q limits and masks: every prepared vector equals numpy's bits (pairwise
+    sums incl. bins of > 128 rows, max(SEM, propagated), empty bins dropped, one-row bins kept)."""
+    from mcsas_b200 import Engine, dataprep
+    rng = np.random.default_rng(11)
+    tables = []
+    for i in range(60):
+        n = int(rng.choice([3, 8, 9, 129, 500, 1000, 6000])) if i else 6000
+        q = np.sort(rng.uniform(0.01, 5.0, n))
+        I = np.abs(rng.normal(100., 30., n)) * q ** -2
+        I[rng.integers(0, n, max(1, n // 50))] = rng.choice([np.nan, 0.0, -3.0, np.inf])
+        s = 0.02 * np.abs(I) * rng.uniform(0.1, 3.0, n)
+        s[rng.integers(0, n, max(1, n // 80))] = rng.choice([np.nan, 0.0, np.inf])
+        tables.append((q, I, s if with_sigma else None))
+    kw = dict(n_bin=n_bin, fu_min=0.015, x0_low=0.03e9, x0_high=4.5e9, mask_zero=True, mask_neg=(n_bin != 37))
+    eng = Engine(0)
+    out = dataprep.prepare_batch(tables, eng, **kw)
+    eng.close()
+    n_multi = 0
+    for (q, I, s), t in zip(out, tables):
+        d = dataprep.prepare(t[0], t[1], t[2], **kw)
+        np.testing.assert_array_equal(q, d.q)
+        np.testing.assert_array_equal(I, d.f.binnedData)
+        np.testing.assert_array_equal(s, d.f.binnedDataU)
+        n_multi += q.size
+    assert n_multi > 100

@@ -136,6 +136,58 @@ def test_philox_chain_matches_oracle(name, prec):
     eng.close()
 
 
+@pytest.mark.parametrize("tag", ["cyl", "kho"])
+def test_long_chain_at_full_size_matches_oracle(tag):
+    """BASELINE configs[2] (CylindersIsotropic, radius + aspect active, 500 q, the reference's 100-node
+    rule, 100 000 steps) and configs[3] (Kholodenko worm, 3 active parameters, 500 q; as many steps as the
+    oracle's adaptive integral manages in half an hour of CPU) at the FULL problem size: one chain of the
+    oracle on the kernels' Philox stream (tests/golden/long_<tag>.npz, oracle/gen_long_chains.py).
+    The fp64 kernel reproduces its accept/reject sequence and the running chi-squared (1e-6); the fp32
+    production kernel follows it.  Neither configuration reaches chi2 <= 1 within maxIterations in the
+    oracle either (cylinder: 6248 -> 1.016 after 1e5 steps): the non-convergence reported for these
+    configurations is the reference algorithm's, not the CUDA path's."""
+    from mcsas_b200 import Engine
+    path = os.path.join(common.GOLDEN, "long_%s.npz" % tag)
+    if not os.path.exists(path):
+        pytest.skip("golden not generated")
+    g = np.load(path)
+    om = orc.Model(str(g["model"]), active=[str(a) for a in g["active"]],
+                   ranges={str(a): (float(lo), float(hi)) for a, lo, hi in zip(g["active"], g["lo"], g["hi"])})
+    n = int(g["num_iter"])
+    acc_ref = np.unpackbits(g["accept"])[:n]
+    assert g["conval"] > 1.0                                  # the oracle does not converge here
+    outs = {}
+    for prec in (FP64, FP32):
+        eng = gpu_common.engine_for(om, [(g["q"], g["I"], g["sigma"])])
+        cfg = Engine.make_config(n_contribs=int(g["N"]), n_reps=1, conv_crit=1.0, max_iter=int(g["max_iter"]),
+                                 max_retries=-1, precision=prec, seed=int(g["seed"]), record_trace=True,
+                                 first_chain=int(g["chain"]))
+        eng.run(cfg)
+        out = eng.fetch()
+        acc, chi = eng.fetch_trace(0, n)
+        eng.close()
+        run = np.empty(n)
+        cur = out["conval0"][0, 0]
+        for t in range(n):
+            if acc[t]:
+                cur = chi[t]
+            run[t] = cur
+        outs[prec] = (out, acc[:n], run)
+    out, acc, run = outs[FP64]
+    assert int(out["num_iter"][0, 0]) == n and int(out["num_moves"][0, 0]) == int(g["num_moves"])
+    assert np.array_equal(acc, acc_ref)                       # every accept/reject decision
+    np.testing.assert_allclose(run[99::100], g["run_chi_every_100"], rtol=REL_CHI)
+    assert abs(out["conval"][0, 0] / g["conval"] - 1) < REL_CHI
+    np.testing.assert_allclose(out["contribs"][0, :, :, 0], g["rset"], rtol=1e-12)
+    out32, acc32, run32 = outs[FP32]
+    differ = np.nonzero(acc32 != acc_ref)[0]
+    first = int(differ[0]) if differ.size else n
+    assert first >= min(n, 2000), first                       # marginal flips appear late, if at all
+    part = run32[99:first:100]
+    np.testing.assert_allclose(part, g["run_chi_every_100"][:part.size], rtol=1e-3)
+    assert out32["conval"][0, 0] > 1.0 and abs(np.log(out32["conval"][0, 0] / g["conval"])) < 0.05
+
+
 def test_fractions_match_oracle():
     from mcsas_b200 import Engine
     g = common.load_chain("sphere_small")

@@ -18,7 +18,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from mcsas_b200 import Engine, synth, FP32  # noqa: E402
+from mcsas_b200 import Engine, synth, dataprep, FP32  # noqa: E402
 from mcsas_b200.dist import partition  # noqa: E402
 
 
@@ -49,7 +49,10 @@ def main():
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for b0 in range(0, count, block):
-        chunk = sets[b0:b0 + block]
+        # raw tables -> the vectors mcFit reads, for the whole block in ONE device call (SURVEY 8(f) f3:
+        # uncertainty floor of DataConfig.fuMin = 1 %, no rebinning -- nBin = 0 keeps the nq points)
+        raw = [(q * 1e-9, I, sig) for q, I, sig in sets[b0:b0 + block]]
+        chunk = dataprep.prepare_batch(raw, eng, n_bin=int(os.environ.get("NBIN", "0")), fu_min=0.01)
         eng.upload_datasets(chunk)
         eng.set_model(0, [10e-9, 1e14], [0], [1e-9], [100e-9], [0])
         cfg = Engine.make_config(n_contribs=300, n_reps=reps, precision=FP32, seed=55,
