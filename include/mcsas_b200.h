@@ -108,6 +108,7 @@ typedef struct mcsas_tuning {
     int qpt;           /* force q points per thread (1, 2, 4), 0 = auto */
     int profile;       /* 1: in-kernel phase cycle counters, printed to stderr by mcsas_wait */
     int verbose;       /* 1: one stderr line per time slice */
+    int half;          /* 1: 4-warp CTAs, two per SM (default 0: 8-warp CTAs, one per SM) */
     int backup_pct;    /* a chain gets a backup attempt from this percentage of maxIterations on, 0 = default (40) */
     int late_steps;    /* chains with at least this many steps take the largest clusters first, by chi-squared:
                           0 = default (never) */

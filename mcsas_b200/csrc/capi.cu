@@ -487,7 +487,7 @@ static int plan_chain_fp64(mcsas_ctx *ctx, int nq, int n_live, ChainPlan *out)
 // 8-warp CTA; eval threads = warps_q * PS * 32.
 // Measured on B200 (tools/tune.py fast, nq = 1000): 8 eval warps with 4 q points per thread
 // are the sweet spot at every cluster size.
-static bool plan_fast_layout(mcsas_ctx *ctx, int nq, int c, ChainPlan *out)
+static bool plan_fast_layout(mcsas_ctx *ctx, int nq, int c, int max_warps, ChainPlan *out)
 {
     const int grp_of[3] = {4, 8, 8};                        // proposals per chunk of layout QPT = 1,2,4
     const int n = (nq + c - 1) / c;
@@ -495,9 +495,9 @@ static bool plan_fast_layout(mcsas_ctx *ctx, int nq, int c, ChainPlan *out)
         const int qpt = CHAIN_QPT[l];
         if (ctx->forced_qpt > 0 && qpt != ctx->forced_qpt) continue;
         const int wq = (n + 32 * qpt - 1) / (32 * qpt);
-        if (wq * 32 > FAST_MAX_EVAL_THREADS[l]) continue;
+        if (wq * 32 > FAST_MAX_EVAL_THREADS[l] || wq > max_warps) continue;
         int ps = 1;
-        while (wq * ps * 2 <= 8 && wq * ps * 2 * 32 <= FAST_MAX_EVAL_THREADS[l]
+        while (wq * ps * 2 <= max_warps && wq * ps * 2 * 32 <= FAST_MAX_EVAL_THREADS[l]
                && ps * 2 * grp_of[l] <= ctx->args.spec_max) ps *= 2;
         const int threads = wq * ps * 32;
         if (threads > FAST_MAX_EVAL_THREADS[l] || threads / 32 > FAST_MAX_WARPS) continue;
@@ -562,9 +562,14 @@ static int launch_slice(mcsas_ctx *ctx, int n_live, bool resume)
     bool have[4] = {false, false, false, false};
     int maxc = ctx->forced_cluster > 0 ? ctx->forced_cluster : ctx->max_cluster;
     if (maxc > MAX_CLUSTER) maxc = MAX_CLUSTER;
+    // half = 1: 4-warp CTAs, two per SM (a chain's decision / update phases overlap with the other
+    // chain's evaluation on the same SM); the machine then holds 2 x #SMs CTAs
+    const bool half = ctx->tune.half > 0;
+    const int max_warps = half ? 4 : 8;
+    const int sms_eff = half ? 2 * sms : sms;
     for (int li = 0, c = 1; li < 4; ++li, c *= 2)
         if (c <= maxc && (ctx->forced_cluster <= 0 || c == ctx->forced_cluster))
-            have[li] = plan_fast_layout(ctx, ctx->nq_max, c, &plans[li]);
+            have[li] = plan_fast_layout(ctx, ctx->nq_max, c, max_warps, &plans[li]);
     int lowest = -1;
     for (int li = 0; li < 4; ++li) if (have[li]) { lowest = li; break; }
     if (lowest < 0) return fail(ctx, MCSAS_ERR_ARG, "no launchable fp32 chain layout for nq=%d", ctx->nq_max);
@@ -594,15 +599,15 @@ static int launch_slice(mcsas_ctx *ctx, int n_live, bool resume)
                 if (ctx->h_cnt[ctx->h_ids[i]] < late) continue;
                 for (int li = level[i] + 1; li < 4 && have[li]; ++li) {
                     const int cost = (1 << li) / 2;
-                    if (used + cost > sms || cnt_at[li] + 1 > plans[li].resident) break;
+                    if (used + cost > sms_eff || cnt_at[li] + 1 > plans[li].resident) break;
                     cnt_at[li]++; cnt_at[level[i]]--; level[i] = li; used += cost;
                 }
             }
         }
-        for (int li = lowest + 1; li < 4 && used < sms; ++li) {
+        for (int li = lowest + 1; li < 4 && used < sms_eff; ++li) {
             if (!have[li]) break;
             const int step_cost = (1 << li) / 2;
-            for (int i = 0; i < n_live && used + step_cost <= sms; ++i) {
+            for (int i = 0; i < n_live && used + step_cost <= sms_eff; ++i) {
                 if (level[i] != li - 1) continue;
                 if (cnt_at[li] + 1 > plans[li].resident) break;  // co-resident clusters of this size
                 level[i] = li; cnt_at[li]++; cnt_at[li - 1]--;
@@ -687,10 +692,8 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     };
     while (ring > 4 && smem_of(ring) > smem_limit) ring /= 2;
     size_t smem = smem_of(ring);
-    // fp32 kernel: one CTA per SM (its contribution-row cache region is indexed by the SM id):
-    // ask for more than half of an SM's shared memory
-    if (cfg->precision == MCSAS_FP32 && smem < (size_t)120 * 1024 && smem_limit >= (size_t)120 * 1024)
-        smem = (size_t)120 * 1024;
+    // (fp32 kernel: 255 registers x 256 threads fill an SM's register file, so 8-warp CTAs have their SM to
+    // themselves; 4-warp CTAs share one in pairs and need their shared memory to fit twice)
     if (smem > smem_limit)
         return fail(ctx, MCSAS_ERR_ARG, "run: configuration needs %zu B shared memory (> %zu)", smem, smem_limit);
     const int kcap_max = cfg->precision == MCSAS_FP32 ? FAST_KCAP : MCSAS_MAX_SPEC;
@@ -810,10 +813,10 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     if (cfg->precision == MCSAS_FP32) {
         // contribution-row cache: n_contribs rows of FAST_QCAP floats per SM (a CTA owns its SM)
         const size_t stride = (size_t)N * FAST_QCAP;
-        const size_t need = stride * FAST_CACHE_SMS;
+        const size_t need = stride * FAST_CACHE_SMS * FAST_CACHE_SLOTS;
         if (need > ctx->cache_cap) { CK(regrow(&ctx->d_cache, need)); ctx->cache_cap = need; }
-        if (!ctx->d_cache_lock) CK(cudaMalloc(&ctx->d_cache_lock, sizeof(int) * FAST_CACHE_SMS));
-        CK(cudaMemsetAsync(ctx->d_cache_lock, 0, sizeof(int) * FAST_CACHE_SMS, ctx->stream));
+        if (!ctx->d_cache_lock) CK(cudaMalloc(&ctx->d_cache_lock, sizeof(int) * FAST_CACHE_SMS * FAST_CACHE_SLOTS));
+        CK(cudaMemsetAsync(ctx->d_cache_lock, 0, sizeof(int) * FAST_CACHE_SMS * FAST_CACHE_SLOTS, ctx->stream));
         a.cache = ctx->d_cache;
         a.cache_stride = (long long)stride;
         a.cache_lock = ctx->d_cache_lock;

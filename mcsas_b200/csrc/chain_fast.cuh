@@ -415,14 +415,13 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     const int RING = a.ring;
     const int kmax = a.spec_max;
     const int RL = QPT * TQ;                       // cached row length of this CTA
-    // one row region per SM: every layout of this kernel fills the register file of an SM, so
-    // a CTA has its SM to itself; the lock word only guards that assumption
+    // row regions: FAST_CACHE_SLOTS per SM (an 8-warp CTA fills the register file of its SM; two
+    // 4-warp CTAs share one), taken under a lock word for the lifetime of the CTA
     unsigned smid = 0;
     if (CACHE) {
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         smid %= FAST_CACHE_SMS;                    // (the lock keeps aliased SMs apart; B200: 148 SMs)
     }
-    float *const crow = CACHE ? a.cache + (size_t)smid * a.cache_stride + qtid * QPT : nullptr;
 
     // ---- shared memory carve-up (keep in sync with fast_smem_bytes) -----------------------
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -432,7 +431,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     uint64_t *s_bar = (uint64_t *)carve(16);
     double *s_data = (double *)carve(sizeof(double) * 3 * ds.nq_pad);
     double *s_rset = (double *)carve(sizeof(double) * N * (P > 0 ? P : 1));
-    carve(64);
+    int *s_ctrl = (int *)carve(64);
     RingEntry<float> *s_ring = (RingEntry<float> *)carve((size_t)RING * sizeof(RingEntry<float>));
     float4 *s_xp = (float4 *)carve(16 * 2 * (size_t)GWC * FAST_KCAP);   // [buf][gw][proposal] (s1..s4)
     double *s_xb = (double *)carve(8 * 2 * (size_t)GWC * 8);            // [buf][gw][5 base sums, flags]
@@ -452,8 +451,14 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     const size_t NSTR = (size_t)NARR * D;
 
     if (CACHE && tid == 0) {
-        while (atomicCAS(a.cache_lock + smid, 0, 1) != 0) __nanosleep(200);
+        int got = -1;
+        while (got < 0) {
+            for (int sl = 0; sl < FAST_CACHE_SLOTS && got < 0; ++sl)
+                if (atomicCAS(a.cache_lock + smid * FAST_CACHE_SLOTS + sl, 0, 1) == 0) got = (int)smid * FAST_CACHE_SLOTS + sl;
+            if (got < 0) __nanosleep(200);
+        }
         __threadfence();
+        s_ctrl[0] = got;
     }
     // ---- stage the dataset once: TMA bulk copy global -> shared ---------------------------
     if (tid == 0) {
@@ -463,6 +468,8 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     }
     unsigned xphase = 0;
     __syncthreads();
+    const int region = CACHE ? s_ctrl[0] : 0;
+    float *const crow = CACHE ? a.cache + (size_t)region * a.cache_stride + qtid * QPT : nullptr;
     if (tid == 0) {
         uint32_t bytes = (uint32_t)(sizeof(double) * 3 * ds.nq_pad);
         mbar_expect_tx(s_bar, bytes);
@@ -1300,7 +1307,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     }
     if (CACHE) {
         __syncthreads();
-        if (tid == 0) { __threadfence(); atomicExch(a.cache_lock + smid, 0); }
+        if (tid == 0) { __threadfence(); atomicExch(a.cache_lock + region, 0); }
     }
     if (C > 1) cluster_sync_all();
 }

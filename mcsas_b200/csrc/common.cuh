@@ -152,7 +152,8 @@ __host__ __device__ inline size_t chain_smem_bytes(int nq_pad, int N, int P, int
 #define FAST_MAX_WARPS 32
 #define FAST_KCAP 64               // fp32 kernel: speculative proposals per batch (2 per decision lane)
 #define FAST_RING_MAX 256          // ... ring entries (>= 4 * FAST_KCAP)
-#define FAST_CACHE_SMS 256         // row regions allocated (>= %nsmid of a B200)
+#define FAST_CACHE_SMS 256         // SMs row regions are allocated for (>= %nsmid of a B200)
+#define FAST_CACHE_SLOTS 2         // row regions per SM (co-resident CTAs of this kernel)
 #define FAST_QCAP 1024            // q points per CTA (QPT * 32 * warps_q)
 // warps of a whole chain (cluster size x warps per CTA slice) for the largest layout the planner
 // may choose: the q slice of a CTA is a whole number of warps of 32 * 4 q points

@@ -313,3 +313,35 @@ def test_batched_dataprep_ragged_batch_is_bit_identical_to_the_host_mirror(n_bin
         np.testing.assert_array_equal(s, d.f.binnedDataU)
         n_multi += q.size
     assert n_multi > 100
+
+
+def test_integration_stub_drives_the_unmodified_reference_objects():
+    """INTEGRATION.md way B executed as a McSAS maintainer would use it: the reference's OWN McSAS /
+    Sphere / SASData objects (oracle/_ref or /root/reference through the test harness) handed to the
+    stub's analyse_b200(); the contribution sets it returns go through the reference's own
+    McSAS.histogram and land on the reference's statistics (stats_sphere200.npz)."""
+    import refharness as rh
+    if not rh.available():
+        pytest.skip("no copy of the reference (oracle/_ref is vendored by __graft_entry__.build())")
+    from test_host_cpu import _integration_stub
+    from mcsas_b200 import _lib
+    rh.install()
+    from mcsas.utils.parameter import Histogram
+    g = np.load(os.path.join(common.GOLDEN, "stats_sphere200.npz"))
+    model = rh.model_class("Sphere")()
+    model.radius.setActiveRange((float(g["lo"][0]), float(g["hi"][0])))
+    data = rh.make_data(g["q"] * 1e-9, g["I"], g["sigma"], nbin=0)
+    np.testing.assert_array_equal(np.asarray(data.f.binnedDataU).ravel(), g["sigma"])
+    algo = rh.make_algo(model, data, numContribs=int(g["N"]), numReps=24)
+    ns = _integration_stub()
+    contribs, meas, sc, bg, conval, nit, el = ns["analyse_b200"](algo, lib_path=_lib.LIB_PATH, device=0, seed=77)
+    assert contribs.shape == (int(g["N"]), 1, 24) and meas.shape == (1, g["q"].size, 24)
+    assert (conval <= 1.0).all()
+    cfg = g["radius_vol_cfg"]
+    h = Histogram(model.radius, float(cfg[0]), float(cfg[1]), int(cfg[2]), str(g["radius_vol_scale"]), "vol")
+    model.radius.histograms().append(h)
+    algo.result = [dict(contribs=contribs)]
+    algo.histogram()                                   # the reference's own post-processing
+    ref = g["radius_vol_moments"]
+    mean, var = h.moments.fields[2], h.moments.fields[4]
+    assert abs(mean - ref[2]) < 1.5 * ref[3] and abs(var - ref[4]) < 1.5 * ref[5], (mean, var, ref[2:6])

@@ -268,3 +268,49 @@ def test_precision_follows_the_data_uncertainty():
     assert algo._resolvePrecision() == _lib.FP64
     algo.precision = _lib.FP32
     assert algo._resolvePrecision() == _lib.FP32
+
+
+def _integration_stub():
+    """The ctypes stub a McSAS maintainer would add (way B), executed as written."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    part = text[text.index("## B."):]
+    code = part[part.index("```python") + len("```python"):]
+    code = code[:code.index("```")]
+    ns = {}
+    exec(compile(code, "INTEGRATION.md#B", "exec"), ns)
+    return ns
+
+
+def test_integration_stub_matches_the_header_and_the_binding():
+    """INTEGRATION.md way B is documentation that must stay executable: its RunConfig is the
+    header's struct mcsas_run_config (field order, C types, size) and the package's own binding;
+    its model / generator tables are the header's enums."""
+    import ctypes as C
+    import re
+    from mcsas_b200 import _lib
+    ns = _integration_stub()
+    stub = ns["RunConfig"]
+    assert [(n, t) for n, t in stub._fields_] == [(n, t) for n, t in _lib.RunConfig._fields_]
+    assert C.sizeof(stub) == C.sizeof(_lib.RunConfig)
+    hdr = open(os.path.join(ROOT, "include", "mcsas_b200.h")).read()
+    body = hdr[hdr.index("typedef struct mcsas_run_config {"):hdr.index("} mcsas_run_config;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    ctype = {"int": C.c_int, "double": C.c_double, "long long": C.c_longlong,
+             "unsigned long long": C.c_ulonglong}
+    fields = [(m.group(2), ctype[m.group(1).strip()])
+              for m in re.finditer(r"((?:unsigned )?(?:long long|int|double))\s+(\w+)\s*;", body)]
+    assert fields == list(stub._fields_)
+    enum = hdr[hdr.index("enum mcsas_model_id {"):hdr.index("MCSAS_N_MODELS")]
+    enum = re.sub(r"/\*.*?\*/", "", enum, flags=re.S)
+    ids = {m.group(1): int(m.group(2)) for m in re.finditer(r"(MCSAS_\w+)\s*=\s*(\d+)", enum)}
+    names = {"Sphere": "MCSAS_SPHERE", "LMADenseSphere": "MCSAS_LMA_DENSE_SPHERE",
+             "SphericalCoreShell": "MCSAS_SPHERICAL_CORE_SHELL", "EllipsoidalCoreShell": "MCSAS_ELLIPSOIDAL_CORE_SHELL",
+             "EllipsoidsIsotropic": "MCSAS_ELLIPSOIDS_ISOTROPIC", "CylindersIsotropic": "MCSAS_CYLINDERS_ISOTROPIC",
+             "GaussianChain": "MCSAS_GAUSSIAN_CHAIN", "Kholodenko": "MCSAS_KHOLODENKO"}
+    assert {k: ids[v] for k, v in names.items()} == ns["MODEL_ID"]
+    assert ns["GEN_KIND"]["RandomUniform"] == _lib.GEN_UNIFORM and ns["GEN_KIND"]["RandomExponential"] == _lib.GEN_EXP1
+    assert ns["GEN_KIND"]["RandomExponential2"] == _lib.GEN_EXP2 and ns["GEN_KIND"]["RandomExponential3"] == _lib.GEN_EXP3
+    # every entry point the stub calls is exported
+    L = _lib.lib()
+    for name in set(re.findall(r"L\.(mcsas_\w+)", open(os.path.join(ROOT, "INTEGRATION.md")).read())):
+        assert hasattr(L, name), name

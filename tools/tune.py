@@ -45,6 +45,22 @@ def run(tag, tuning, seeds=(1, 2, 4, 7), **cfgkw):
               % (tag, ms, wall, steps / ms * 1e3, nl, mx, eff, conv, chk), flush=True)
 
 
+def saturated(tag, tuning, n_sets=16):
+    """16 datasets x 100 repetitions: every SM busy (bench.py's `saturated` record)."""
+    eng = Engine(0)
+    eng.upload_datasets(synth.sphere_batch(n_sets, nq=NQ))
+    eng.set_model(0, [10e-9, 1e14], [0], [1e-9], [100e-9], [0])
+    eng.set_tuning(verbose=VERBOSE, **tuning)
+    for seed in (99, 100):
+        ms = eng.run(Engine.make_config(n_contribs=300, n_reps=100, precision=FP32, seed=seed, max_retries=0))
+        r = eng.fetch()
+        steps = float(r["steps_all"].sum())
+        print("%-34s saturated: kernel %8.2f ms  %.3e steps/s  (algorithmic MUFU fraction %.3f of 4.63e12/s)  chk %08x"
+              % (tag, ms, steps / ms * 1e3, steps / ms * 1e3 * 6000 / 4.63e12,
+                 int(r["contribs"].view(np.uint64).sum() & 0xFFFFFFFF)), flush=True)
+    eng.close()
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["base"]
     if "base" in which:
@@ -62,6 +78,11 @@ if __name__ == "__main__":
         for pct in (30, 40, 50, 60):
             for bd in (2, 4):
                 run("backup_pct=%d div=%d" % (pct, bd), {"backup_pct": pct, "backup_div": bd}, seeds=(1, 2, 4, 7, 9, 11))
+    if "half" in which:
+        for h in (0, 1, 0, 1):
+            run("half=%d" % h, {"half": h}, seeds=(1, 2, 4, 7, 9, 11))
+        for h in (0, 1):
+            saturated("half=%d" % h, {"half": h})
     if "gram" in which:
         for g in (0, -1):
             run("gram=%d" % g, {"gram": g}, seeds=(1, 2, 4, 7, 9, 11))
