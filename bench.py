@@ -399,7 +399,7 @@ def main():
     s_first, s_count = mdist.partition(N_REPS, world, rank)         # strong scaling: ONE fit over all ranks
     algo_strong = make_algo(max(1, s_count), s_first) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
-    gatherer = mdist.Gatherer(local_rank) if world > 1 else None
+    gatherer = mdist.Gatherer(local_rank, max_rows=N_REPS, n_contribs=N_CONTRIBS, n_active=1) if world > 1 else None
 
     def barrier():
         torch.cuda.synchronize()

@@ -1015,6 +1015,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     // ascending global-warp order
                     double x = 0.;
                     if (lane < 6 && (dirty || lane == 5))
+#pragma unroll 4
                         for (int g = 0; g < GW; ++g) x += allb[g * 8 + lane];
                     const double fl = __shfl_sync(0xffffffffu, x, 5);
                     if (fl != 0.) slice_over = true;
@@ -1034,12 +1035,14 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                 const bool mine = lane < Kb, mine2 = lane + 32 < Kb;
                 const float4 *allp = s_xp + (size_t)xb * GWC * FAST_KCAP;
                 if (mine) {
+#pragma unroll 4
                     for (int g = 0; g < GW; ++g) {
                         const float4 v = allp[(size_t)g * FAST_KCAP + lane];
                         s1 += v.x; s2 += v.y; s3 += v.z; s4 += v.w;
                     }
                 }
                 if (mine2) {
+#pragma unroll 4
                     for (int g = 0; g < GW; ++g) {
                         const float4 v = allp[(size_t)g * FAST_KCAP + lane + 32];
                         t1 += v.x; t2 += v.y; t3 += v.z; t4 += v.w;

@@ -43,11 +43,16 @@ def _unpack(rows, N, P):
 
 class Gatherer(object):
     """Asynchronous all-gather of every rank's result block.  Ranks may hold different numbers of
-    repetitions (block partition) or none at all (a fit that returned no result): a small header
-    all-gather (R, N, P per rank) sizes the padded payload, and a rank without a result makes EVERY
-    rank raise -- no rank is left waiting in a collective."""
+    repetitions (block partition) or none at all (a fit that returned no result).
 
-    def __init__(self, device=0):
+    With `max_rows` (the largest repetition count any rank can hold; the usual case: it is known
+    from the partition) a gather is ONE fixed-size asynchronous collective whose first row is a
+    header (rows, numContribs, nActive), so start() never waits for another rank -- the ranks' fits
+    differ in length by several ms and a blocking header exchange would make every fit wait for
+    the slowest rank.  Without it, a small blocking header all-gather sizes the payload first.
+    A rank without a result makes EVERY rank raise (in wait()) -- none is left in a collective."""
+
+    def __init__(self, device=0, max_rows=None, n_contribs=None, n_active=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -55,6 +60,11 @@ class Gatherer(object):
         self.world = dist.get_world_size() if self.active else 1
         self.cuda = self.active and dist.get_backend() == "nccl"
         self.dev = torch.device("cuda", device) if self.cuda else torch.device("cpu")
+        if max_rows is not None and not (n_contribs and n_active):
+            raise ValueError("Gatherer(max_rows=...) needs n_contribs and n_active: the fixed-size form must not "
+                             "depend on whether this rank has a result")
+        self.max_rows = max_rows
+        self.shape = (int(n_contribs), int(n_active)) if n_contribs else None
         self._cap = 0
         self._work = None
         self._pending = None
@@ -71,36 +81,50 @@ class Gatherer(object):
             self._cap = n
 
     def start(self, res):
-        torch, dist = self.torch, self.dist
+        torch = self.torch
         if not self.active:
             self.result = res
             return
         if self._work is not None:
             self.wait()
-        if res is not None:
-            rows, (N, P) = _pack(res)
-            hdr = [rows.shape[0], N, P]
+        rows, shape = (None, None) if res is None else _pack(res)
+        if self.max_rows is not None:
+            if shape is not None and tuple(shape) != self.shape:
+                raise ValueError("gather: result of shape %s, Gatherer built for %s" % (shape, self.shape))
+            N, P = self.shape
+            rmax, width = int(self.max_rows), N * P + 5
+            if rows is not None and rows.shape[0] > rmax:
+                raise ValueError("gather: %d repetitions exceed max_rows %d" % (rows.shape[0], rmax))
+            counts = None                                   # read from the gathered headers
         else:
-            rows, hdr = None, [-1, 0, 0]
-        h = torch.tensor(hdr, dtype=torch.int64, device=self.dev)
-        hs = torch.empty(3 * self.world, dtype=torch.int64, device=self.dev)
-        self._all_gather(hs, h, False)
-        hs = hs.cpu().numpy().reshape(self.world, 3)
+            hdr = [-1, 0, 0] if rows is None else [rows.shape[0], shape[0], shape[1]]
+            h = torch.tensor(hdr, dtype=torch.int64, device=self.dev)
+            hs = torch.empty(3 * self.world, dtype=torch.int64, device=self.dev)
+            self._all_gather(hs, h, False)
+            hs = hs.cpu().numpy().reshape(self.world, 3)
+            self._check_headers(hs)
+            N, P = int(hs[0, 1]), int(hs[0, 2])
+            rmax, width = int(hs[:, 0].max()), N * P + 5
+            counts = hs[:, 0].copy()
+        n = (rmax + 1) * width                              # row 0: header
+        self._buffers(n)
+        src = self._h_in[:n].view(rmax + 1, width)
+        src.zero_()
+        src[0, 0] = -1. if rows is None else float(rows.shape[0])
+        src[0, 1], src[0, 2] = float(N), float(P)
+        if rows is not None:
+            src[1:1 + rows.shape[0]] = torch.from_numpy(rows)
+        self._d_in[:n].copy_(self._h_in[:n], non_blocking=True)
+        self._work = self._all_gather(self._d_out[:n * self.world], self._d_in[:n], True)
+        self._pending = (counts, N, P, rmax, width)
+
+    @staticmethod
+    def _check_headers(hs):
         if (hs[:, 0] < 0).any():
             raise RuntimeError("gather_results: rank(s) %s hold no result (fit not converged and showIncomplete "
                                "off); nothing gathered" % np.nonzero(hs[:, 0] < 0)[0].tolist())
         if len(set(map(tuple, hs[:, 1:].tolist()))) != 1:
             raise RuntimeError("gather_results: ranks disagree on (numContribs, nActive): %s" % hs[:, 1:].tolist())
-        N, P = int(hs[0, 1]), int(hs[0, 2])
-        rmax, width = int(hs[:, 0].max()), N * P + 5
-        n = rmax * width
-        self._buffers(n)
-        src = self._h_in[:n].view(rmax, width)
-        src.zero_()
-        src[:rows.shape[0]] = torch.from_numpy(rows)
-        self._d_in[:n].copy_(self._h_in[:n], non_blocking=True)
-        self._work = self._all_gather(self._d_out[:n * self.world], self._d_in[:n], True)
-        self._pending = (hs[:, 0].copy(), N, P, rmax, width)
 
     def _all_gather(self, out, inp, async_op):
         try:
@@ -114,14 +138,16 @@ class Gatherer(object):
             return self.result
         self._work.wait()
         counts, N, P, rmax, width = self._pending
-        n = rmax * width * self.world
+        n = (rmax + 1) * width * self.world
         self._h_out[:n].copy_(self._d_out[:n], non_blocking=True)
         if self.cuda:
             self.torch.cuda.current_stream().synchronize()
-        blocks = self._h_out[:n].view(self.world, rmax, width).numpy()
-        rows = np.concatenate([blocks[r, :int(counts[r])] for r in range(self.world)], 0)
-        self.result = _unpack(rows.copy(), N, P)
+        blocks = self._h_out[:n].view(self.world, rmax + 1, width).numpy()
         self._work, self._pending = None, None
+        hs = np.rint(blocks[:, 0, :3]).astype(np.int64)
+        self._check_headers(hs)                             # the same verdict on every rank
+        rows = np.concatenate([blocks[r, 1:1 + int(hs[r, 0])] for r in range(self.world)], 0)
+        self.result = _unpack(rows.copy(), N, P)
         return self.result
 
 

@@ -164,6 +164,37 @@ for r in range(world):
     assert np.array_equal(g["contribs"][:, :, r * R:(r + 1) * R], exp)
     assert (g["scalingAll"][r * R:(r + 1) * R] == 1.0 + r).all()
     assert (g["numIterAll"][r * R:(r + 1) * R] == np.arange(R) + 10 * r).all()
+# ragged blocks (partition sizes differ by one), fixed-capacity asynchronous form: start() does not
+# wait for the other rank, two gathers back to back reuse the pinned buffers
+R2 = 2 + rank
+def block(seed):
+    r = np.random.default_rng(seed)
+    return dict(contribs=r.random((N, P, R2)) + rank, scalingAll=np.full(R2, 2.0 + rank),
+                backgroundAll=np.zeros(R2), conval=np.full(R2, 0.7), numIterAll=np.arange(R2) + 100 * rank,
+                numMoves=np.arange(R2))
+G = mdist.Gatherer(0, max_rows=3, n_contribs=N, n_active=P)
+for seed in (5, 6):
+    G.start(block(seed + 10 * rank))
+    g = G.wait()
+    assert g["contribs"].shape == (N, P, 2 + 3), g["contribs"].shape
+    off = 0
+    for r in range(world):
+        exp = np.random.default_rng(seed + 10 * r).random((N, P, 2 + r)) + r
+        assert np.array_equal(g["contribs"][:, :, off:off + 2 + r], exp)
+        assert (g["numIterAll"][off:off + 2 + r] == np.arange(2 + r) + 100 * r).all()
+        off += 2 + r
+# a rank without a result (fit not converged, showIncomplete off): EVERY rank raises, none hangs
+G.start(block(1) if rank == 0 else None)
+try:
+    G.wait()
+    raise SystemExit("expected an error on rank %%d" %% rank)
+except RuntimeError as ex:
+    assert "hold no result" in str(ex)
+try:
+    mdist.gather_results(None if rank == 0 else block(2))
+    raise SystemExit("expected an error on rank %%d" %% rank)
+except RuntimeError as ex:
+    assert "hold no result" in str(ex)
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
