@@ -70,7 +70,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop_evt.wait(0.1)
+            self._stop_evt.wait(0.25)
 
     def finish(self):
         self._stop_evt.set()
@@ -432,8 +432,11 @@ def main():
     if gatherer is not None:
         gatherer.wait()
     launches[0] = 0
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    # rank 0 samples its GPU (every nvidia-smi call takes a driver lock: 8 ranks polling at 10 Hz slowed
+    # every rank's scheduler loop by ~10 %)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler is not None:
+        sampler.start()
     barrier()
     mc_steps, kern_ms, e2e_s, evals, t2c, nconv = 0, 0.0, 0.0, 0, [], 0
     wall0 = time.perf_counter()
@@ -451,7 +454,7 @@ def main():
         e2e_s += time.perf_counter() - t0
     barrier()
     wall = time.perf_counter() - wall0
-    clocks = sampler.finish()
+    clocks = sampler.finish() if sampler is not None else None
 
     # ---- strong scaling: one nRep=100 fit partitioned over the ranks -----------------------------
     strong = None

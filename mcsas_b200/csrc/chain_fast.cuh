@@ -759,6 +759,11 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                 long long rem = a.max_iter - step;
                 if (rem < Kb) { Kb = rem >= 1 ? (1 << (31 - __clz((int)rem))) : 0; gram = false; }   // power of two
             }
+            // The exact base sums after a move are accumulated by the LAST proposal group, so that warp 0
+            // (which decides) is not the one that starts its evaluation late; a speculative batch that
+            // would give every group the same number of chunks is one chunk shorter then.
+            const int rgrp = PS - 1;
+            if (dirty && PS >= 2 && !gram && Kb >= PS * FGRP && Kb % (PS * FGRP) == 0 && Kb > FGRP) Kb -= FGRP;
             ++batch;
             if (Kb < 1 || batch > wd_batches) { status = -2; break; }   // watchdog (uniform over the cluster)
             const int ri0 = (int)((uint32_t)step % (uint32_t)N);  // contribution replaced by the batch's first step
@@ -768,9 +773,9 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             uint64_t *const xbar = s_xbar + xb;
             const long long pt1 = a.prof ? clock64() : 0;
             // ---- exact base sums of the current state (after an accepted move) + this rank's flags
-            if (grp == 0) {
+            if (grp == rgrp && dirty) {
                 double x = 0.;
-                if (dirty) {
+                {
                     double b5[5] = {0., 0., 0., 0., 0.};
 #pragma unroll
                     for (int j = 0; j < QPT; ++j) {
@@ -793,6 +798,8 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     if (lane == 4) x = b5[4];
                     if (lane < 5) xsend8(xbs + lane, xbar, C, x);
                 }
+            }
+            if (grp == 0) {
                 if (lane == 5) {                                 // time budget of this launch (any warp may end it)
                     const bool over = a.slice_ns > 0 && globaltimer_ns() - t_start > budget_ns;
                     xsend8(xbs + 5, xbar, C, over ? 1. : 0.);
@@ -1168,7 +1175,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                             if ((accmask >> (s ^ perm)) & 1) du += uu[s][j];
                         // uu = (new - old)/sigma in the model's units: undo the 1/sigma
                         const double f = s_ft[cur * FAST_QCAP + ql] + (om[j] > 0.f ? (double)__fdividef(du, om[j]) : 0.);
-                        if (grp == 0) s_ft[(cur ^ 1) * FAST_QCAP + ql] = f;
+                        if (grp == PS - 1) s_ft[(cur ^ 1) * FAST_QCAP + ql] = f;   // the group that re-reads it (refresh)
                         rho[j] = (float)(sq * (s_In[ql] - (a0 * f + b0)));
                         mu[j] = (float)(sq * f);
                     }
@@ -1221,7 +1228,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     const int ql = qtid * QPT + j;
                     const double f = s_ft[cur * FAST_QCAP + ql] + (double)dd[j] * (double)s_qs[ql];
                     const double sq = s_sw[ql];
-                    if (grp == 0) s_ft[(cur ^ 1) * FAST_QCAP + ql] = f;      // other groups still read `cur`
+                    if (grp == PS - 1) s_ft[(cur ^ 1) * FAST_QCAP + ql] = f; // other groups still read `cur`
                     rho[j] = (float)(sq * (s_In[ql] - (a0 * f + b0)));
                     mu[j] = (float)(sq * f);
                 }
