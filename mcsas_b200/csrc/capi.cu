@@ -57,6 +57,10 @@ struct mcsas_ctx {
     std::vector<DatasetDesc> sets;
     DatasetDesc *d_sets = nullptr;
     double *d_data = nullptr;
+    size_t sets_cap = 0, data_cap = 0, quad_cap = 0;   // device buffers are kept between uploads (cudaMalloc / cudaFree
+                                                       // synchronise the device: they do not belong in a per-fit path)
+    double *h_stage = nullptr;                         // pinned staging of mcsas_fetch
+    size_t stage_cap = 0;
     // model
     bool have_model = false;
     ModelParams mp;
@@ -131,6 +135,13 @@ static int fail(mcsas_ctx *ctx, int code, const char *fmt, ...)
                         cudaGetErrorString(e_), __FILE__, __LINE__);                         \
     } while (0)
 
+template <class T> static cudaError_t regrow(T **p, size_t n)
+{
+    cudaFree(*p);
+    *p = nullptr;
+    return cudaMalloc((void **)p, sizeof(T) * (n ? n : 1));
+}
+
 static thread_local std::string g_create_err;
 
 extern "C" int mcsas_ctx_create(int device, mcsas_ctx **out)
@@ -177,7 +188,7 @@ extern "C" void mcsas_ctx_destroy(mcsas_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_sets); cudaFree(ctx->d_data); cudaFree(ctx->d_quad); cudaFree(ctx->d_stream);
     cudaFree(ctx->d_rset); cudaFree(ctx->d_fit); cudaFree(ctx->d_scal); cudaFree(ctx->d_cnt);
-    cudaFree(ctx->d_ftsave); cudaFreeHost(ctx->h_att); cudaFreeHost(ctx->h_cnt); cudaFreeHost(ctx->h_cv);
+    cudaFree(ctx->d_ftsave); cudaFreeHost(ctx->h_stage); cudaFreeHost(ctx->h_att); cudaFreeHost(ctx->h_cnt); cudaFreeHost(ctx->h_cv);
     cudaFree(ctx->d_att); cudaFree(ctx->d_tacc); cudaFree(ctx->d_tchi); cudaFree(ctx->d_ids); cudaFree(ctx->d_prof); cudaFree(ctx->d_cache); cudaFree(ctx->d_cache_lock);
     cudaFreeHost(ctx->h_stop);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_begin);
@@ -246,10 +257,8 @@ extern "C" int mcsas_upload_datasets(mcsas_ctx *ctx, int n_sets, const int *nq, 
         sets[s].i_scale = (imax > 0. && std::isfinite(imax)) ? imax : 1.;
         src += nq[s];
     }
-    cudaFree(ctx->d_sets); cudaFree(ctx->d_data);
-    ctx->d_sets = nullptr; ctx->d_data = nullptr;
-    CK(cudaMalloc(&ctx->d_sets, sizeof(DatasetDesc) * n_sets));
-    CK(cudaMalloc(&ctx->d_data, sizeof(double) * packed.size()));
+    if ((size_t)n_sets > ctx->sets_cap) { CK(regrow(&ctx->d_sets, (size_t)n_sets)); ctx->sets_cap = (size_t)n_sets; }
+    if (packed.size() > ctx->data_cap) { CK(regrow(&ctx->d_data, packed.size())); ctx->data_cap = packed.size(); }
     CK(cudaMemcpyAsync(ctx->d_sets, sets.data(), sizeof(DatasetDesc) * n_sets, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_data, packed.data(), sizeof(double) * packed.size(), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -341,9 +350,7 @@ extern "C" int mcsas_set_model(mcsas_ctx *ctx, int model_id, const double *param
     }
     mp.quad_rule = quad_rule;
     mp.quad_nodes = D;
-    cudaFree(ctx->d_quad);
-    ctx->d_quad = nullptr;
-    CK(cudaMalloc(&ctx->d_quad, sizeof(double) * 2 * (D + 1)));
+    if ((size_t)2 * (D + 1) > ctx->quad_cap) { CK(regrow(&ctx->d_quad, (size_t)2 * (D + 1))); ctx->quad_cap = (size_t)2 * (D + 1); }
     if (D) {
         CK(cudaMemcpy(ctx->d_quad, qx.data(), sizeof(double) * D, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(ctx->d_quad + D, qw.data(), sizeof(double) * D, cudaMemcpyHostToDevice));
@@ -410,13 +417,6 @@ extern "C" int mcsas_eval(mcsas_ctx *ctx, int set, const double *pset, int m, do
     if (w) memcpy(w, h.data() + (size_t)m * nq + m, sizeof(double) * m);
     if (s) memcpy(s, h.data() + (size_t)m * nq + 2 * m, sizeof(double) * m);
     return MCSAS_OK;
-}
-
-template <class T> static cudaError_t regrow(T **p, size_t n)
-{
-    cudaFree(*p);
-    *p = nullptr;
-    return cudaMalloc((void **)p, sizeof(T) * (n ? n : 1));
 }
 
 // Thread layout of one chain: cluster size C (q split), q points per eval thread, eval
@@ -1047,34 +1047,46 @@ extern "C" int mcsas_fetch(mcsas_ctx *ctx, double *contribs, double *fit_meas, d
     CK(cudaSetDevice(ctx->device));
     const int C = ctx->n_chains, N = ctx->n_contribs, P = ctx->n_active, R = ctx->n_reps, NS = ctx->n_slots;
     const std::vector<int> &fs = ctx->cur;                // slot holding each chain's final attempt
+    // one pinned staging buffer, every copy asynchronous, one synchronisation
+    const size_t n_rset = contribs ? (size_t)NS * N * P : 0, n_fit = fit_meas ? (size_t)NS * ctx->nq_max : 0;
+    const size_t n_sc = (size_t)NS * 5, n_cnt = (size_t)NS * 4, n_att = ((size_t)NS + 1) / 2;   // (ints packed in doubles)
+    const size_t need = n_rset + n_fit + n_sc + n_cnt + n_att;
+    if (need > ctx->stage_cap) {
+        cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr; ctx->stage_cap = 0;
+        CK(cudaHostAlloc((void **)&ctx->h_stage, sizeof(double) * need, cudaHostAllocDefault));
+        ctx->stage_cap = need;
+    }
+    double *h_rset = ctx->h_stage, *h_fit = h_rset + n_rset, *sc = h_fit + n_fit;
+    long long *cn = (long long *)(sc + n_sc);
+    int *at = (int *)(cn + n_cnt);
+    cudaStream_t st = ctx->stream;
+    if (n_rset) CK(cudaMemcpyAsync(h_rset, ctx->d_rset, sizeof(double) * n_rset, cudaMemcpyDeviceToHost, st));
+    if (n_fit) CK(cudaMemcpyAsync(h_fit, ctx->d_fit, sizeof(double) * n_fit, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(sc, ctx->d_scal, sizeof(double) * n_sc, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(cn, ctx->d_cnt, sizeof(long long) * n_cnt, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(at, ctx->d_att, sizeof(int) * (size_t)NS, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     if (contribs) {
-        std::vector<double> h((size_t)NS * N * P);
-        CK(cudaMemcpy(h.data(), ctx->d_rset, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
         // [slot][N][P] -> [set][N][P][R]
         for (int c = 0; c < C; ++c) {
             int s = c / R, r = c % R;
-            for (int i = 0; i < N * P; ++i)
-                contribs[((size_t)s * N * P + i) * R + r] = h[(size_t)fs[c] * N * P + i];
+            const double *src = h_rset + (size_t)fs[c] * N * P;
+            double *dst = contribs + (size_t)s * N * P * R + r;
+            for (int i = 0; i < N * P; ++i) dst[(size_t)i * R] = src[i];
         }
     }
     if (fit_meas) {
-        std::vector<double> h((size_t)NS * ctx->nq_max);
-        CK(cudaMemcpy(h.data(), ctx->d_fit, sizeof(double) * h.size(), cudaMemcpyDeviceToHost));
         size_t base = 0;
         for (int s = 0; s < ctx->n_sets; ++s) {
             int nq = ctx->sets[s].nq;
-            for (int r = 0; r < R; ++r)
-                for (int i = 0; i < nq; ++i)
-                    fit_meas[base + (size_t)i * R + r] = h[(size_t)fs[s * R + r] * ctx->nq_max + i];
+            for (int r = 0; r < R; ++r) {
+                const double *src = h_fit + (size_t)fs[s * R + r] * ctx->nq_max;
+                for (int i = 0; i < nq; ++i) fit_meas[base + (size_t)i * R + r] = src[i];
+            }
             base += (size_t)nq * R;
         }
     }
-    std::vector<double> sc((size_t)NS * 5);
-    CK(cudaMemcpy(sc.data(), ctx->d_scal, sizeof(double) * sc.size(), cudaMemcpyDeviceToHost));
-    std::vector<long long> cn((size_t)NS * 4);
-    CK(cudaMemcpy(cn.data(), ctx->d_cnt, sizeof(long long) * cn.size(), cudaMemcpyDeviceToHost));
-    std::vector<int> at((size_t)NS);
-    CK(cudaMemcpy(at.data(), ctx->d_att, sizeof(int) * at.size(), cudaMemcpyDeviceToHost));
     for (int c = 0; c < C; ++c) {
         const size_t f = (size_t)fs[c];
         if (scaling) scaling[c] = sc[f];
