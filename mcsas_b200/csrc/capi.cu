@@ -888,10 +888,19 @@ extern "C" int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms)
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         ctx->kernel_ms += ms;
-        if (ctx->tune.verbose)
-            fprintf(stderr, "[mcsas_b200] slice %d: live %d  chains at cluster 1/2/4/8: %d/%d/%d/%d  %.3f ms\n",
-                    ctx->n_slices, ctx->n_live, ctx->last_sizes[0], ctx->last_sizes[1], ctx->last_sizes[2],
+        {
+            int nb = 0, maxit = 0;
+            if (ctx->tune.verbose && ctx->h_cnt && ctx->n_slices > 1)
+                for (int i = 0; i < ctx->n_live; ++i) {
+                    const int sl = ctx->h_ids[i];
+                    if (ctx->cur[sl % NC] != sl) ++nb;
+                }
+            if (ctx->tune.verbose)
+            fprintf(stderr, "[mcsas_b200] slice %d: live %d (%d backup attempts)  chains at cluster 1/2/4/8: %d/%d/%d/%d  %.3f ms\n",
+                    ctx->n_slices, ctx->n_live, nb, ctx->last_sizes[0], ctx->last_sizes[1], ctx->last_sizes[2],
                     ctx->last_sizes[3], ms);
+            (void)maxit;
+        }
         if (!sliced) break;
         int *att = ctx->h_att;
         long long *cnt = ctx->h_cnt;
@@ -934,26 +943,48 @@ extern "C" int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms)
             ++n_primary;
             if (b >= 0 && ctx->bak_state[c] == 1) ctx->h_ids[n++] = b;
         }
-        // ---- start backups: few chains alive, SMs idle, chain is late in its attempt -------------
+        // ---- start backups ------------------------------------------------------------------------
+        // (a) few chains alive, SMs idle: every chain that is late in its attempt;
+        // (b) earlier, while the machine is still full: only the few chains most likely to use all their
+        //     iterations -- the largest chi-squared among those past `early_pct` % of maxIterations (from
+        //     ~30 000 steps on the chi-squared rank predicts the length, tools/predict_len.py).  The second
+        //     attempt of a failing repetition is what a fit waits for at the end; started this early it is
+        //     finished when the first attempt gives up.
         bool new_backups = false;
         const int bdiv = ctx->tune.backup_div > 0 ? ctx->tune.backup_div : 2;
-        if (ctx->backups && n_primary > 0 && n_primary * bdiv <= ctx->prop.multiProcessorCount) {
+        const int bpct = ctx->tune.backup_pct > 0 ? ctx->tune.backup_pct : 40;
+        const int epct = ctx->tune.early_pct > 0 ? ctx->tune.early_pct : 30;
+        const int etop = ctx->tune.early_top > 0 ? ctx->tune.early_top : 0;   // (measured on config 2: no gain at 8..24 chains from 25..35 %, off by default)
+        auto start_backup = [&](int c) -> int {
+            const int pslot = ctx->cur[c];
+            const int b = pslot < NC ? pslot + NC : pslot - NC;
+            // fresh state of the backup slot, uploaded below with the host copies
+            att[b] = attempts[pslot] + 1; att[(size_t)NS + b] = 2;
+            for (int k = 0; k < 4; ++k) cnt[(size_t)k * NS + b] = 0;
+            ctx->h_conval[b] = 1e300;
+            new_backups = true;
+            cudaMemsetAsync(ctx->d_scal + 4 * (size_t)NS + b, 0, sizeof(double), ctx->stream);   // elapsed
+            ctx->bak[c] = b; ctx->bak_state[c] = 1;
+            ctx->h_ids[n++] = b;
+            ctx->n_backups_started++;
+            return b;
+        };
+        if (ctx->backups && n_primary > 0) {
+            const bool idle = n_primary * bdiv <= ctx->prop.multiProcessorCount;
+            std::vector<std::pair<double, int>> cand;
+            int n_bak_alive = 0;
             for (int c = 0; c < NC; ++c) {
-                if (ctx->done[c] || ctx->bak[c] >= 0) continue;
+                if (ctx->done[c]) continue;
+                if (ctx->bak[c] >= 0) { ++n_bak_alive; continue; }
                 const int pslot = ctx->cur[c];
                 if (status[pslot] != 0 || attempts[pslot] >= ctx->max_attempts) continue;
-                const int bpct = ctx->tune.backup_pct > 0 ? ctx->tune.backup_pct : 40;
-                if (100 * num_iter[pslot] < (long long)bpct * ctx->max_iter) continue;
-                const int b = pslot < NC ? pslot + NC : pslot - NC;
-                // fresh state of the backup slot, uploaded below with the host copies
-                att[b] = attempts[pslot] + 1; att[(size_t)NS + b] = 2;
-                for (int k = 0; k < 4; ++k) cnt[(size_t)k * NS + b] = 0;
-                ctx->h_conval[b] = 1e300;
-                new_backups = true;
-                CK(cudaMemsetAsync(ctx->d_scal + 4 * (size_t)NS + b, 0, sizeof(double), ctx->stream));   // elapsed
-                ctx->bak[c] = b; ctx->bak_state[c] = 1;
-                ctx->h_ids[n++] = b;
-                ctx->n_backups_started++;
+                if (idle && 100 * num_iter[pslot] >= (long long)bpct * ctx->max_iter) start_backup(c);
+                else if (!idle && etop > 0 && 100 * num_iter[pslot] >= (long long)epct * ctx->max_iter)
+                    cand.push_back(std::make_pair(-ctx->h_conval[pslot], c));
+            }
+            if (!idle && !cand.empty()) {
+                std::sort(cand.begin(), cand.end());
+                for (size_t i = 0; i < cand.size() && n_bak_alive < etop; ++i, ++n_bak_alive) start_backup(cand[i].second);
             }
         }
         if (new_backups) {                                  // nothing runs between slices: whole arrays

@@ -83,6 +83,12 @@ if __name__ == "__main__":
             run("half=%d" % h, {"half": h}, seeds=(1, 2, 4, 7, 9, 11))
         for h in (0, 1):
             saturated("half=%d" % h, {"half": h})
+    if "early" in which:
+        for top in [int(x) for x in os.environ.get("EARLY_TOP", "-1,8,12,16,24").split(",")]:
+            for pct in [int(x) for x in os.environ.get("EARLY_PCT", "25,30,35").split(",")]:
+                run("early_top=%d early_pct=%d" % (top, pct), {"early_top": top, "early_pct": pct}, seeds=(1, 2, 4, 7, 9, 11, 13))
+                if top < 0:
+                    break
     if "gram" in which:
         for g in (0, -1):
             run("gram=%d" % g, {"gram": g}, seeds=(1, 2, 4, 7, 9, 11))
