@@ -25,13 +25,28 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def _find_reference():
-    """/root/reference (build container) or the verbatim copy __graft_entry__.build() leaves in the
-    git-ignored oracle/_ref/ so that the reference arm of bench.py can time the UNMODIFIED reference on
-    the GPU box's host cores (it travels with gpurun like the built .so files; never committed)."""
-    for root in ("/root/reference", os.path.join(_HERE, "_ref")):
-        if os.path.isdir(os.path.join(root, "src", "mcsas")):
-            return os.path.join(root, "src"), os.path.join(root, "testdata")
-    return "/root/reference/src", "/root/reference/testdata"
+    """/root/reference (build container), or the archive __graft_entry__.build() leaves in the
+    git-ignored oracle/_ref/ so that the reference arm of bench.py can time the UNMODIFIED reference
+    on the GPU box's host cores (it travels with gpurun like the built .so files; never committed,
+    never unpacked inside the repository: the archive is extracted to a temporary directory, once
+    per process tree)."""
+    if os.path.isdir("/root/reference/src/mcsas"):
+        return "/root/reference/src", "/root/reference/testdata"
+    root = os.environ.get("MCSAS_B200_REFDIR")
+    if not (root and os.path.isdir(os.path.join(root, "src", "mcsas"))):
+        arc = os.path.join(_HERE, "_ref", "reference.tar.gz")
+        if not os.path.exists(arc):
+            return "/root/reference/src", "/root/reference/testdata"
+        import atexit
+        import shutil
+        import tarfile
+        import tempfile
+        root = tempfile.mkdtemp(prefix="mcsas_reference_")
+        with tarfile.open(arc) as tf:
+            tf.extractall(root)
+        os.environ["MCSAS_B200_REFDIR"] = root            # child processes reuse it
+        atexit.register(shutil.rmtree, root, True)
+    return os.path.join(root, "src"), os.path.join(root, "testdata")
 
 
 REFERENCE_SRC, REFERENCE_TESTDATA = _find_reference()
