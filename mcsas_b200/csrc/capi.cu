@@ -888,18 +888,14 @@ extern "C" int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms)
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         ctx->kernel_ms += ms;
-        {
-            int nb = 0, maxit = 0;
-            if (ctx->tune.verbose && ctx->h_cnt && ctx->n_slices > 1)
-                for (int i = 0; i < ctx->n_live; ++i) {
-                    const int sl = ctx->h_ids[i];
-                    if (ctx->cur[sl % NC] != sl) ++nb;
-                }
-            if (ctx->tune.verbose)
+        if (ctx->tune.verbose) {
+            int nb = 0;                                      // backup attempts among the slots of this slice
+            if (ctx->n_slices > 1)
+                for (int i = 0; i < ctx->n_live; ++i)
+                    if (ctx->cur[ctx->h_ids[i] % NC] != ctx->h_ids[i]) ++nb;
             fprintf(stderr, "[mcsas_b200] slice %d: live %d (%d backup attempts)  chains at cluster 1/2/4/8: %d/%d/%d/%d  %.3f ms\n",
                     ctx->n_slices, ctx->n_live, nb, ctx->last_sizes[0], ctx->last_sizes[1], ctx->last_sizes[2],
                     ctx->last_sizes[3], ms);
-            (void)maxit;
         }
         if (!sliced) break;
         int *att = ctx->h_att;
