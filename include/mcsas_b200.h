@@ -110,6 +110,8 @@ typedef struct mcsas_tuning {
     int verbose;       /* 1: one stderr line per time slice */
     int half;          /* 1: 4-warp CTAs, two per SM (default 0: 8-warp CTAs, one per SM) */
     int backup_pct;    /* a chain gets a backup attempt from this percentage of maxIterations on, 0 = default (40) */
+    int hedge_pct;     /* with <= #SMs/4 chains alive every chain gets its backup from this percentage on:
+                          0 = off (default) */
     int early_pct;     /* ... and, while the machine is still full, the early_top chains with the largest chi-squared */
     int early_top;     /* from early_pct % (0 = 30) on; early_top = 0: off (default) */
     int late_steps;    /* chains with at least this many steps take the largest clusters first, by chi-squared:

@@ -822,6 +822,9 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
         a.cache_lock = ctx->d_cache_lock;
     }
     if (ctx->tune.profile && cfg->precision == MCSAS_FP32) {
+#ifndef MCSAS_B200_PROF
+        fprintf(stderr, "[mcsas_b200] tuning.profile: this library was built without the phase counters (make PROF=1)\n");
+#endif
         cudaFree(ctx->d_prof);
         ctx->d_prof = nullptr;
         CK(cudaMalloc(&ctx->d_prof, sizeof(long long) * 48 * n_slots));
@@ -948,7 +951,12 @@ extern "C" int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms)
         //     finished when the first attempt gives up.
         bool new_backups = false;
         const int bdiv = ctx->tune.backup_div > 0 ? ctx->tune.backup_div : 2;
-        const int bpct = ctx->tune.backup_pct > 0 ? ctx->tune.backup_pct : 40;
+        // with at most #SMs/4 chains alive there are SMs to spare from the start (a fit partitioned over
+        // several GPUs): hedge every repetition early, from `hedge_pct` % of maxIterations on
+        // (measured, tools/tune.py hedge: 25 repetitions per GPU -15 %, 13 repetitions +4 %, 50 flat: off by default)
+        const int hpct = ctx->tune.hedge_pct > 0 ? ctx->tune.hedge_pct : 100;
+        const int bpct0 = ctx->tune.backup_pct > 0 ? ctx->tune.backup_pct : 40;
+        const int bpct = n_primary * 4 <= ctx->prop.multiProcessorCount ? (hpct < bpct0 ? hpct : bpct0) : bpct0;
         const int epct = ctx->tune.early_pct > 0 ? ctx->tune.early_pct : 30;
         const int etop = ctx->tune.early_top > 0 ? ctx->tune.early_top : 0;   // (measured on config 2: no gain at 8..24 chains from 25..35 %, off by default)
         auto start_backup = [&](int c) -> int {

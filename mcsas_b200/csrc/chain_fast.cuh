@@ -37,6 +37,65 @@
 #pragma once
 #include "chain_kernel.cuh"
 
+// ---- packed fp32 (f32x2: FFMA2 / FMUL2 / FADD2 of sm_100a) -------------------------------------------
+// The evaluation loop is bound by issue slots, not by arithmetic: two q points of a thread share one
+// instruction.  Every packed operation rounds each half exactly as the scalar one does.
+__device__ __forceinline__ float2 pk2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 pk1(float a) { return make_float2(a, a); }       // (ptxas: broadcast operand)
+__device__ __forceinline__ float2 pkneg(float2 a) { return make_float2(-a.x, -a.y); } // (operand modifier)
+// a - b, each half rounded once: opaque to the compiler, so it is never contracted with a producing
+// multiplication (the packed intrinsics are)
+__device__ __forceinline__ float2 sub2_exact(float2 a, float2 b)
+{
+    float2 c;
+    asm("{ .reg .b64 ra, rb, rc;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "sub.rn.f32x2 rc, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rc; }"
+        : "=f"(c.x), "=f"(c.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return c;
+}
+
+// The four delta sums of one proposal over the thread's q points (file header): u = cq * dd,
+// s1 += rho u, s2 += u u, s3 += mu u, s4 += om u.  ONE definition for every batch kind, so a proposal's
+// sums never depend on the path that evaluated it.  Even QPT: the even and the odd q points of the
+// thread accumulate in the two halves of packed registers and are added at the end.
+template <int QPT>
+__device__ __forceinline__ void fast_sums(const float (&dd)[QPT], const float (&cq)[QPT], const float (&rho)[QPT],
+                                          const float (&mu)[QPT], const float (&om)[QPT], float (&acc)[4],
+                                          float (&u)[QPT])
+{
+    if constexpr (QPT % 2 == 0) {
+        float2 A0, A1, A2, A3;
+#pragma unroll
+        for (int p = 0; p < QPT / 2; ++p) {
+            const float2 u2 = __fmul2_rn(pk2(cq[2 * p], cq[2 * p + 1]), pk2(dd[2 * p], dd[2 * p + 1]));
+            u[2 * p] = u2.x; u[2 * p + 1] = u2.y;
+            const float2 r2 = pk2(rho[2 * p], rho[2 * p + 1]), m2 = pk2(mu[2 * p], mu[2 * p + 1]);
+            const float2 o2 = pk2(om[2 * p], om[2 * p + 1]);
+            if (p == 0) {
+                A0 = __fmul2_rn(r2, u2); A1 = __fmul2_rn(u2, u2); A2 = __fmul2_rn(m2, u2); A3 = __fmul2_rn(o2, u2);
+            } else {
+                A0 = __ffma2_rn(r2, u2, A0); A1 = __ffma2_rn(u2, u2, A1);
+                A2 = __ffma2_rn(m2, u2, A2); A3 = __ffma2_rn(o2, u2, A3);
+            }
+        }
+        acc[0] = __fadd_rn(A0.x, A0.y); acc[1] = __fadd_rn(A1.x, A1.y);
+        acc[2] = __fadd_rn(A2.x, A2.y); acc[3] = __fadd_rn(A3.x, A3.y);
+    } else {
+        acc[0] = 0.f; acc[1] = 0.f; acc[2] = 0.f; acc[3] = 0.f;
+#pragma unroll
+        for (int j = 0; j < QPT; ++j) {
+            u[j] = cq[j] * dd[j];
+            acc[0] = fmaf(rho[j], u[j], acc[0]);
+            acc[1] = fmaf(u[j], u[j], acc[1]);
+            acc[2] = fmaf(mu[j], u[j], acc[2]);
+            acc[3] = fmaf(om[j], u[j], acc[3]);
+        }
+    }
+}
+
 // ---- per-model fast evaluation: scaled intensity D with  I(q) = D * (q_ref/q)^QS_POW ------
 template <int MODEL> struct FastOps {
     using O = Ops<MODEL, float>;
@@ -87,6 +146,20 @@ template <int MODEL> struct FastOps {
             evalN<QPT>(cn, nodes + (size_t)(ent[s] * 2) * nstr, qt, Q, d[s]);
         }
     }
+    // NS proposals against the cached rows `od` of the contributions they replace:
+    // dn = D(new) (the new row), dd = dn - od
+    template <int QPT, int NS>
+    __device__ __forceinline__ static void diffChunk(const RingEntry<float> *ring, const int (&ent)[NS],
+                                                     const float *nodes, size_t nstr, const QuadTab<float> &qt,
+                                                     const QRep<float> (&Q)[QPT], const float (&od)[NS][QPT],
+                                                     float (&dn)[NS][QPT], float (&dd)[NS][QPT])
+    {
+        evalChunk<QPT, NS>(ring, ent, nodes, nstr, qt, Q, dn);
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+            for (int j = 0; j < QPT; ++j) dd[s][j] = __fsub_rn(dn[s][j], od[s][j]);
+    }
 };
 
 // g(x) = sin x - x cos x = x^3 F(x)/3 (sphere.py:62) for the M (q, radius) pairs of a
@@ -131,6 +204,66 @@ __device__ __forceinline__ void sph_g_vec(const float (&q)[M], const float (&th)
         for (int i = 0; i < M; ++i) p[i] = fmaf(x2[i], p[i], 0.33333333f);
 #pragma unroll
         for (int i = 0; i < M; ++i) g[i] = x[i] < 1.f ? (x[i] * x2[i]) * p[i] : g[i];
+    }
+}
+
+// The same g(x), same operations and roundings, for MP PAIRS of q points (packed halves) and NS radii:
+// stage by stage over all NS x MP packed chains.
+template <int NS, int MP, bool SER>
+__device__ __forceinline__ void sph_g_pack(const float2 (&q)[MP], const float2 (&th)[MP], const float2 (&tl)[MP],
+                                           const float (&r)[NS], float2 (&g)[NS][MP])
+{
+    float2 x[NS][MP], t[NS][MP], fr[NS][MP], sn[NS][MP], cs[NS][MP];
+    const float2 magic = pk1(12582912.f), nmagic = pk1(-12582912.f), twopi = pk1(6.2831853071795865f);
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int i = 0; i < MP; ++i) t[s][i] = __ffma2_rn(th[i], pk1(r[s]), magic);   // rint(th r) for |t| < 2^22
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int i = 0; i < MP; ++i) x[s][i] = __fmul2_rn(q[i], pk1(r[s]));
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int i = 0; i < MP; ++i) t[s][i] = __fadd2_rn(t[s][i], nmagic);
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int i = 0; i < MP; ++i) fr[s][i] = __ffma2_rn(th[i], pk1(r[s]), pkneg(t[s][i]));
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int i = 0; i < MP; ++i) fr[s][i] = __ffma2_rn(tl[i], pk1(r[s]), fr[s][i]);
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int i = 0; i < MP; ++i) fr[s][i] = __fmul2_rn(fr[s][i], twopi);
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int i = 0; i < MP; ++i) {
+            sn[s][i] = pk2(__sinf(fr[s][i].x), __sinf(fr[s][i].y));
+            cs[s][i] = pk2(__cosf(fr[s][i].x), __cosf(fr[s][i].y));
+        }
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+        for (int i = 0; i < MP; ++i) g[s][i] = __ffma2_rn(pkneg(x[s][i]), cs[s][i], sn[s][i]);
+    if (SER) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+            for (int i = 0; i < MP; ++i) {
+                const float2 x2 = __fmul2_rn(x[s][i], x[s][i]);
+                float2 p = __ffma2_rn(x2, pk1(2.5052108e-7f), pk1(-2.2045855e-5f));
+                p = __ffma2_rn(x2, p, pk1(1.1904762e-3f));
+                p = __ffma2_rn(x2, p, pk1(-0.033333333f));
+                p = __ffma2_rn(x2, p, pk1(0.33333333f));
+                const float2 sg = __fmul2_rn(__fmul2_rn(x[s][i], x2), p);
+                g[s][i].x = x[s][i].x < 1.f ? sg.x : g[s][i].x;
+                g[s][i].y = x[s][i].y < 1.f ? sg.y : g[s][i].y;
+            }
     }
 }
 
@@ -234,6 +367,55 @@ template <> struct FastOps<MCSAS_SPHERE> {
             }
         }
     }
+    // NS proposals against their cached rows: dn = g^2 A (the new row, what evalN returns), dd = dn - od.
+    // Packed over pairs of q points (even QPT); the series variant is selected by ONE vote for the
+    // whole chunk, so the NS x QPT evaluations form a single basic block.
+    template <int QPT, int NS>
+    __device__ __forceinline__ static void diffChunk(const RingEntry<float> *ring, const int (&ent)[NS],
+                                                     const float *nodes, size_t nstr, const QuadTab<float> &qt,
+                                                     const QRep<float> (&Q)[QPT], const float (&od)[NS][QPT],
+                                                     float (&dn)[NS][QPT], float (&dd)[NS][QPT])
+    {
+        if (QPT % 2 != 0 || qt.nsm) {
+            evalChunk<QPT, NS>(ring, ent, nodes, nstr, qt, Q, dn);
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+#pragma unroll
+                for (int j = 0; j < QPT; ++j) dd[s][j] = __fsub_rn(dn[s][j], od[s][j]);
+            return;
+        }
+        constexpr int MP = QPT / 2 > 0 ? QPT / 2 : 1;
+        float rr[NS], aa[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const float2 ra = *(const float2 *)&ring[ent[s]].cn.c[1];
+            rr[s] = ra.x; aa[s] = ra.y;
+        }
+        float rmin = rr[0];
+#pragma unroll
+        for (int s = 1; s < NS; ++s) rmin = fminf(rmin, rr[s]);
+        float qmin = Q[0].q;
+#pragma unroll
+        for (int j = 1; j < QPT; ++j) qmin = fminf(qmin, Q[j].q);
+        float2 q[MP], th[MP], tl[MP], g[NS][MP];
+#pragma unroll
+        for (int i = 0; i < MP; ++i) {
+            q[i] = pk2(Q[2 * i].q, Q[(2 * i + 1) % QPT].q);
+            th[i] = pk2(Q[2 * i].th, Q[(2 * i + 1) % QPT].th);
+            tl[i] = pk2(Q[2 * i].tl, Q[(2 * i + 1) % QPT].tl);
+        }
+        if (__any_sync(0xffffffffu, qmin * rmin < 1.f)) sph_g_pack<NS, MP, true>(q, th, tl, rr, g);
+        else sph_g_pack<NS, MP, false>(q, th, tl, rr, g);
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+            for (int i = 0; i < MP; ++i) {
+                const float2 n2 = __fmul2_rn(__fmul2_rn(g[s][i], g[s][i]), pk1(aa[s]));
+                dn[s][2 * i] = n2.x; dn[s][(2 * i + 1) % QPT] = n2.y;
+                const float2 d2 = sub2_exact(n2, pk2(od[s][2 * i], od[s][(2 * i + 1) % QPT]));
+                dd[s][2 * i] = d2.x; dd[s][(2 * i + 1) % QPT] = d2.y;
+            }
+    }
     template <int QPT>
     __device__ __forceinline__ static void diffS(const Contrib<float> &cn, const Contrib<float> &co,
                                                  const float *, const float *, const QuadTab<float> &qt,
@@ -284,6 +466,23 @@ template <int QPT> __device__ __forceinline__ void row_store(float *p, const flo
         for (int j = 0; j < QPT; ++j) __stcg(p + j, v[j]);
     }
 }
+
+// Per-phase cycle counters (tools/prof_phases.py) are compiled in only with -DMCSAS_B200_PROF
+// (make PROF=1): their time stamps would otherwise occupy registers of the evaluation loop.
+#ifdef MCSAS_B200_PROF
+#define FAST_PROF (a.prof != nullptr)
+#else
+#define FAST_PROF false
+#endif
+
+// Loop state that only thread 0 and the final write-back need, kept in shared memory: the evaluation
+// needs every register (a chunk's old rows, new rows and sums next to the q points' constants).
+struct FastCold {
+    long long moves, evals, steps_all;
+    double conval0, G;
+    unsigned long long t_start, deadline;        // of this launch (deadline 0: not set yet / no budget)
+    LsqConst L;
+};
 
 struct FastDec {
     int kstar;
@@ -392,6 +591,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     constexpr int NARR = O::NARR;
     constexpr int FGRP = QPT == 1 ? 4 : 8;         // proposals per reduce-scatter chunk
     constexpr int NGP = FGRP * (FGRP - 1) / 2;     // pairs of a chunk (Gram matrix, off diagonal)
+    constexpr int NH = FGRP == 8 ? 4 : FGRP;       // proposals evaluated together (register budget)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T = blockDim.x;                      // all warps evaluate; the last one also fills the ring
     const int W = T >> 5;
@@ -438,8 +638,11 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     float *s_xg = (float *)carve(4 * 2 * (size_t)GWC * 32);             // [buf][gw][Gram pairs]
     uint64_t *s_xbar = (uint64_t *)carve(16);
     float *s_gtot = (float *)carve(4 * 32);
-    double *s_chi = (double *)carve(8 * (size_t)FAST_KCAP + 128);
+    double *s_chi = (double *)carve(8 * (size_t)FAST_KCAP + 256);
     FastDec *s_dec = (FastDec *)(s_chi + FAST_KCAP);
+    FastBase *s_B = (FastBase *)((char *)s_dec + 64);             // base sums of the current state (warp 0's)
+    FastCold *s_cold = (FastCold *)((char *)s_dec + 128);
+    static_assert(sizeof(FastDec) <= 64 && sizeof(FastBase) <= 64 && sizeof(FastCold) <= 128, "decision block layout");
     double *s_apart = (double *)carve(8 * 2 * (size_t)GWC * 3);         // [buf][gw][3] full-LSQ all-sum
     double *s_ft = (double *)carve(8 * 2 * FAST_QCAP);            // model intensity, double buffered
     double *s_In = (double *)carve(8 * FAST_QCAP);                // I / i_scale
@@ -542,13 +745,18 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     };
 
     cluster_allsum3(v3);
-    LsqConst L;
-    L.S = v3[0]; L.Si = v3[1]; L.Sii = v3[2];
-    L.inv_nq = 1. / (double)nq;
-    L.find_bg = a.find_bg; L.pos_bg = a.pos_bg;
+    if (tid == 0) {
+        LsqConst L0;
+        L0.S = v3[0]; L0.Si = v3[1]; L0.Sii = v3[2];
+        L0.inv_nq = 1. / (double)nq;
+        L0.find_bg = a.find_bg; L0.pos_bg = a.pos_bg;
+        s_cold->L = L0;
+        s_cold->t_start = globaltimer_ns();
+        s_cold->deadline = 0;
+    }
+    const double inv_nq = 1. / (double)nq;
 
     // ---- fp32 amplitude scale G: 1 / amplitude at the upper end of the active ranges ------
-    double G = 1.;
     {
         if (tid == 0) {
             PVec p(a.mp, a.mp.hi);
@@ -556,12 +764,11 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             VWS o = O::template prep<false>(p, a.comp_exp, 1., qt, tmp, s_nodes);
             double g = 1. / o.amp_raw;
             if (!(g > 0.) || isinf(g)) g = 1.;
-            s_chi[0] = g;
+            s_cold->G = g;
         }
         __syncthreads();
-        G = s_chi[0];
-        __syncthreads();
     }
+#define FAST_G (*(volatile const double *)&s_cold->G)
 
     // exact fp64 fit of the resident ft over the cluster (initial and final fit)
     auto lsq_all = [&](double &sa, double &sb, double &chi) {
@@ -576,7 +783,10 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             }
         }
         cluster_allsum3(v);
-        lsq_solve(L, v[0], v[1], v[2], sa, sb, chi);
+        {
+            const LsqConst L = s_cold->L;
+            lsq_solve(L, v[0], v[1], v[2], sa, sb, chi);
+        }
         double r2[3] = {0., 0., 0.};                             // residual form (:73-77,:135)
         if (grp == 0) {
 #pragma unroll
@@ -587,10 +797,10 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             }
         }
         cluster_allsum3(r2);
-        chi = r2[0] * L.inv_nq;
+        chi = r2[0] * inv_nq;
     };
 
-    auto fill_entry = [&](long long t, int attempt, long long sbase) {
+    auto fill_entry = [&](long long t, int attempt) {
         const int e = (int)t & (RING - 1);                       // RING is a power of two
         RingEntry<float> &E = s_ring[e];
         uint32_t o4[4];
@@ -598,12 +808,13 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
 #pragma unroll
         for (int k = 0; k < MCSAS_MAX_ACTIVE; ++k) {
             if (k < P) {
-                double u = a.stream ? a.stream[sbase + t * P + k]
+                double u = a.stream ? a.stream[(long long)chain * a.stream_stride + (a.start_min ? 0 : (long long)N * P) + t * P + k]
                                     : generator_output(o4[k], a.mp.gen_kind[k]);
                 E.prop[k] = u * (a.mp.hi[k] - a.mp.lo[k]) + a.mp.lo[k];  // mcsas.py:358
             }
         }
         PVec pn(a.mp, E.prop);
+        const double G = FAST_G;
         FO::prep(pn, a.comp_exp, G, qref, qt, E.cn, s_nodes + (size_t)(e * 2) * NSTR);
         if (!CACHE) {                                            // cached rows replace the old contribution
             PVec po(a.mp, s_rset + (int)((uint32_t)t % (uint32_t)N) * P);   // max_iter < 2^31 (host)
@@ -611,9 +822,9 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         }
     };
 
-    const unsigned long long t_start = globaltimer_ns();
-    long long step = 0, moves = 0, evals = 0, steps_all = 0;
-    double conval = 0., conval0 = 0., sc_a = 1., sc_b = 0.;
+    long long step = 0;
+    double conval = 0., sc_a = 1., sc_b = 0.;
+    if (tid == 0) { s_cold->moves = 0; s_cold->evals = 0; s_cold->steps_all = 0; s_cold->conval0 = 0.; }
     double a0 = 1., b0 = 0.;                       // centre of the quadratic expansion (fit of the last accepted state)
     double cv_run = 0.;                            // chi-squared the accept test compares against
     // Batch kind and size.  Which batches are Gram batches follows from the positions of the
@@ -627,12 +838,14 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     int attempt = 0, status = 1;
     bool resume = a.resume != 0 && a.status[chain] == 0;
     if (a.resume) {
-        evals = a.evals[chain]; steps_all = a.steps_all[chain];
+        if (tid == 0) { s_cold->evals = a.evals[chain]; s_cold->steps_all = a.steps_all[chain]; }
         attempt = a.attempts[chain] - 1;
-        if (resume) { step = a.num_iter[chain]; moves = a.num_moves[chain]; conval0 = a.conval0[chain]; }
+        if (resume) {
+            step = a.num_iter[chain];
+            if (tid == 0) { s_cold->moves = a.num_moves[chain]; s_cold->conval0 = a.conval0[chain]; }
+        }
     }
     const long long slice_end = a.slice_steps > 0 ? step + a.slice_steps : (1LL << 62);
-    unsigned long long budget_ns = 0;              // this launch's time budget (set once the rows are built)
 
     for (;; ++attempt) {
         // ---- contribution set: fresh draws (mcsas.py:310-317) or saved state ---------------
@@ -667,7 +880,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             int nb = min(RING, N - i0);
             for (int e = tid; e < nb; e += blockDim.x) {
                 PVec p(a.mp, s_rset + (i0 + e) * P);
-                FO::prep(p, a.comp_exp, G, qref, qt, s_ring[e].co, s_nodes + (size_t)(e * 2 + 1) * NSTR);
+                FO::prep(p, a.comp_exp, FAST_G, qref, qt, s_ring[e].co, s_nodes + (size_t)(e * 2 + 1) * NSTR);
             }
             __syncthreads();
             {
@@ -683,12 +896,12 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             }
             __syncthreads();
         }
-        if (!resume) evals += N;                                 // (rebuilding the rows of a resumed chain is not counted)
+        if (!resume && tid == 0) s_cold->evals += N;             // (rebuilding the rows of a resumed chain is not counted)
         // a launch's time budget is at least 16 x what building the rows cost it (orientation-averaged
         // and integral models: N evaluations are many MC steps' worth), so re-packing stays cheap
-        if (a.slice_ns > 0 && budget_ns == 0) {
-            const unsigned long long t_rows = globaltimer_ns() - t_start;
-            budget_ns = max((unsigned long long)a.slice_ns, 16ULL * t_rows);
+        if (a.slice_ns > 0 && tid == 0 && s_cold->deadline == 0) {
+            const unsigned long long now = globaltimer_ns(), t_rows = now - s_cold->t_start;
+            s_cold->deadline = s_cold->t_start + max((unsigned long long)a.slice_ns, 16ULL * t_rows);
         }
         if (resume) {
             // continue exactly where the previous launch stopped: the fp64 master intensity, the
@@ -709,11 +922,11 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             last_acc = (long long)a.last_acc[chain];
             K = a.batch_k[chain] & 0xffff;
             gmode = (a.batch_k[chain] >> 16) != 0;
-            sc_a = a0; sc_b = b0;
             __syncthreads();
         } else {
             lsq_all(sc_a, sc_b, conval);                         // mcsas.py:339-344
-            conval0 = conval; step = 0; moves = 0;
+            step = 0;
+            if (tid == 0) { s_cold->conval0 = conval; s_cold->moves = 0; }
             a0 = sc_a; b0 = sc_b; cv_run = conval;
             K = max(1, kmax / 2);
             gmode = true; last_acc = -(1LL << 40);
@@ -728,10 +941,9 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             mu[j] = (float)(sq * ft0[j]);
         }
         bool dirty = true;                                       // base sums not yet accumulated
-        const long long sbase = (long long)chain * a.stream_stride + (a.start_min ? 0 : (long long)N * P);
         // ---- first ring fill: the next two batches' worth of steps ------------------------------
         long long filled = min(step + 2LL * kmax, a.max_iter);   // ring holds steps [.., filled)
-        for (long long t = step + tid; t < filled; t += blockDim.x) fill_entry(t, attempt, sbase);
+        for (long long t = step + tid; t < filled; t += blockDim.x) fill_entry(t, attempt);
         __syncthreads();
         int batch = 0;
         const int wd_batches = (int)min((long long)0x3fffffff, 2 * (min(a.max_iter, slice_end) - step) + 64);
@@ -745,12 +957,13 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         // committed up to the first accepted one) when moves are rare, and GRAM (exactly FGRP
         // steps: the Gram matrix of the proposals' changes lets warp 0 re-derive the sums of
         // later proposals after each accepted one) when moves are frequent.
-        FastBase B;                                              // meaningful in warp 0 only
-        B.S = L.S; B.Sm = 0.; B.Smm = 0.; B.E0 = 0.; B.E1 = 0.; B.E2 = 0.; B.a0 = a0; B.b0 = b0;
+        // (the base sums live in shared memory: only warp 0's decision uses them, and the evaluation
+        // needs every register)
+        if (tid == 0) { FastBase B0; B0.S = s_cold->L.S; B0.Sm = 0.; B0.Smm = 0.; B0.E0 = 0.; B0.E1 = 0.; B0.E2 = 0.; B0.a0 = a0; B0.b0 = b0; *s_B = B0; }
         int xb_ = 0;                                             // exchange buffer of the next batch
         for (;;) {
         while (live) {
-            const long long pt0 = a.prof ? clock64() : 0;
+            const long long pt0 = FAST_PROF ? clock64() : 0;
             // a speculative batch smaller than one chunk per proposal group would take as long
             int Kb = min(max(K, PS * FGRP), kmax);
             bool gram = a.gram && gmode && kmax >= FGRP;
@@ -771,7 +984,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             float4 *const xp = s_xp + (size_t)xb * GWC * FAST_KCAP + (size_t)gw * FAST_KCAP;
             double *const xbs = s_xb + (size_t)xb * GWC * 8 + (size_t)gw * 8;
             uint64_t *const xbar = s_xbar + xb;
-            const long long pt1 = a.prof ? clock64() : 0;
+            const long long pt1 = FAST_PROF ? clock64() : 0;
             // ---- exact base sums of the current state (after an accepted move) + this rank's flags
             if (grp == rgrp && dirty) {
                 double x = 0.;
@@ -801,11 +1014,11 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             }
             if (grp == 0) {
                 if (lane == 5) {                                 // time budget of this launch (any warp may end it)
-                    const bool over = a.slice_ns > 0 && globaltimer_ns() - t_start > budget_ns;
+                    const bool over = a.slice_ns > 0 && globaltimer_ns() > *(volatile unsigned long long *)&s_cold->deadline;
                     xsend8(xbs + 5, xbar, C, over ? 1. : 0.);
                 }
             }
-            const long long pt1a = a.prof ? clock64() : 0;
+            const long long pt1a = FAST_PROF ? clock64() : 0;
             long long ptc[4] = {0, 0, 0, 0};
             // ---- evaluate the batch ---------------------------------------------------------
             // pinned in a register: ptxas otherwise re-reads %tid (S2R) for every proposal slot
@@ -817,46 +1030,40 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                 // every group evaluates the chunk (all need uu for the update); group 0 reports
                 const int e0 = (int)step & (RING - 1);
                 float acc[FGRP][4], gq[NGP];
-                float od[CACHE ? FGRP : 1][QPT];
-                if (CACHE) {
-#pragma unroll
-                    for (int s = 0; s < FGRP; ++s) {
-                        int ri = ri0 + (s ^ perm);
-                        if (ri >= N) ri -= N;
-                        row_load<QPT>(crow + (size_t)ri * RL, od[CACHE ? s : 0]);
-                    }
-                    int ent[FGRP];
-#pragma unroll
-                    for (int s = 0; s < FGRP; ++s) ent[s] = (e0 + (s ^ perm)) & (RING - 1);
-                    FO::template evalChunk<QPT, CACHE ? FGRP : 1>(s_ring, (const int (&)[CACHE ? FGRP : 1])ent,
-                                                                  s_nodes, NSTR, qt, Q, dnk);
-                }
 #pragma unroll
                 for (int i = 0; i < NGP; ++i) gq[i] = 0.f;
 #pragma unroll
-                for (int s = 0; s < FGRP; ++s) {
-                    acc[s][0] = 0.f; acc[s][1] = 0.f; acc[s][2] = 0.f; acc[s][3] = 0.f;
-                    const int e = (e0 + (s ^ perm)) & (RING - 1);
-                    const Contrib<float> cn = s_ring[e].cn, co = s_ring[e].co;
-                    const float *nn = s_nodes + (size_t)(e * 2) * NSTR, *no = nn + NSTR;
-                    float dd[QPT];
+                for (int h0 = 0; h0 < FGRP; h0 += NH) {
+                    float dd[NH][QPT];
                     if (CACHE) {
+                        float od[NH][QPT];
+                        int ent[NH];
 #pragma unroll
-                        for (int j = 0; j < QPT; ++j) dd[j] = dnk[CACHE ? s : 0][j] - od[CACHE ? s : 0][j];
+                        for (int s = 0; s < NH; ++s) {
+                            int ri = ri0 + ((h0 + s) ^ perm);
+                            if (ri >= N) ri -= N;
+                            row_load<QPT>(crow + (size_t)ri * RL, od[s]);
+                            ent[s] = (e0 + ((h0 + s) ^ perm)) & (RING - 1);
+                        }
+                        FO::template diffChunk<QPT, NH>(s_ring, ent, s_nodes, NSTR, qt, Q, od,
+                                                        *reinterpret_cast<float (*)[NH][QPT]>(&dnk[CACHE ? h0 : 0]), dd);
                     } else {
-                        FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd);
+#pragma unroll
+                        for (int s = 0; s < NH; ++s) {
+                            const int e = (e0 + ((h0 + s) ^ perm)) & (RING - 1);
+                            const Contrib<float> cn = s_ring[e].cn, co = s_ring[e].co;
+                            const float *nn = s_nodes + (size_t)(e * 2) * NSTR, *no = nn + NSTR;
+                            FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd[s]);
+                        }
                     }
 #pragma unroll
-                    for (int j = 0; j < QPT; ++j) {
-                        const float u = cq[j] * dd[j];
-                        uu[s][j] = u;
-                        acc[s][0] = fmaf(rho[j], u, acc[s][0]);
-                        acc[s][1] = fmaf(u, u, acc[s][1]);
-                        acc[s][2] = fmaf(mu[j], u, acc[s][2]);
-                        acc[s][3] = fmaf(om[j], u, acc[s][3]);
+                    for (int s = h0; s < h0 + NH; ++s) {
+                        fast_sums<QPT>(dd[s - h0], cq, rho, mu, om, acc[s], uu[s]);
 #pragma unroll
-                        for (int t = 0; t < s; ++t)
-                            gq[tri_idx<FGRP>(t, s)] = fmaf(uu[t][j], u, gq[tri_idx<FGRP>(t, s)]);
+                        for (int j = 0; j < QPT; ++j)
+#pragma unroll
+                            for (int t = 0; t < s; ++t)
+                                gq[tri_idx<FGRP>(t, s)] = fmaf(uu[t][j], uu[s][j], gq[tri_idx<FGRP>(t, s)]);
                     }
                 }
                 if (grp == 0) {
@@ -902,44 +1109,45 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             } else if (Kb >= FGRP) {
                 const int e0 = (int)step & (RING - 1);
                 for (int k0 = grp * FGRP; k0 < Kb; k0 += PS * FGRP) {
-                    const long long ptk = a.prof ? clock64() : 0;
+                    const long long ptk = FAST_PROF ? clock64() : 0;
                     float acc[FGRP][4];
-                    float dn[CACHE ? FGRP : 1][QPT], od[CACHE ? FGRP : 1][QPT];
+                    // NH proposals at a time: the new rows and the evaluations in flight of a whole chunk do
+                    // not fit the register file next to the loop's state (ptxas then serialises the
+                    // evaluations at the end of the chunk); the old rows of the whole chunk are requested
+                    // first (L2 / DRAM latency hides behind the evaluations)
+                    float od[CACHE ? FGRP : 1][QPT];
                     if (CACHE) {
-                        // old rows first (L2 latency hides behind the new evaluations)
 #pragma unroll
                         for (int s = 0; s < FGRP; ++s) {
                             int ri = ri0 + k0 + (s ^ perm);
                             if (ri >= N) ri -= N;
                             row_load<QPT>(crow + (size_t)ri * RL, od[CACHE ? s : 0]);
                         }
-                        int ent[FGRP];
-#pragma unroll
-                        for (int s = 0; s < FGRP; ++s) ent[s] = (e0 + k0 + (s ^ perm)) & (RING - 1);
-                        FO::template evalChunk<QPT, CACHE ? FGRP : 1>(s_ring, (const int (&)[CACHE ? FGRP : 1])ent,
-                                                                      s_nodes, NSTR, qt, Q, dn);
                     }
 #pragma unroll
-                    for (int s = 0; s < FGRP; ++s) {
-                        acc[s][0] = 0.f; acc[s][1] = 0.f; acc[s][2] = 0.f; acc[s][3] = 0.f;
-                        float dd[QPT];
+                    for (int h0 = 0; h0 < FGRP; h0 += NH) {
+                        float dd[NH][QPT];
                         if (CACHE) {
+                            float dn[NH][QPT];
+                            int ent[NH];
 #pragma unroll
-                            for (int j = 0; j < QPT; ++j) dd[j] = dn[CACHE ? s : 0][j] - od[CACHE ? s : 0][j];
+                            for (int s = 0; s < NH; ++s) ent[s] = (e0 + k0 + ((h0 + s) ^ perm)) & (RING - 1);
+                            FO::template diffChunk<QPT, NH>(s_ring, ent, s_nodes, NSTR, qt, Q,
+                                                            *reinterpret_cast<const float (*)[NH][QPT]>(&od[CACHE ? h0 : 0]), dn, dd);
                         } else {
-                            const int k = k0 + (s ^ perm);
-                            const int e = (e0 + k) & (RING - 1);
-                            const Contrib<float> cn = s_ring[e].cn, co = s_ring[e].co;
-                            const float *nn = s_nodes + (size_t)(e * 2) * NSTR, *no = nn + NSTR;
-                            FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd);  // mcsas.py:360-362
+#pragma unroll
+                            for (int s = 0; s < NH; ++s) {
+                                const int k = k0 + ((h0 + s) ^ perm);
+                                const int e = (e0 + k) & (RING - 1);
+                                const Contrib<float> cn = s_ring[e].cn, co = s_ring[e].co;
+                                const float *nn = s_nodes + (size_t)(e * 2) * NSTR, *no = nn + NSTR;
+                                FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd[s]);  // mcsas.py:360-362
+                            }
                         }
 #pragma unroll
-                        for (int j = 0; j < QPT; ++j) {
-                            float u = cq[j] * dd[j];                     // (new - old)/sigma, :366
-                            acc[s][0] = fmaf(rho[j], u, acc[s][0]);
-                            acc[s][1] = fmaf(u, u, acc[s][1]);
-                            acc[s][2] = fmaf(mu[j], u, acc[s][2]);
-                            acc[s][3] = fmaf(om[j], u, acc[s][3]);
+                        for (int s = 0; s < NH; ++s) {
+                            float u[QPT];                                // (new - old)/sigma, :366
+                            fast_sums<QPT>(dd[s], cq, rho, mu, om, acc[h0 + s], u);
                         }
                     }
                     // select-free reduce-scatter: slot s of lane l holds proposal s ^ perm(l)
@@ -958,34 +1166,27 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                             acc[0][i] += __shfl_xor_sync(0xffffffffu, acc[0][i], off);
                     if ((lane & (32 / FGRP - 1)) == 0)
                         xsend16(xp + k0 + perm, xbar, C, make_float4(acc[0][0], acc[0][1], acc[0][2], acc[0][3]));
-                    if (a.prof) { ptc[k0 == 0 ? 0 : 1] += clock64() - ptk; ptc[k0 == 0 ? 2 : 3] += 1; }
+                    if (FAST_PROF) { ptc[k0 == 0 ? 0 : 1] += clock64() - ptk; ptc[k0 == 0 ? 2 : 3] += 1; }
                 }
             } else if (grp == 0) {
                 for (int k = 0; k < Kb; ++k) {
-                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                    float acc[4];
                     const int e = ((int)step + k) & (RING - 1);
-                    const Contrib<float> cn = s_ring[e].cn, co = s_ring[e].co;
-                    const float *nn = s_nodes + (size_t)(e * 2) * NSTR, *no = nn + NSTR;
-                    float dd[QPT];
+                    float dd[1][QPT];
                     if (CACHE) {
                         int ri = ri0 + k;
                         if (ri >= N) ri -= N;
-                        FO::template evalN<QPT>(cn, nn, qt, Q, dd);
-                        float ov[QPT];
-                        row_load<QPT>(crow + (size_t)ri * RL, ov);
-#pragma unroll
-                        for (int j = 0; j < QPT; ++j) dd[j] -= ov[j];
+                        float ov[1][QPT], dv[1][QPT];
+                        row_load<QPT>(crow + (size_t)ri * RL, ov[0]);
+                        const int ent[1] = {e};
+                        FO::template diffChunk<QPT, 1>(s_ring, ent, s_nodes, NSTR, qt, Q, ov, dv, dd);
                     } else {
-                        FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd);
+                        const Contrib<float> cn = s_ring[e].cn, co = s_ring[e].co;
+                        const float *nn = s_nodes + (size_t)(e * 2) * NSTR, *no = nn + NSTR;
+                        FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd[0]);
                     }
-#pragma unroll
-                    for (int j = 0; j < QPT; ++j) {
-                        float u = cq[j] * dd[j];
-                        acc[0] = fmaf(rho[j], u, acc[0]);
-                        acc[1] = fmaf(u, u, acc[1]);
-                        acc[2] = fmaf(mu[j], u, acc[2]);
-                        acc[3] = fmaf(om[j], u, acc[3]);
-                    }
+                    float u[QPT];
+                    fast_sums<QPT>(dd[0], cq, rho, mu, om, acc, u);
                     // the same shuffle tree as the chunk evaluator's (lane bits 4..0), so that a
                     // proposal's sums do not depend on the size of the batch it was evaluated in
 #pragma unroll
@@ -999,23 +1200,24 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                 __syncwarp();
                 if (lane == 0) mbar_arrive_release(xbar);
             }
-            const long long pt2 = a.prof ? clock64() : 0;
+            const long long pt2 = FAST_PROF ? clock64() : 0;
             // ---- the last warp prepares the ring entries of the NEXT batch while warp 0 decides:
             // steps [filled, step + Kb + kmax); their slots held steps <= step - RING/2 (consumed),
             // and the contributions they replace are not touched by this batch (Kb + kmax < N)
             const long long fill_from = filled, fill_to = min(step + Kb + (long long)kmax, a.max_iter);
             if (warp == W - 1 && W > 1)
-                for (long long t = fill_from + lane; t < fill_to; t += 32) fill_entry(t, attempt, sbase);
+                for (long long t = fill_from + lane; t < fill_to; t += 32) fill_entry(t, attempt);
             filled = max(filled, fill_to);
             long long pd[4] = {0, 0, 0, 0};
-            const long long pt3 = a.prof ? clock64() : 0;
+            const long long pt3 = FAST_PROF ? clock64() : 0;
             if (warp == 0) {
                 if (C > 1 && lane == 0) {                        // bytes this rank receives per batch
                     const uint32_t per_gw = (uint32_t)(Kb * 16 + 8 + (dirty ? 40 : 0) + (gram ? ((NGP + 1) / 2) * 8 : 0));
                     mbar_expect_tx(xbar, (uint32_t)GW * per_gw);
                 }
                 mbar_wait(xbar, (xphase >> xb) & 1);             // every warp's partial sums have landed
-                if (a.prof) pd[0] = clock64();
+                if (FAST_PROF) pd[0] = clock64();
+                FastBase B = *s_B;
                 const double *allb = s_xb + (size_t)xb * GWC * 8;
                 {
                     // lane i < 5: base sum i (fresh only after a move), lane 5: launch budget flag;
@@ -1033,10 +1235,10 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                         B.a0 = a0; B.b0 = b0;
                         // the centre is the fit of this state up to the fp32 error of the delta sums:
                         // chi2 at the centre exceeds the minimum by O(1e-14) relative
-                        conval = B.E0 * L.inv_nq;
+                        conval = B.E0 * inv_nq;
                     }
                 }
-                if (a.prof) pd[1] = clock64();
+                if (FAST_PROF) pd[1] = clock64();
                 // lane l owns proposals l and l + 32 (second round only for batches of 64)
                 float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, t4 = 0.f;
                 const bool mine = lane < Kb, mine2 = lane + 32 < Kb;
@@ -1055,15 +1257,15 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                         t1 += v.x; t2 += v.y; t3 += v.z; t4 += v.w;
                     }
                 }
-                if (a.prof) pd[2] = clock64();
+                if (FAST_PROF) pd[2] = clock64();
                 int ks = -1, accmask = 0, gused = Kb;
                 double ca = a0, cb = b0, cc = conval;
                 if (!gram) {
                     double chi = 0., an = 0., bn = 0., e1, e2, rss;
                     bool better = false;
                     if (mine) {
-                        fast_solve(B, L.find_bg, L.pos_bg, s1, s2, s3, s4, rss, an, bn, e1, e2);   // mcsas.py:376
-                        chi = rss * L.inv_nq;
+                        fast_solve(B, a.find_bg, a.pos_bg, s1, s2, s3, s4, rss, an, bn, e1, e2);   // mcsas.py:376
+                        chi = rss * inv_nq;
                         better = chi < conval;                   // :379 strict
                         s_chi[lane] = chi;
                     }
@@ -1072,8 +1274,8 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     if (!mask && Kb > 32) {                      // second round: proposals 32 .. 63
                         better = false;
                         if (mine2) {
-                            fast_solve(B, L.find_bg, L.pos_bg, t1, t2, t3, t4, rss, an, bn, e1, e2);
-                            chi = rss * L.inv_nq;
+                            fast_solve(B, a.find_bg, a.pos_bg, t1, t2, t3, t4, rss, an, bn, e1, e2);
+                            chi = rss * inv_nq;
                             better = chi < conval;
                             s_chi[lane + 32] = chi;
                         }
@@ -1101,8 +1303,8 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                         double rss = 0., an = 0., bn = 0., e1 = 0., e2 = 0.;
                         bool better = false;
                         if (mine && lane >= pos) {
-                            fast_solve(B, L.find_bg, L.pos_bg, g1, g2, g3, g4, rss, an, bn, e1, e2);
-                            const double chi = rss * L.inv_nq;
+                            fast_solve(B, a.find_bg, a.pos_bg, g1, g2, g3, g4, rss, an, bn, e1, e2);
+                            const double chi = rss * inv_nq;
                             better = chi < cc;                   // :379 against the state reached so far
                             s_chi[lane] = chi;
                         }
@@ -1122,7 +1324,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                         }
                         B.Sm += s4i; B.Smm += 2. * s3i + s2i;
                         B.E0 = ri; B.E1 = e1i; B.E2 = e2i; B.a0 = ai; B.b0 = bi;
-                        ca = ai; cb = bi; cc = ri * L.inv_nq;
+                        ca = ai; cb = bi; cc = ri * inv_nq;
                         accmask |= 1 << i;
                         pos = i + 1;
                         // the reference tests the criterion before EVERY step (mcsas.py:354-357):
@@ -1131,8 +1333,9 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     }
                     ks = accmask ? 0 : -1;
                 }
-                if (a.prof) pd[3] = clock64();
+                if (FAST_PROF) pd[3] = clock64();
                 if (lane == 0) {
+                    *s_B = B;
                     s_dec->kstar = ks;
                     s_dec->accmask = accmask;
                     s_dec->used = gused;
@@ -1143,12 +1346,12 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                 }
             }
             if (W == 1)                                          // one-warp CTA: fill after deciding
-                for (long long t = fill_from + lane; t < fill_to; t += 32) fill_entry(t, attempt, sbase);
+                for (long long t = fill_from + lane; t < fill_to; t += 32) fill_entry(t, attempt);
             xphase ^= 1u << xb;
             xb_ = xb ^ 1;
-            const long long pt4 = a.prof ? clock64() : 0;
+            const long long pt4 = FAST_PROF ? clock64() : 0;
             named_bar_sync(1, T);                                // B2: the decision is published
-            const long long pt5 = a.prof ? clock64() : 0;
+            const long long pt5 = FAST_PROF ? clock64() : 0;
             const int kstar = s_dec->kstar;
             const int accmask = s_dec->accmask;
             const int used = gram ? s_dec->used : (kstar >= 0 ? kstar + 1 : Kb);
@@ -1164,7 +1367,6 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             if (gram) {
                 if (accmask) {                                   // mcsas.py:381-384 for every accepted step
                     a0 = s_dec->a; b0 = s_dec->b;
-                    sc_a = a0; sc_b = b0;
 #pragma unroll
                     for (int j = 0; j < QPT; ++j) {
                         const int ql = qtid * QPT + j;
@@ -1197,7 +1399,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                             s_rset[rix * P + p] = s_ring[e].prop[p];
                         }
                     }
-                    moves += __popc(accmask);
+                    if (tid == 0) s_cold->moves += __popc(accmask);
                     dirty = true;
                     last_acc = step + (31 - __clz(accmask));
                 } else {
@@ -1206,20 +1408,20 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                 }
             } else if (kstar >= 0) {                             // mcsas.py:381-384
                 a0 = s_dec->a; b0 = s_dec->b;
-                sc_a = a0; sc_b = b0;
                 const int e = ((int)step + kstar) & (RING - 1);
                 const Contrib<float> cn = s_ring[e].cn, co = s_ring[e].co;
                 const float *nn = s_nodes + (size_t)(e * 2) * NSTR, *no = nn + NSTR;
                 const int rix = (int)((uint32_t)(step + kstar) % (uint32_t)N);
                 float dd[QPT];
                 if (CACHE) {
-                    float dv[QPT], ov[QPT];
-                    row_load<QPT>(crow + (size_t)rix * RL, ov);   // in flight during the evaluation
-                    FO::template evalN<QPT>(cn, nn, qt, Q, dv);
+                    float dv[1][QPT], ov[1][QPT], d1[1][QPT];
+                    row_load<QPT>(crow + (size_t)rix * RL, ov[0]);   // in flight during the evaluation
+                    const int ent[1] = {e};
+                    FO::template diffChunk<QPT, 1>(s_ring, ent, s_nodes, NSTR, qt, Q, ov, dv, d1);
 #pragma unroll
-                    for (int j = 0; j < QPT; ++j) dd[j] = dv[j] - ov[j];
+                    for (int j = 0; j < QPT; ++j) dd[j] = d1[0][j];
                     if (PS > 1) named_bar_sync(1, T);            // every group has read the old row
-                    if (grp == 0) row_store<QPT>(crow + (size_t)rix * RL, dv);
+                    if (grp == 0) row_store<QPT>(crow + (size_t)rix * RL, dv[0]);
                 } else {
                     FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd);
                 }
@@ -1234,8 +1436,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                 }
                 cur ^= 1;
                 if (tid < P) s_rset[rix * P + tid] = s_ring[e].prop[tid];
-                ++moves;
-                evals += 2;
+                if (tid == 0) { s_cold->moves += 1; s_cold->evals += 2; }
                 dirty = true;
                 gmode = step + kstar - last_acc <= FGRP;
                 last_acc = step + kstar;
@@ -1243,10 +1444,9 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             } else {
                 K = min(kmax, K * 2);
             }
-            evals += 2 * Kb;
+            if (tid == 0) { s_cold->evals += 2 * Kb; s_cold->steps_all += used; }
             step += used;                                        // :403-404 (ri = step % N)
-            steps_all += used;
-            if (a.prof && tid == 0 && rank == 0) {               // phase cycles of warp 0 (tools/prof)
+            if (FAST_PROF && tid == 0 && rank == 0) {               // phase cycles of warp 0 (tools/prof)
                 long long *pp = a.prof + ((long long)chain * 2 + (gram ? 1 : 0)) * 24;
                 pp[16] += pd[3] - pd[2]; pp[17] += pt4 - pd[3];
                 pp[13] += pd[0] - pt3; pp[14] += pd[1] - pd[0]; pp[15] += pd[2] - pd[1];
@@ -1278,7 +1478,8 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         if (conval <= a.conv_crit || a.stream || attempt + 1 >= a.max_attempts || N <= 1)
             break;
         if (a.slice_steps > 0 || a.slice_ns > 0) {               // retry (mcsas.py:220-246) in a later launch
-            status = 2; ++attempt; step = 0; moves = 0;
+            status = 2; ++attempt; step = 0;
+            if (tid == 0) s_cold->moves = 0;
             break;
         }
         __syncthreads();
@@ -1300,19 +1501,19 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     }
     if (tid == 0 && rank == 0) {
         // internal model = (reference model) * G / i_scale-normalised data: undo both
-        a.scaling[chain] = sc_a * G * ds.i_scale;
+        a.scaling[chain] = sc_a * FAST_G * ds.i_scale;
         a.background[chain] = sc_b * ds.i_scale;
         a.conval[chain] = conval;
-        a.conval0[chain] = conval0;
+        a.conval0[chain] = s_cold->conval0;
         a.cen_a[chain] = a0; a.cen_b[chain] = b0; a.cv_run[chain] = cv_run;
         a.batch_k[chain] = K | (gmode ? 1 << 16 : 0);
         a.last_acc[chain] = (double)last_acc;
         a.num_iter[chain] = step;
-        a.num_moves[chain] = moves;
-        a.evals[chain] = evals;
-        a.steps_all[chain] = steps_all;
+        a.num_moves[chain] = s_cold->moves;
+        a.evals[chain] = s_cold->evals;
+        a.steps_all[chain] = s_cold->steps_all;
         a.attempts[chain] = attempt + 1;
-        a.elapsed_s[chain] = (a.resume ? a.elapsed_s[chain] : 0.) + 1e-9 * (double)(globaltimer_ns() - t_start);
+        a.elapsed_s[chain] = (a.resume ? a.elapsed_s[chain] : 0.) + 1e-9 * (double)(globaltimer_ns() - s_cold->t_start);
         a.status[chain] = status;
     }
     if (CACHE) {

@@ -179,7 +179,7 @@ __host__ __device__ inline size_t fast_smem_bytes(int nq_pad, int N, int P, int 
     s += AL16(4 * 2 * (size_t)gw_cap * 32);                      // exchange: per-warp Gram pairs
     s += 16;                                                     // exchange mbarriers
     s += AL16(4 * 32);                                           // Gram totals
-    s += AL16(8 * (size_t)FAST_KCAP + 128);                      // chi per proposal + decision
+    s += AL16(8 * (size_t)FAST_KCAP + 256);                      // chi per proposal + decision, base sums, cold loop state
     s += AL16(8 * 2 * (size_t)gw_cap * 3);                       // full-LSQ all-sum
     s += AL16(8 * 2 * FAST_QCAP) + 2 * AL16(8 * FAST_QCAP) + AL16(4 * FAST_QCAP);   // ft (x2), I, 1/sigma, q scale
     s += 2 * AL16(4 * (size_t)(D + 1));                          // quadrature table

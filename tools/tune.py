@@ -89,6 +89,9 @@ if __name__ == "__main__":
                 run("early_top=%d early_pct=%d" % (top, pct), {"early_top": top, "early_pct": pct}, seeds=(1, 2, 4, 7, 9, 11, 13))
                 if top < 0:
                     break
+    if "hedge" in which:
+        for h in (-1, 5, 10, 20, -1, 10):
+            run("hedge_pct=%d (%d reps)" % (h, REPS), {"hedge_pct": h}, seeds=(1, 2, 4, 7, 9, 11, 13))
     if "gram" in which:
         for g in (0, -1):
             run("gram=%d" % g, {"gram": g}, seeds=(1, 2, 4, 7, 9, 11))
