@@ -344,9 +344,10 @@ def sub_records(peaks, sm_count):
 
 
 def measured_traffic():
-    """DRAM bytes per launch of the dominant kernel from the kept ncu --set full capture of THIS
-    round's build (profiles/ncu_traffic.json, written from the capture's dram__bytes_read.sum +
-    dram__bytes_write.sum); None when no capture is on record."""
+    """DRAM bytes per launch of the dominant kernel, measured with ncu on THIS round's build over the
+    launches of the headline fit (profiles/ncu_traffic.json, written by tools/launch_traffic.py from the
+    kept launch list's dram__bytes_read.sum + dram__bytes_write.sum; its `saturated_slice` is the
+    ncu --set full capture of one steady-state slice with every SM busy); None when nothing is on record."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
             t = json.load(fh)
@@ -522,6 +523,7 @@ def main():
             "roofline": {"bound": "sfu", "achieved": mufu_ach, "peak": peaks["mufu_gops"],
                          "unit": "GMUFU/s", "frac": mufu_ach / peaks["mufu_gops"],
                          "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                         "traffic_per_mc_step": traffic.get("dram_bytes_per_mc_step") if traffic else None,
                          "traffic_source": traffic.get("source") if traffic else
                          "no ncu --set full capture of this build on record (profiles/ncu_traffic.json)",
                          "executed_mufu_frac": per_gpu * MUFU_EXECUTED_PER_STEP * 1e-9 / peaks["mufu_gops"],
@@ -545,6 +547,9 @@ def main():
             line["saturated"] = {"value": sat, "unit": "MC steps/s", "chains": 1600, "kernel_ms": ms_sat,
                                  "mufu_frac_algorithmic": sat * MUFU_PER_STEP * 1e-9 / peaks["mufu_gops"],
                                  "mufu_frac_executed": sat * MUFU_EXECUTED_PER_STEP * 1e-9 / peaks["mufu_gops"]}
+            if traffic and traffic.get("saturated_slice"):      # ncu --set full capture of a steady-state slice
+                line["saturated"]["dram_bytes_per_mc_step"] = traffic["saturated_slice"]["dram_bytes_per_mc_step"]
+                line["saturated"]["traffic_source"] = traffic["saturated_slice"]["source"]
             if not args.no_sub_records:
                 line["sub_records"] = sub_records(peaks, info["sm_count"])
         if not args.no_cpu_baseline and world == 1:

@@ -46,4 +46,5 @@ out = {"kernel": m["Kernel Name"][0], "dram_bytes_per_launch": dram, "mc_steps_p
        "source": "profiles/%s (ncu --set full --clock-control none, one steady-state slice of 148 chains x 8192 steps, "
                  "tools/prof_one.py)" % os.path.basename(sys.argv[4]) if len(sys.argv) > 4 else rep}
 if len(sys.argv) > 4:
-    json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(sys.argv[4])), "ncu_traffic.json"), "w"), indent=1)
+    # (the steady-state slice with every SM busy; tools/launch_traffic.py merges it into ncu_traffic.json)
+    json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(sys.argv[4])), "ncu_saturated_slice.json"), "w"), indent=1)

@@ -3,6 +3,9 @@
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+from mcsas_b200 import _lib
+# (cd mcsas_b200/csrc && make PROF=1 BUILD=../../build/csrc_prof OUT=../../build/libmcsas_b200_prof.so)
+_lib.LIB_PATH = os.path.join(ROOT, "build", "libmcsas_b200_prof.so")
 from mcsas_b200 import Engine, synth, FP32
 q, I, sig = synth.sphere_curve(nq=1000)
 for cl in [int(x) for x in os.environ.get("CLUSTERS", "1,2,4,8").split(",")]:
