@@ -55,6 +55,9 @@ struct mcsas_ctx {
     int n_sets = 0;
     int nq_max = 0;
     std::vector<DatasetDesc> sets;
+    std::vector<double> h_q;                           // host copy of the q vectors (set after set): the smeared-location
+    float4 *d_smloc = nullptr;                         // table of the fp32 sphere kernel is built from them
+    size_t smloc_cap = 0;
     DatasetDesc *d_sets = nullptr;
     double *d_data = nullptr;
     size_t sets_cap = 0, data_cap = 0, quad_cap = 0;   // device buffers are kept between uploads (cudaMalloc / cudaFree
@@ -189,7 +192,7 @@ extern "C" void mcsas_ctx_destroy(mcsas_ctx *ctx)
     cudaFree(ctx->d_sets); cudaFree(ctx->d_data); cudaFree(ctx->d_quad); cudaFree(ctx->d_stream);
     cudaFree(ctx->d_rset); cudaFree(ctx->d_fit); cudaFree(ctx->d_scal); cudaFree(ctx->d_cnt);
     cudaFree(ctx->d_ftsave); cudaFreeHost(ctx->h_stage); cudaFreeHost(ctx->h_att); cudaFreeHost(ctx->h_cnt); cudaFreeHost(ctx->h_cv);
-    cudaFree(ctx->d_att); cudaFree(ctx->d_tacc); cudaFree(ctx->d_tchi); cudaFree(ctx->d_ids); cudaFree(ctx->d_prof); cudaFree(ctx->d_cache); cudaFree(ctx->d_cache_lock);
+    cudaFree(ctx->d_att); cudaFree(ctx->d_tacc); cudaFree(ctx->d_tchi); cudaFree(ctx->d_ids); cudaFree(ctx->d_prof); cudaFree(ctx->d_cache); cudaFree(ctx->d_cache_lock); cudaFree(ctx->d_smloc);
     cudaFreeHost(ctx->h_stop);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->ev_begin);
     for (int i = 0; i < 3; ++i) { cudaEventDestroy(ctx->ev_side[i]); cudaStreamDestroy(ctx->side[i]); }
@@ -263,6 +266,7 @@ extern "C" int mcsas_upload_datasets(mcsas_ctx *ctx, int n_sets, const int *nq, 
     CK(cudaMemcpyAsync(ctx->d_data, packed.data(), sizeof(double) * packed.size(), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->sets = sets;
+    ctx->h_q.assign(q, q + src);
     ctx->n_sets = n_sets;
     ctx->nq_max = nq_max;
     ctx->have_run = false;
@@ -776,6 +780,35 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     a.start_min = cfg->start_from_minimum != 0;
     a.spec_max = kcap; a.ring = ring;
     a.gw_cap = gw_cap;
+    // fp32 sphere kernel on smeared data: per (profile point, q point) the smeared location
+    // sqrt(q^2 + off^2) (slit) or q + off (2-D averaged; sasconfig.py:326-337) as the kernel wants it --
+    // q in 1/nm, q/(2 pi) split hi + lo -- and weight * (q_ref/location)^6, so that the evaluation loop
+    // has neither the fp64 square root nor the phase split (one 16-byte load per location instead)
+    a.smloc = nullptr; a.smloc_row = 0;
+    if (cfg->precision == MCSAS_FP32 && ctx->smear.n > 0 && mp.model_id == MCSAS_SPHERE) {
+        const int row = gw_cap * 128, n = ctx->smear.n;
+        std::vector<float4> tab((size_t)ctx->n_sets * n * row);
+        size_t src = 0;
+        for (int s = 0; s < ctx->n_sets; ++s) {
+            const int nq = ctx->sets[s].nq;
+            const double qref = (double)(float)(ctx->sets[s].q_ref * 1e-9);
+            for (int k = 0; k < n; ++k)
+                for (int i = 0; i < row; ++i) {
+                    const double q = ctx->h_q[src + (i < nq ? i : nq - 1)], o = ctx->smear.off[k];
+                    const double loc = (ctx->smear.two_d ? q + o : sqrt(q * q + o * o)) * 1e-9;
+                    const double t = loc * 0.15915494309189535, ql = qref / loc, q2 = ql * ql;
+                    float4 e;
+                    e.x = (float)loc; e.y = (float)t; e.z = (float)(t - (double)e.y);
+                    e.w = (float)(ctx->smear.tw[k] * q2 * q2 * q2);
+                    tab[((size_t)s * n + k) * row + i] = e;
+                }
+            src += nq;
+        }
+        if (tab.size() > ctx->smloc_cap) { CK(regrow(&ctx->d_smloc, tab.size())); ctx->smloc_cap = tab.size(); }
+        CK(cudaMemcpyAsync(ctx->d_smloc, tab.data(), sizeof(float4) * tab.size(), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        a.smloc = ctx->d_smloc; a.smloc_row = row;
+    }
     a.gram = ctx->tune.gram < 0 ? 0 : 1;
     a.first_chain = cfg->first_chain; a.record_trace = cfg->record_trace;
     a.seed = cfg->seed;

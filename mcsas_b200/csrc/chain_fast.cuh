@@ -297,6 +297,30 @@ template <> struct FastOps<MCSAS_SPHERE> {
                                                  const QRep<float> (&Q)[QPT], float (&d)[QPT])
     {
         if (qt.nsm) {
+            if (qt.smloc) {
+                // smeared (sasmodel.py:56-73): sum over the profile points of w g(loc r)^2 at the tabulated
+                // locations (location, its split phase factor and weight * (q_ref/loc)^6 come from ONE
+                // 16-byte load: no fp64 square root, no phase split in the loop)
+                float acc[QPT];
+#pragma unroll
+                for (int j = 0; j < QPT; ++j) acc[j] = 0.f;
+#pragma unroll 2
+                for (int k = 0; k < qt.nsm; ++k) {
+                    float q[QPT], th[QPT], tl[QPT], r[QPT], w[QPT], g[QPT];
+#pragma unroll
+                    for (int j = 0; j < QPT; ++j) {
+                        const float4 e = __ldg(qt.smloc + (size_t)k * qt.smstride + j);
+                        q[j] = e.x; th[j] = e.y; tl[j] = e.z; w[j] = e.w; r[j] = cc.c[0];
+                    }
+                    // (the series variant for every point: a vote per profile point costs more than it saves)
+                    sph_g_vec<QPT, true>(q, th, tl, r, g);
+#pragma unroll
+                    for (int j = 0; j < QPT; ++j) acc[j] = fmaf(w[j], g[j] * g[j], acc[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < QPT; ++j) d[j] = acc[j] * cc.c[2];
+                return;
+            }
 #pragma unroll
             for (int j = 0; j < QPT; ++j) d[j] = eval_q<MCSAS_SPHERE, float>(cc, nullptr, qt, Q[j]);
             return;
@@ -684,7 +708,9 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     }
     mbar_wait(s_bar, 0);
     if (C > 1) cluster_sync_all(); else __syncthreads();         // every rank's mbarriers are initialised
-    const QuadTab<float> qt = { D, a.mp.quad_rule, s_qx, s_qw, &a.smear, SMEAR ? a.smear.n : 0 };
+    const QuadTab<float> qt = { D, a.mp.quad_rule, s_qx, s_qw, &a.smear, SMEAR ? a.smear.n : 0,
+                                SMEAR && a.smloc ? a.smloc + ((size_t)set * a.smear.n * a.smloc_row + (size_t)(rank * TQ + qtid) * QPT) : nullptr,
+                                a.smloc_row };
     const float qref = (float)(ds.q_ref * 1e-9);   // 1/nm
 
     // ---- per-thread resident state of q points (rank*TQ + qtid)*QPT + j, j < QPT (contiguous:

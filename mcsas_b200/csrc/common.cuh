@@ -97,6 +97,9 @@ struct ChainArgs {
     long long cache_stride;      // floats per SM (n_contribs * FAST_QCAP)
     int *cache_lock;             // [SM id] 0 = free
     long long *prof;             // NULL or [chain][2][8] phase cycle counters (MCSAS_B200_PROF)
+    const float4 *smloc;         // fp32 sphere kernel, smeared data: NULL or [set][profile point][smloc_row] table of
+                                 // (q, split q/(2 pi), weight * (q_ref/q)^6) at the smeared locations of every q point
+    int smloc_row;               // entries per profile point (>= q points of the largest chain layout)
 };
 
 struct EvalArgs {

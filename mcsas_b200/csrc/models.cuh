@@ -202,6 +202,8 @@ template <class Real> struct QuadTab {
     const SmearTab *sm;      // smearing profile (n = 0: none)
     int nsm;                 // profile points in use: sm->n, or a compile-time 0 in the kernel
                              // instantiations for unsmeared data (their hot loops carry no smear code)
+    const float4 *smloc;     // fp32 sphere kernel: this thread's column of the smeared-location table
+    int smstride;            // (ChainArgs::smloc), entries between two profile points; NULL: none
 };
 
 template <int MODEL, class Real> struct Ops;

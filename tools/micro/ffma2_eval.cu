@@ -28,7 +28,7 @@ __device__ __forceinline__ void g_scalar(const float (&q)[M], const float (&th)[
     for (int i = 0; i < M; ++i) g[i] = fmaf(-x[i], cs[i], sn[i]);
 }
 
-__global__ void __launch_bounds__(256, 1) k_scalar(const float *in, float *out, int iters)
+template <int BPS> __global__ void __launch_bounds__(256, BPS) k_scalar(const float *in, float *out, int iters)
 {
     const int tid = threadIdx.x + blockIdx.x * blockDim.x;
     float q[4], th[4], tl[4], cq[4], rho[4], mu[4], om[4];
@@ -109,7 +109,7 @@ __device__ __forceinline__ void g_packed(const float2 (&q)[MP], const float2 (&t
     for (int i = 0; i < MP; ++i) g[i] = __ffma2_rn(f2(-x[i].x, -x[i].y), cs[i], sn[i]);
 }
 
-__global__ void __launch_bounds__(256, 1) k_packed(const float *in, float *out, int iters)
+template <int BPS> __global__ void __launch_bounds__(256, BPS) k_packed(const float *in, float *out, int iters)
 {
     const int tid = threadIdx.x + blockIdx.x * blockDim.x;
     float2 q[2], th[2], tl[2], cq[2], rho[2], mu[2], om[2];
@@ -164,22 +164,26 @@ __global__ void __launch_bounds__(256, 1) k_packed(const float *in, float *out, 
     out[tid] = tot;
 }
 
+template <int BPS> void run(const float *in, float *out, int iters)
+{
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int rep = 0; rep < 2; ++rep)
+        for (int v = 0; v < 2; ++v) {
+            cudaEventRecord(e0);
+            if (v == 0) k_scalar<BPS><<<148 * BPS, 256>>>(in, out, iters); else k_packed<BPS><<<148 * BPS, 256>>>(in, out, iters);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            double cyc = ms * 1e-3 * 1.965e9 / ((double)iters * 8 * BPS * 32 / 4);
+            printf("%d warps/SM %s %8.3f ms  -> %.1f cycles per warp-evaluation per SMSP  (%s)\n", 8 * BPS, v ? "packed" : "scalar", ms, cyc, cudaGetErrorString(cudaGetLastError()));
+        }
+}
 int main()
 {
     float *in, *out;
-    cudaMalloc(&in, 4 << 20); cudaMalloc(&out, 1 << 20);
+    cudaMalloc(&in, 4 << 20); cudaMalloc(&out, 4 << 20);
     cudaMemset(in, 0x3c, 4 << 20);
-    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    const int iters = 4000;
-    for (int rep = 0; rep < 3; ++rep)
-        for (int v = 0; v < 2; ++v) {
-            cudaEventRecord(e0);
-            if (v == 0) k_scalar<<<148, 256>>>(in, out, iters); else k_packed<<<148, 256>>>(in, out, iters);
-            cudaEventRecord(e1); cudaEventSynchronize(e1);
-            float ms; cudaEventElapsedTime(&ms, e0, e1);
-            // warp-level evaluations: 8 warps x iters x 32 (proposal, q) per SM
-            double cyc = ms * 1e-3 * 1.965e9 / ((double)iters * 8 * 32 / 4);
-            printf("%s %8.3f ms  -> %.1f cycles per warp-evaluation per SMSP  (%s)\n", v ? "packed" : "scalar", ms, cyc, cudaGetErrorString(cudaGetLastError()));
-        }
+    run<1>(in, out, 4000);
+    run<2>(in, out, 4000);
+    run<4>(in, out, 4000);
     return 0;
 }
