@@ -86,7 +86,7 @@ typedef struct mcsas_run_config {
     int start_from_minimum;    /* startFromMinimum */
     int precision;             /* mcsas_precision */
     unsigned long long seed;   /* Philox key (production proposals) */
-    int spec_max;              /* max speculative proposals per batch: 0 = default (fp64 kernel 32, fp32 kernel 64),
+    int spec_max;              /* max speculative proposals per batch: 0 = default (fp64 kernel 32, fp32 kernel 64, 128 on >= 4 CTAs),
                                   1 = none (sequential).  The fp64 kernel's results do not depend on it; in the
                                   fp32 kernel it decides which batches are Gram batches (different rounding) */
     int record_trace;          /* 1: keep per-step accept flag + chi-squared (parity tests) */
@@ -116,6 +116,9 @@ typedef struct mcsas_tuning {
     int early_top;     /* from early_pct % (0 = 30) on; early_top = 0: off (default) */
     int late_steps;    /* chains with at least this many steps take the largest clusters first, by chi-squared:
                           0 = default (never) */
+    int big_batch;     /* fp32 kernel: speculative batches of up to 128 proposals (instead of 64) for chains on at
+                          least this many CTAs: 0 = default (4: the chains that run on otherwise idle SMs),
+                          1 / 2 / 4 / 8, -1 = never.  (A run_config.spec_max > 0 overrides it.) */
 } mcsas_tuning;
 
 /* -- context ------------------------------------------------------------- */

@@ -111,6 +111,7 @@ struct mcsas_ctx {
     int n_live = 0, n_launches = 0, n_slices = 0, last_cluster = 1, last_threads = 0, last_qpt = 0, last_resident = 0;
     int last_sizes[4] = {0, 0, 0, 0};   // chains launched with cluster size 1, 2, 4, 8 in the last slice
     int max_cluster = 8, forced_qpt = 0;
+    bool spec_forced = false;                          // run_config.spec_max > 0
     mcsas_tuning tune;                  // experiment knobs (mcsas_set_tuning), all 0 = defaults
     float kernel_ms = 0.f;
     volatile int *stop_flag = nullptr;
@@ -521,6 +522,12 @@ static int launch_one_size(mcsas_ctx *ctx, const ChainArgs &base, const ChainPla
     ChainArgs a = base;
     a.cluster = pl.cluster;
     a.warps_q = pl.warps_q;
+    // batches of more than FAST_KDEF proposals only where the SMs would otherwise idle (a chain on >= 4 CTAs
+    // is one of few left): on a full machine the proposals evaluated behind an accepted move are lost work
+    if (ctx->precision == MCSAS_FP32 && !ctx->spec_forced) {
+        const int from = ctx->tune.big_batch > 0 ? ctx->tune.big_batch : (ctx->tune.big_batch < 0 ? 1 << 30 : 4);
+        if (pl.cluster < from && a.spec_max > FAST_KDEF) a.spec_max = FAST_KDEF;
+    }
     a.chain_ids = d_ids;
     const int extra = ctx->precision == MCSAS_FP64 ? 32 : 0;                          // fp64: + producer warp
     cudaError_t e = CHAIN_FN[a.mp.model_id](ctx->precision, pl.layout, n * pl.cluster, pl.threads + extra,
@@ -687,6 +694,10 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
         int p2 = 1;
         while (p2 * 2 <= ring) p2 *= 2;
         ring = p2;
+        // (the ring holds prepared proposals, not contributions: it may be larger than the set -- what a
+        // batch needs is distinct rows, Kb <= N / 2 below -- so that sets of >= 257 contributions get
+        // batches of FAST_KCAP)
+        if (N > 2 * FAST_KCAP && ring < FAST_RING_MAX) ring = FAST_RING_MAX;
         if (cfg->max_iter >= (1LL << 31)) return fail(ctx, MCSAS_ERR_ARG, "run: max_iter must be < 2^31");
     }
     const int gw_cap = fast_gw_cap(ctx->nq_max);
@@ -703,6 +714,7 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     const int kcap_max = cfg->precision == MCSAS_FP32 ? FAST_KCAP : MCSAS_MAX_SPEC;
     int kcap = cfg->spec_max <= 0 ? kcap_max : (cfg->spec_max > kcap_max ? kcap_max : cfg->spec_max);
     if (kcap > ring / 4) kcap = ring / 4;
+    if (cfg->precision == MCSAS_FP32 && kcap > (N - 1) / 2) kcap = (N - 1) / 2;
     if (kcap < 1) kcap = 1;
     if (cfg->precision == MCSAS_FP32) {                  // fp32 kernel: batches are powers of two
         int p2 = 1;
@@ -779,6 +791,7 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     a.find_bg = cfg->find_background != 0; a.pos_bg = cfg->positive_background != 0;
     a.start_min = cfg->start_from_minimum != 0;
     a.spec_max = kcap; a.ring = ring;
+    ctx->spec_forced = cfg->spec_max > 0;
     a.gw_cap = gw_cap;
     // fp32 sphere kernel on smeared data: per (profile point, q point) the smeared location
     // sqrt(q^2 + off^2) (slit) or q + off (2-D averaged; sasconfig.py:326-337) as the kernel wants it --

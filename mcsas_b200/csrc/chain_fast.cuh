@@ -1265,48 +1265,43 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     }
                 }
                 if (FAST_PROF) pd[1] = clock64();
-                // lane l owns proposals l and l + 32 (second round only for batches of 64)
-                float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f, t4 = 0.f;
-                const bool mine = lane < Kb, mine2 = lane + 32 < Kb;
+                // lane l owns proposals l, l + 32, ...: the batch is decided 32 proposals at a time
+                float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
+                const bool mine = lane < Kb;
                 const float4 *allp = s_xp + (size_t)xb * GWC * FAST_KCAP;
-                if (mine) {
+                auto prop_sums = [&](int k, float &x1, float &x2, float &x3, float &x4) {
+                    x1 = 0.f; x2 = 0.f; x3 = 0.f; x4 = 0.f;
+                    if (k < Kb) {
 #pragma unroll 4
-                    for (int g = 0; g < GW; ++g) {
-                        const float4 v = allp[(size_t)g * FAST_KCAP + lane];
-                        s1 += v.x; s2 += v.y; s3 += v.z; s4 += v.w;
+                        for (int g = 0; g < GW; ++g) {           // ascending global-warp order
+                            const float4 v = allp[(size_t)g * FAST_KCAP + k];
+                            x1 += v.x; x2 += v.y; x3 += v.z; x4 += v.w;
+                        }
                     }
-                }
-                if (mine2) {
-#pragma unroll 4
-                    for (int g = 0; g < GW; ++g) {
-                        const float4 v = allp[(size_t)g * FAST_KCAP + lane + 32];
-                        t1 += v.x; t2 += v.y; t3 += v.z; t4 += v.w;
-                    }
-                }
+                };
+                prop_sums(lane, s1, s2, s3, s4);
                 if (FAST_PROF) pd[2] = clock64();
                 int ks = -1, accmask = 0, gused = Kb;
                 double ca = a0, cb = b0, cc = conval;
                 if (!gram) {
                     double chi = 0., an = 0., bn = 0., e1, e2, rss;
-                    bool better = false;
-                    if (mine) {
-                        fast_solve(B, a.find_bg, a.pos_bg, s1, s2, s3, s4, rss, an, bn, e1, e2);   // mcsas.py:376
-                        chi = rss * inv_nq;
-                        better = chi < conval;                   // :379 strict
-                        s_chi[lane] = chi;
-                    }
-                    unsigned mask = __ballot_sync(0xffffffffu, better);
+                    unsigned mask = 0;
                     int koff = 0;
-                    if (!mask && Kb > 32) {                      // second round: proposals 32 .. 63
-                        better = false;
-                        if (mine2) {
-                            fast_solve(B, a.find_bg, a.pos_bg, t1, t2, t3, t4, rss, an, bn, e1, e2);
+                    float c1 = s1, c2 = s2, c3 = s3, c4 = s4;
+                    for (int r0 = 0; r0 < Kb; r0 += 32) {        // rounds of 32 proposals, up to the first move
+                        float n1, n2, n3, n4;                    // (the next round's sums load under this round's solve)
+                        prop_sums(lane + r0 + 32, n1, n2, n3, n4);
+                        bool better = false;
+                        if (lane + r0 < Kb) {
+                            fast_solve(B, a.find_bg, a.pos_bg, c1, c2, c3, c4, rss, an, bn, e1, e2);   // mcsas.py:376
                             chi = rss * inv_nq;
-                            better = chi < conval;
-                            s_chi[lane + 32] = chi;
+                            better = chi < conval;               // :379 strict
+                            s_chi[lane + r0] = chi;
                         }
                         mask = __ballot_sync(0xffffffffu, better);
-                        koff = 32;
+                        koff = r0;
+                        if (mask) break;
+                        c1 = n1; c2 = n2; c3 = n3; c4 = n4;
                     }
                     const int kl = mask ? (__ffs(mask) - 1) : -1;
                     ks = kl >= 0 ? kl + koff : -1;

@@ -153,8 +153,9 @@ __host__ __device__ inline size_t chain_smem_bytes(int nq_pad, int N, int P, int
 
 // ---- shared-memory footprint of chain_fast_kernel (mirrors its carve-up) -----------------------------
 #define FAST_MAX_WARPS 32
-#define FAST_KCAP 64               // fp32 kernel: speculative proposals per batch (2 per decision lane)
-#define FAST_RING_MAX 256          // ... ring entries (>= 4 * FAST_KCAP)
+#define FAST_KCAP 128              // fp32 kernel: speculative proposals per batch (decided 32 at a time)
+#define FAST_KDEF 64               // ... by default on one or two CTAs per chain (every SM has other work)
+#define FAST_RING_MAX 512          // ... ring entries (>= 4 * FAST_KCAP)
 #define FAST_CACHE_SMS 256         // SMs row regions are allocated for (>= %nsmid of a B200)
 #define FAST_CACHE_SLOTS 2         // row regions per SM (co-resident CTAs of this kernel)
 #define FAST_QCAP 1024            // q points per CTA (QPT * 32 * warps_q)
