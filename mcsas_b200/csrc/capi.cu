@@ -701,10 +701,17 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
         if (cfg->max_iter >= (1LL << 31)) return fail(ctx, MCSAS_ERR_ARG, "run: max_iter must be < 2^31");
     }
     const int gw_cap = fast_gw_cap(ctx->nq_max);
+    // (batches of FAST_KCAP proposals where the exchange buffers and a ring of 4 x FAST_KCAP prepared
+    // proposals fit next to the chain's state; FAST_KDEF and the smaller ring otherwise)
+    int xp_cap = FAST_KCAP;
     auto smem_of = [&](int rg) {
         return cfg->precision == MCSAS_FP64 ? chain_smem_bytes(nq_pad_max, N, P, D, narr, real, rg)
-                                            : fast_smem_bytes(nq_pad_max, N, P, D, narr, rg, gw_cap);
+                                            : fast_smem_bytes(nq_pad_max, N, P, D, narr, rg, gw_cap, xp_cap);
     };
+    if (cfg->precision == MCSAS_FP32 && smem_of(ring) > smem_limit) {
+        xp_cap = FAST_KDEF;
+        if (ring > 4 * FAST_KDEF) ring = 4 * FAST_KDEF;
+    }
     while (ring > 4 && smem_of(ring) > smem_limit) ring /= 2;
     size_t smem = smem_of(ring);
     // (fp32 kernel: 255 registers x 256 threads fill an SM's register file, so 8-warp CTAs have their SM to
@@ -715,6 +722,7 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     int kcap = cfg->spec_max <= 0 ? kcap_max : (cfg->spec_max > kcap_max ? kcap_max : cfg->spec_max);
     if (kcap > ring / 4) kcap = ring / 4;
     if (cfg->precision == MCSAS_FP32 && kcap > (N - 1) / 2) kcap = (N - 1) / 2;
+    if (cfg->precision == MCSAS_FP32 && kcap > xp_cap) kcap = xp_cap;
     if (kcap < 1) kcap = 1;
     if (cfg->precision == MCSAS_FP32) {                  // fp32 kernel: batches are powers of two
         int p2 = 1;
@@ -793,6 +801,7 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     a.spec_max = kcap; a.ring = ring;
     ctx->spec_forced = cfg->spec_max > 0;
     a.gw_cap = gw_cap;
+    a.xp_cap = xp_cap;
     // fp32 sphere kernel on smeared data: per (profile point, q point) the smeared location
     // sqrt(q^2 + off^2) (slit) or q + off (2-D averaged; sasconfig.py:326-337) as the kernel wants it --
     // q in 1/nm, q/(2 pi) split hi + lo -- and weight * (q_ref/location)^6, so that the evaluation loop

@@ -657,7 +657,8 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     double *s_rset = (double *)carve(sizeof(double) * N * (P > 0 ? P : 1));
     int *s_ctrl = (int *)carve(64);
     RingEntry<float> *s_ring = (RingEntry<float> *)carve((size_t)RING * sizeof(RingEntry<float>));
-    float4 *s_xp = (float4 *)carve(16 * 2 * (size_t)GWC * FAST_KCAP);   // [buf][gw][proposal] (s1..s4)
+    const int XPC = a.xp_cap;                      // proposals per batch the exchange buffers hold
+    float4 *s_xp = (float4 *)carve(16 * 2 * (size_t)GWC * XPC);   // [buf][gw][proposal] (s1..s4)
     double *s_xb = (double *)carve(8 * 2 * (size_t)GWC * 8);            // [buf][gw][5 base sums, flags]
     float *s_xg = (float *)carve(4 * 2 * (size_t)GWC * 32);             // [buf][gw][Gram pairs]
     uint64_t *s_xbar = (uint64_t *)carve(16);
@@ -1007,7 +1008,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             if (Kb < 1 || batch > wd_batches) { status = -2; break; }   // watchdog (uniform over the cluster)
             const int ri0 = (int)((uint32_t)step % (uint32_t)N);  // contribution replaced by the batch's first step
             const int xb = xb_;
-            float4 *const xp = s_xp + (size_t)xb * GWC * FAST_KCAP + (size_t)gw * FAST_KCAP;
+            float4 *const xp = s_xp + (size_t)xb * GWC * XPC + (size_t)gw * XPC;
             double *const xbs = s_xb + (size_t)xb * GWC * 8 + (size_t)gw * 8;
             uint64_t *const xbar = s_xbar + xb;
             const long long pt1 = FAST_PROF ? clock64() : 0;
@@ -1268,13 +1269,13 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                 // lane l owns proposals l, l + 32, ...: the batch is decided 32 proposals at a time
                 float s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
                 const bool mine = lane < Kb;
-                const float4 *allp = s_xp + (size_t)xb * GWC * FAST_KCAP;
+                const float4 *allp = s_xp + (size_t)xb * GWC * XPC;
                 auto prop_sums = [&](int k, float &x1, float &x2, float &x3, float &x4) {
                     x1 = 0.f; x2 = 0.f; x3 = 0.f; x4 = 0.f;
                     if (k < Kb) {
 #pragma unroll 4
                         for (int g = 0; g < GW; ++g) {           // ascending global-warp order
-                            const float4 v = allp[(size_t)g * FAST_KCAP + k];
+                            const float4 v = allp[(size_t)g * XPC + k];
                             x1 += v.x; x2 += v.y; x3 += v.z; x4 += v.w;
                         }
                     }

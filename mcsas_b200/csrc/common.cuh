@@ -66,6 +66,7 @@ struct ChainArgs {
     int slice_batches;           // fp32 kernel: batches per chain in this launch (0 = no limit)
     long long slice_ns;          // fp32 kernel: time budget of this launch per chain in ns (0 = no limit)
     int gw_cap;                  // fp32 kernel: capacity (in warps of a whole chain) of the exchange buffers
+    int xp_cap;                  // ... and in proposals per batch (>= spec_max: FAST_KCAP where it fits, else FAST_KDEF)
     const int *chain_ids;        // chains of this launch (grid = n * cluster) or NULL
     int *status;                 // per chain: 1 finished, 0 needs another slice
     int first_chain;
@@ -170,7 +171,8 @@ __host__ __device__ inline int fast_gw_cap(int nq)
     }
     return cap;
 }
-__host__ __device__ inline size_t fast_smem_bytes(int nq_pad, int N, int P, int D, int narr, int ring, int gw_cap)
+__host__ __device__ inline size_t fast_smem_bytes(int nq_pad, int N, int P, int D, int narr, int ring, int gw_cap,
+                                                  int xp_cap)
 {
 #define AL16(b) ((((size_t)(b)) + 15) & ~size_t(15))
     size_t s = 16;                                               // mbarrier
@@ -178,7 +180,7 @@ __host__ __device__ inline size_t fast_smem_bytes(int nq_pad, int N, int P, int 
     s += AL16(8 * (size_t)N * (P > 0 ? P : 1));                  // rset
     s += AL16(64);                                               // ctrl
     s += AL16((size_t)ring * (8 * MCSAS_MAX_ACTIVE + 2 * 4 * 8));// ring entries
-    s += AL16(16 * 2 * (size_t)gw_cap * FAST_KCAP);              // exchange: per-warp proposal sums (float4), 2 buffers
+    s += AL16(16 * 2 * (size_t)gw_cap * xp_cap);                 // exchange: per-warp proposal sums (float4), 2 buffers
     s += AL16(8 * 2 * (size_t)gw_cap * 8);                       // exchange: per-warp base sums + flags
     s += AL16(4 * 2 * (size_t)gw_cap * 32);                      // exchange: per-warp Gram pairs
     s += 16;                                                     // exchange mbarriers
