@@ -119,6 +119,10 @@ typedef struct mcsas_tuning {
     int big_batch;     /* fp32 kernel: speculative batches of up to 128 proposals (instead of 64) for chains on at
                           least this many CTAs: 0 = default (4: the chains that run on otherwise idle SMs),
                           1 / 2 / 4 / 8, -1 = never.  (A run_config.spec_max > 0 overrides it.) */
+    int gram_in;       /* fp32 kernel: a move at most this many steps behind the previous one switches to Gram
+                          batches, 0 = default (8).  NOT result-neutral (a Gram batch rounds a proposal's sums
+                          differently): part of the chain's definition, the same on every schedule */
+    int gram_out;      /* ... and a Gram batch with fewer than this many moves switches back, 0 = default (1) */
 } mcsas_tuning;
 
 /* -- context ------------------------------------------------------------- */

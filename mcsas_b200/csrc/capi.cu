@@ -832,6 +832,8 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
         a.smloc = ctx->d_smloc; a.smloc_row = row;
     }
     a.gram = ctx->tune.gram < 0 ? 0 : 1;
+    a.gram_in = ctx->tune.gram_in > 0 ? ctx->tune.gram_in : 8;
+    a.gram_out = ctx->tune.gram_out > 0 ? ctx->tune.gram_out : 1;
     a.first_chain = cfg->first_chain; a.record_trace = cfg->record_trace;
     a.seed = cfg->seed;
     // Time slicing.  Deterministic (uploaded stream / traced) runs are one launch.  fp32 production

@@ -1424,8 +1424,9 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     if (tid == 0) s_cold->moves += __popc(accmask);
                     dirty = true;
                     last_acc = step + (31 - __clz(accmask));
-                } else {
-                    gmode = false;                               // no move in a whole chunk: speculate
+                }
+                if (__popc(accmask) < a.gram_out) {              // too few moves in a whole chunk: speculate
+                    gmode = false;
                     K = min(kmax, 2 * FGRP);
                 }
             } else if (kstar >= 0) {                             // mcsas.py:381-384
@@ -1460,7 +1461,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                 if (tid < P) s_rset[rix * P + tid] = s_ring[e].prop[tid];
                 if (tid == 0) { s_cold->moves += 1; s_cold->evals += 2; }
                 dirty = true;
-                gmode = step + kstar - last_acc <= FGRP;
+                gmode = step + kstar - last_acc <= a.gram_in;
                 last_acc = step + kstar;
                 K = max(1, min(kmax, 1 << (31 - __clz(kstar + 1))));
             } else {

@@ -60,6 +60,8 @@ struct ChainArgs {
     int ring;                    // ring entries = min(RING_MAX, n_contribs)
     int cluster;                 // CTAs per chain (q split)
     int gram;                    // fp32 kernel: 1 = Gram batches (multi-accept chunks) when moves are frequent
+    int gram_in, gram_out;       // ... entered by a move at most gram_in steps behind the previous one, left by a
+                                 // Gram batch with fewer than gram_out moves (part of the chain's definition)
     int warps_q;                 // fp32 kernel: warps covering one CTA's q slice (eval warps = warps_q * groups)
     int resume;                  // 1: continue from the saved state (rset, counters)
     long long slice_steps;       // MC steps per chain in this launch, 0 = run to the end
