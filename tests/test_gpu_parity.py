@@ -439,6 +439,15 @@ def test_results_do_not_depend_on_cluster_size_or_slicing(nq, N):
         out, info = run(tuning=dict(slice_us=us))
         assert info["launches"] > 1
         _assert_same_results(ref, out, "auto scheduler slice_us=%d" % us)
+    # the size of a speculative batch never changes a result: batches of at most 16 / 32 / 64 / 128
+    # proposals (128 where the contribution set allows it), on one CTA and on clusters, and the
+    # scheduler's own choice (128 from 4 CTAs on) forced on for every chain / off
+    for sm, c in ((16, 1), (32, 4), (64, 8), (128, 1), (128, 8)):
+        out, info = run(cluster_size=c, slice_steps=-1, spec_max=sm)
+        _assert_same_results(ref, out, "spec_max %d on %d CTAs" % (sm, c))
+    for bb in (1, -1):
+        out, info = run(tuning=dict(big_batch=bb))
+        _assert_same_results(ref, out, "auto scheduler big_batch=%d" % bb)
 
 
 def _sphere_engine(sets, lo=1e-9, hi=100e-9):
