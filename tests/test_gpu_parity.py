@@ -489,6 +489,30 @@ def test_smeared_production_results_do_not_depend_on_the_schedule_or_the_batch()
     assert not np.array_equal(plain["conval"], ref["conval"])
 
 
+@pytest.mark.parametrize("qpt", [4, 2, 1])
+def test_production_kernel_layouts_of_1_2_4_q_points_per_thread(qpt):
+    """mcsas_tuning.qpt forces the fp32 kernel's q points per thread (4 in production: packed pairs;
+    2: one pair; 1: the scalar sums).  Every layout fits (chi-squared falls by more than 100x), and the
+    chi-squared it reports is what the fp64 evaluation says about the contribution set it returns."""
+    from mcsas_b200 import Engine, synth
+    q, I, sig = synth.sphere_curve(nq=200, seed=5)
+    eng = _sphere_engine([(q, I, sig)])
+    eng.set_tuning(qpt=qpt)
+    eng.run(Engine.make_config(n_contribs=60, n_reps=4, conv_crit=1.0, max_iter=8000, max_retries=-1,
+                               precision=FP32, seed=17))
+    out = eng.fetch()
+    assert (out["conval"][0] < 1e-2 * out["conval0"][0]).all(), (out["conval"], out["conval0"])
+    for r in range(4):
+        it, _, _, _ = eng.eval(out["contribs"][0, :, :, r], 0.6666666, 0, FP64)   # [N, nq], fp64
+        m = it.sum(axis=0)
+        wgt = 1. / sig ** 2                               # backgroundscalingfit.py:112-139 in closed form
+        A = np.array([[(wgt * m * m).sum(), (wgt * m).sum()], [(wgt * m).sum(), wgt.sum()]])
+        a, b = np.linalg.solve(A, np.array([(wgt * m * I).sum(), (wgt * I).sum()]))
+        chi = float((wgt * (I - a * m - b) ** 2).sum() / q.size)
+        assert abs(chi / out["conval"][0, r] - 1) < 1e-3, (chi, out["conval"][0, r])
+    eng.close()
+
+
 def _sphere_engine(sets, lo=1e-9, hi=100e-9):
     from mcsas_b200 import Engine
     eng = Engine(0)
