@@ -123,6 +123,8 @@ typedef struct mcsas_tuning {
                           batches, 0 = default (8).  NOT result-neutral (a Gram batch rounds a proposal's sums
                           differently): part of the chain's definition, the same on every schedule */
     int gram_out;      /* ... and a Gram batch with fewer than this many moves switches back, 0 = default (1) */
+    int gpc_pack;      /* scheduler: bound a mix of cluster sizes by the clusters' shares of the machine (a cluster
+                          lives inside one GPC): 0 = default (on), -1 = off (count CTAs only) */
 } mcsas_tuning;
 
 /* -- context ------------------------------------------------------------- */

@@ -600,6 +600,14 @@ static int launch_slice(mcsas_ctx *ctx, int n_live, bool resume)
         long long used = (long long)n_live << lowest;
         int cnt_at[4] = {0, 0, 0, 0};
         cnt_at[lowest] = n_live;
+        // A cluster must sit inside one GPC, so a mix of cluster sizes cannot use every SM: a cluster of size
+        // c takes 1 / resident(c) of the machine (resident = cudaOccupancyMaxActiveClusters of that size
+        // alone).  Without this bound 13 chains on 4 and 12 on 8 CTAs -- 148 CTAs -- ran in TWO waves: every
+        // slice of a 25-chain fit took twice its budget (one fit split over 4 GPUs: 29 instead of 20 ms).
+        auto share = [&](int li) { return 1. / (double)(plans[li].resident > 0 ? plans[li].resident : 1); };
+        double frac = n_live * share(lowest);
+        const bool pack = ctx->tune.gpc_pack >= 0;
+        auto fits = [&](int li) { return !pack || frac + share(li) - share(li - 1) <= 1.0 + 1e-9; };
         // Late chains first, as far as they can go: the chi-squared of a chain says little about its
         // length before ~20 000 steps (tools/predict_len.py: rank correlation 0.0 at 10 000, 0.4 at
         // 20 000, 0.7 at 40 000 steps); from then on the chains furthest from the criterion are the
@@ -610,7 +618,8 @@ static int launch_slice(mcsas_ctx *ctx, int n_live, bool resume)
                 if (ctx->h_cnt[ctx->h_ids[i]] < late) continue;
                 for (int li = level[i] + 1; li < 4 && have[li]; ++li) {
                     const int cost = (1 << li) / 2;
-                    if (used + cost > sms_eff || cnt_at[li] + 1 > plans[li].resident) break;
+                    if (used + cost > sms_eff || cnt_at[li] + 1 > plans[li].resident || !fits(li)) break;
+                    frac += share(li) - share(li - 1);
                     cnt_at[li]++; cnt_at[level[i]]--; level[i] = li; used += cost;
                 }
             }
@@ -621,6 +630,8 @@ static int launch_slice(mcsas_ctx *ctx, int n_live, bool resume)
             for (int i = 0; i < n_live && used + step_cost <= sms_eff; ++i) {
                 if (level[i] != li - 1) continue;
                 if (cnt_at[li] + 1 > plans[li].resident) break;  // co-resident clusters of this size
+                if (!fits(li)) break;                            // ... and of the mix
+                frac += share(li) - share(li - 1);
                 level[i] = li; cnt_at[li]++; cnt_at[li - 1]--;
                 used += step_cost;
             }
