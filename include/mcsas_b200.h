@@ -125,6 +125,9 @@ typedef struct mcsas_tuning {
     int gram_out;      /* ... and a Gram batch with fewer than this many moves switches back, 0 = default (1) */
     int gpc_pack;      /* scheduler: bound a mix of cluster sizes by the clusters' shares of the machine (a cluster
                           lives inside one GPC): 0 = default (on), -1 = off (count CTAs only) */
+    int l2_keep_pct;   /* fp32 kernel, contribution-row cache: percentage of the L2 the evict_last part of the resident
+                          chains' rows may take (the rest of every chain's rows is streamed evict_first): 0 = default
+                          (50: measured optimum on B200, whose L2 keeps about half of its 126 MB for lines of this kind), -1 = off (every row evict_last, plain LRU) */
 } mcsas_tuning;
 
 /* -- context ------------------------------------------------------------- */

@@ -642,6 +642,16 @@ static int launch_slice(mcsas_ctx *ctx, int n_live, bool resume)
         std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return lv[x] > lv[y]; });
         for (int i = 0; i < n_live; ++i) { ctx->h_ids[i] = ids[idx[i]]; level[i] = lv[idx[i]]; }
     }
+    // Contribution-row cache and the L2: the chains resident at a time sweep N rows of nq floats each, cyclically
+    // (row = step % N) -- with more bytes than the L2 holds, the LRU worst case.  The first keep_rows rows of every
+    // chain are accessed evict_last, the others evict_first, so that what fits stays resident.
+    a.keep_rows = ctx->args.n_contribs;
+    if (ctx->tune.l2_keep_pct >= 0) {
+        const double pct = ctx->tune.l2_keep_pct > 0 ? ctx->tune.l2_keep_pct : 50;
+        const double bytes = (double)std::min(n_live, sms_eff) * ctx->args.n_contribs * (double)ctx->nq_max * sizeof(float);
+        const double room = pct / 100. * (double)ctx->prop.l2CacheSize;
+        if (bytes > room) a.keep_rows = (int)(ctx->args.n_contribs * room / bytes);
+    }
     CK(cudaMemcpyAsync(ctx->d_ids, ctx->h_ids.data(), sizeof(int) * n_live, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     // chains are sorted by level descending (upgrades are prefixes of the priority order)

@@ -347,6 +347,78 @@ template <> struct FastOps<MCSAS_SPHERE> {
                                                      const QRep<float> (&Q)[QPT], float (&d)[NS][QPT])
     {
         if (qt.nsm) {
+            if (qt.smloc) {
+                // smeared, tabulated locations: the NS proposals share every table entry (ONE 16-byte load per
+                // (profile point, q point) and chunk instead of one per proposal -- the loads held the L1 for
+                // as long as the evaluations hold the XU pipe) and run through the packed evaluation; per
+                // (proposal, q point) the same operations in the same order as evalN above
+                float rr[NS], aa[NS];
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    const float2 ra = *(const float2 *)&ring[ent[s]].cn.c[1];
+                    rr[s] = ra.x; aa[s] = ra.y;
+                }
+                if constexpr (QPT % 2 == 0) {
+                    constexpr int MP = QPT / 2;
+                    float2 acc[NS][MP];
+#pragma unroll
+                    for (int s = 0; s < NS; ++s)
+#pragma unroll
+                        for (int i = 0; i < MP; ++i) acc[s][i] = pk1(0.f);
+#pragma unroll 1
+                    for (int k = 0; k < qt.nsm; ++k) {
+                        float2 q[MP], th[MP], tl[MP], w[MP], g[NS][MP];
+#pragma unroll
+                        for (int i = 0; i < MP; ++i) {
+                            const float4 e0 = __ldg(qt.smloc + (size_t)k * qt.smstride + 2 * i);
+                            const float4 e1 = __ldg(qt.smloc + (size_t)k * qt.smstride + 2 * i + 1);
+                            q[i] = pk2(e0.x, e1.x); th[i] = pk2(e0.y, e1.y); tl[i] = pk2(e0.z, e1.z); w[i] = pk2(e0.w, e1.w);
+                        }
+                        sph_g_pack<NS, MP, true>(q, th, tl, rr, g);
+#pragma unroll
+                        for (int s = 0; s < NS; ++s)
+#pragma unroll
+                            for (int i = 0; i < MP; ++i)
+                                acc[s][i] = __ffma2_rn(w[i], __fmul2_rn(g[s][i], g[s][i]), acc[s][i]);
+                    }
+#pragma unroll
+                    for (int s = 0; s < NS; ++s)
+#pragma unroll
+                        for (int i = 0; i < MP; ++i) {
+                            const float2 v = __fmul2_rn(acc[s][i], pk1(aa[s]));
+                            d[s][2 * i] = v.x; d[s][(2 * i + 1) % QPT] = v.y;
+                        }
+                } else {
+                    float acc[NS][QPT];
+#pragma unroll
+                    for (int s = 0; s < NS; ++s)
+#pragma unroll
+                        for (int j = 0; j < QPT; ++j) acc[s][j] = 0.f;
+#pragma unroll 1
+                    for (int k = 0; k < qt.nsm; ++k) {
+                        float q[QPT], th[QPT], tl[QPT], w[QPT];
+#pragma unroll
+                        for (int j = 0; j < QPT; ++j) {
+                            const float4 e = __ldg(qt.smloc + (size_t)k * qt.smstride + j);
+                            q[j] = e.x; th[j] = e.y; tl[j] = e.z; w[j] = e.w;
+                        }
+#pragma unroll
+                        for (int s = 0; s < NS; ++s) {
+                            float r[QPT], g[QPT];
+#pragma unroll
+                            for (int j = 0; j < QPT; ++j) r[j] = rr[s];
+                            sph_g_vec<QPT, true>(q, th, tl, r, g);
+#pragma unroll
+                            for (int j = 0; j < QPT; ++j) acc[s][j] = fmaf(w[j], g[j] * g[j], acc[s][j]);
+                        }
+                    }
+#pragma unroll
+                    for (int s = 0; s < NS; ++s)
+#pragma unroll
+                        for (int j = 0; j < QPT; ++j) d[s][j] = acc[s][j] * aa[s];
+                }
+                return;
+            }
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
                 const Contrib<float> cn = ring[ent[s]].cn;
@@ -471,23 +543,43 @@ template <> struct FastOps<MCSAS_SPHERE> {
     }
 };
 
-// one thread's slice of a cached contribution row: QPT contiguous floats, one vector access
-template <int QPT> __device__ __forceinline__ void row_load(const float *p, float (&v)[QPT])
+// one thread's slice of a cached contribution row: QPT contiguous floats, one vector access.
+// `keep` selects the L2 eviction priority of the line (createpolicy encodings of evict_last / evict_first):
+// with more resident chains than the L2 holds rows for, the cyclic sweep over a chain's rows is the LRU
+// worst case (hit rate ~ 30 %); the scheduler marks the first a.keep_rows rows of every chain -- what fits --
+// evict_last and streams the rest, so that the marked part stays resident.  The policy operand of a load is
+// warp-uniform (ptxas moves it to a uniform register), and the lanes of a chunk load read FGRP consecutive rows:
+// a chunk takes the policy of its first row.
+__device__ __forceinline__ unsigned long long row_policy(bool keep)
 {
-    if (QPT == 4) { const float4 x = __ldcg((const float4 *)p); v[0] = x.x; v[1] = x.y; v[2 % QPT] = x.z; v[3 % QPT] = x.w; }
-    else if (QPT == 2) { const float2 x = __ldcg((const float2 *)p); v[0] = x.x; v[1 % QPT] = x.y; }
+    return (unsigned long long)(keep ? 0x14F00000u : 0x12F00000u) << 32;
+}
+template <int QPT> __device__ __forceinline__ void row_load(const float *p, float (&v)[QPT], unsigned long long pol)
+{
+    if (QPT == 4)
+        asm volatile("ld.global.cg.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                     : "=f"(v[0]), "=f"(v[1 % QPT]), "=f"(v[2 % QPT]), "=f"(v[3 % QPT]) : "l"(p), "l"(pol));
+    else if (QPT == 2)
+        asm volatile("ld.global.cg.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;"
+                     : "=f"(v[0]), "=f"(v[1 % QPT]) : "l"(p), "l"(pol));
     else {
 #pragma unroll
-        for (int j = 0; j < QPT; ++j) v[j] = __ldcg(p + j);
+        for (int j = 0; j < QPT; ++j)
+            asm volatile("ld.global.cg.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v[j]) : "l"(p + j), "l"(pol));
     }
 }
-template <int QPT> __device__ __forceinline__ void row_store(float *p, const float (&v)[QPT])
+template <int QPT> __device__ __forceinline__ void row_store(float *p, const float (&v)[QPT], unsigned long long pol)
 {
-    if (QPT == 4) __stcg((float4 *)p, make_float4(v[0], v[1], v[2 % QPT], v[3 % QPT]));
-    else if (QPT == 2) __stcg((float2 *)p, make_float2(v[0], v[1 % QPT]));
+    if (QPT == 4)
+        asm volatile("st.global.cg.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+                     :: "l"(p), "f"(v[0]), "f"(v[1 % QPT]), "f"(v[2 % QPT]), "f"(v[3 % QPT]), "l"(pol) : "memory");
+    else if (QPT == 2)
+        asm volatile("st.global.cg.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;"
+                     :: "l"(p), "f"(v[0]), "f"(v[1 % QPT]), "l"(pol) : "memory");
     else {
 #pragma unroll
-        for (int j = 0; j < QPT; ++j) __stcg(p + j, v[j]);
+        for (int j = 0; j < QPT; ++j)
+            asm volatile("st.global.cg.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(p + j), "f"(v[j]), "l"(pol) : "memory");
     }
 }
 
@@ -638,6 +730,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     const int D = NARR ? a.mp.quad_nodes : 0;
     const int RING = a.ring;
     const int kmax = a.spec_max;
+    const int keep_rows = a.keep_rows;             // cached rows [0, keep_rows) are evict_last in the L2
     const int RL = QPT * TQ;                       // cached row length of this CTA
     // row regions: FAST_CACHE_SLOTS per SM (an 8-warp CTA fills the register file of its SM; two
     // 4-warp CTAs share one), taken under a lock word for the lifetime of the CTA
@@ -918,7 +1011,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     FO::template evalN<QPT>(cc, nd, qt, Q, dv);
 #pragma unroll
                     for (int j = 0; j < QPT; ++j) ft0[j] += (double)dv[j] * (double)s_qs[qtid * QPT + j];
-                    if (CACHE && grp == 0) row_store<QPT>(crow + (size_t)(i0 + e) * RL, dv);
+                    if (CACHE && grp == 0) row_store<QPT>(crow + (size_t)(i0 + e) * RL, dv, row_policy(i0 + e < keep_rows));
                 }
             }
             __syncthreads();
@@ -1051,6 +1144,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             // pinned in a register: ptxas otherwise re-reads %tid (S2R) for every proposal slot
             int perm = grp_perm<FGRP>(lane);
             asm volatile("mov.b32 %0, %0;" : "+r"(perm));
+            const unsigned long long gpol = row_policy(ri0 < keep_rows);   // L2 policy of a Gram batch's rows
             float uu[FGRP][QPT];                                 // GRAM: (new - old)/sigma of slot s
             float dnk[CACHE ? FGRP : 1][QPT];                    // GRAM + CACHE: new row of slot s
             if (gram) {
@@ -1069,7 +1163,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                         for (int s = 0; s < NH; ++s) {
                             int ri = ri0 + ((h0 + s) ^ perm);
                             if (ri >= N) ri -= N;
-                            row_load<QPT>(crow + (size_t)ri * RL, od[s]);
+                            row_load<QPT>(crow + (size_t)ri * RL, od[s], gpol);
                             ent[s] = (e0 + ((h0 + s) ^ perm)) & (RING - 1);
                         }
                         FO::template diffChunk<QPT, NH>(s_ring, ent, s_nodes, NSTR, qt, Q, od,
@@ -1143,12 +1237,15 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                     // evaluations at the end of the chunk); the old rows of the whole chunk are requested
                     // first (L2 / DRAM latency hides behind the evaluations)
                     float od[CACHE ? FGRP : 1][QPT];
+                    int rb = ri0 + k0;
+                    if (rb >= N) rb -= N;
+                    const unsigned long long cpol = row_policy(rb < keep_rows);
                     if (CACHE) {
 #pragma unroll
                         for (int s = 0; s < FGRP; ++s) {
                             int ri = ri0 + k0 + (s ^ perm);
                             if (ri >= N) ri -= N;
-                            row_load<QPT>(crow + (size_t)ri * RL, od[CACHE ? s : 0]);
+                            row_load<QPT>(crow + (size_t)ri * RL, od[CACHE ? s : 0], cpol);
                         }
                     }
 #pragma unroll
@@ -1204,7 +1301,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                         int ri = ri0 + k;
                         if (ri >= N) ri -= N;
                         float ov[1][QPT], dv[1][QPT];
-                        row_load<QPT>(crow + (size_t)ri * RL, ov[0]);
+                        row_load<QPT>(crow + (size_t)ri * RL, ov[0], row_policy(ri < keep_rows));
                         const int ent[1] = {e};
                         FO::template diffChunk<QPT, 1>(s_ring, ent, s_nodes, NSTR, qt, Q, ov, dv, dd);
                     } else {
@@ -1410,7 +1507,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                             if (!((accmask >> (s ^ perm)) & 1)) continue;
                             int ri = ri0 + (s ^ perm);
                             if (ri >= N) ri -= N;
-                            row_store<QPT>(crow + (size_t)ri * RL, dnk[CACHE ? s : 0]);
+                            row_store<QPT>(crow + (size_t)ri * RL, dnk[CACHE ? s : 0], gpol);
                         }
                     }
                     if (tid < FGRP * P) {
@@ -1438,13 +1535,13 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                 float dd[QPT];
                 if (CACHE) {
                     float dv[1][QPT], ov[1][QPT], d1[1][QPT];
-                    row_load<QPT>(crow + (size_t)rix * RL, ov[0]);   // in flight during the evaluation
+                    row_load<QPT>(crow + (size_t)rix * RL, ov[0], row_policy(rix < keep_rows));   // in flight during the evaluation
                     const int ent[1] = {e};
                     FO::template diffChunk<QPT, 1>(s_ring, ent, s_nodes, NSTR, qt, Q, ov, dv, d1);
 #pragma unroll
                     for (int j = 0; j < QPT; ++j) dd[j] = d1[0][j];
                     if (PS > 1) named_bar_sync(1, T);            // every group has read the old row
-                    if (grp == 0) row_store<QPT>(crow + (size_t)rix * RL, dv[0]);
+                    if (grp == 0) row_store<QPT>(crow + (size_t)rix * RL, dv[0], row_policy(rix < keep_rows));
                 } else {
                     FO::template diffS<QPT>(cn, co, nn, no, qt, Q, dd);
                 }

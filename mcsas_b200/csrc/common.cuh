@@ -99,6 +99,8 @@ struct ChainArgs {
     float *cache;                // fp32 kernel: NULL or [SM id][cache_stride] contribution rows
     long long cache_stride;      // floats per SM (n_contribs * FAST_QCAP)
     int *cache_lock;             // [SM id] 0 = free
+    int keep_rows;               // cached rows [0, keep_rows) of every chain are loaded / stored evict_last, the
+                                 // others evict_first (set per slice: what the L2 holds of the resident chains' rows)
     long long *prof;             // NULL or [chain][2][8] phase cycle counters (MCSAS_B200_PROF)
     const float4 *smloc;         // fp32 sphere kernel, smeared data: NULL or [set][profile point][smloc_row] table of
                                  // (q, split q/(2 pi), weight * (q_ref/q)^6) at the smeared locations of every q point

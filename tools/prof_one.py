@@ -12,6 +12,8 @@ q, I, sig = synth.sphere_curve(nq=1000)
 eng = Engine(0)
 eng.upload_datasets([(q, I, sig)])
 eng.set_model(0, [10e-9, 1e14], [0], [1e-9], [100e-9], [0])
+if os.environ.get("TUNE_L2"):
+    eng.set_tuning(l2_keep_pct=int(os.environ["TUNE_L2"]))
 cfg = Engine.make_config(n_contribs=300, n_reps=reps, precision=FP32, seed=5, max_iter=int(os.environ.get("TUNE_MAXIT", "24576")),
                          conv_crit=0.0, max_retries=-1, slice_steps=int(os.environ.get("TUNE_SLICE", "8192")),
                          cluster_size=int(os.environ.get("TUNE_CLUSTER", "1")))

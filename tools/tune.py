@@ -74,6 +74,11 @@ if __name__ == "__main__":
     if "late" in which:
         for d in (-1, 20000, 30000, 40000, 50000, -1):
             run("late_steps=%d" % d, {"late_steps": d}, seeds=(1, 2, 4, 7, 9, 11))
+    if "l2" in which:
+        for pct in [int(x) for x in os.environ.get("L2_PCT", "-1,40,55,70,85,-1").split(",")]:
+            saturated("l2_keep_pct=%d" % pct, {"l2_keep_pct": pct})
+        run("l2_keep_pct=-1", {"l2_keep_pct": -1}, seeds=(1, 2, 4, 7, 9, 11))
+        run("l2_keep_pct=default", {}, seeds=(1, 2, 4, 7, 9, 11))
     if "backup" in which:
         for pct in (30, 40, 50, 60):
             for bd in (2, 4):
