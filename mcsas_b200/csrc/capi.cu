@@ -827,7 +827,7 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
     // sqrt(q^2 + off^2) (slit) or q + off (2-D averaged; sasconfig.py:326-337) as the kernel wants it --
     // q in 1/nm, q/(2 pi) split hi + lo -- and weight * (q_ref/location)^6, so that the evaluation loop
     // has neither the fp64 square root nor the phase split (one 16-byte load per location instead)
-    a.smloc = nullptr; a.smloc_row = 0;
+    a.smloc = nullptr; a.smloc_row = 0; a.smloc_mono = 0;
     if (cfg->precision == MCSAS_FP32 && ctx->smear.n > 0 && mp.model_id == MCSAS_SPHERE) {
         const int row = gw_cap * 128, n = ctx->smear.n;
         std::vector<float4> tab((size_t)ctx->n_sets * n * row);
@@ -851,6 +851,9 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
         CK(cudaMemcpyAsync(ctx->d_smloc, tab.data(), sizeof(float4) * tab.size(), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         a.smloc = ctx->d_smloc; a.smloc_row = row;
+        a.smloc_mono = 1;                                    // sqrt(q^2 + off^2) >= q; q + off >= q for off >= 0
+        if (ctx->smear.two_d)
+            for (int k = 0; k < n; ++k) if (!(ctx->smear.off[k] >= 0.)) a.smloc_mono = 0;
     }
     a.gram = ctx->tune.gram < 0 ? 0 : 1;
     a.gram_in = ctx->tune.gram_in > 0 ? ctx->tune.gram_in : 8;

@@ -339,6 +339,32 @@ template <> struct FastOps<MCSAS_SPHERE> {
 #pragma unroll
         for (int j = 0; j < QPT; ++j) d[j] = g[j] * cc.c[2];
     }
+    // smeared, tabulated locations: sum over the profile points of w g(loc r)^2 for NS radii and MP pairs of
+    // q points; every table entry is loaded once for the NS proposals
+    template <int NS, int MP, bool SER>
+    __device__ __forceinline__ static void smear_pack(const QuadTab<float> &qt, const float (&rr)[NS], float2 (&acc)[NS][MP])
+    {
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+            for (int i = 0; i < MP; ++i) acc[s][i] = pk1(0.f);
+#pragma unroll 1
+        for (int k = 0; k < qt.nsm; ++k) {
+            float2 q[MP], th[MP], tl[MP], w[MP], g[NS][MP];
+#pragma unroll
+            for (int i = 0; i < MP; ++i) {
+                const float4 e0 = __ldg(qt.smloc + (size_t)k * qt.smstride + 2 * i);
+                const float4 e1 = __ldg(qt.smloc + (size_t)k * qt.smstride + 2 * i + 1);
+                q[i] = pk2(e0.x, e1.x); th[i] = pk2(e0.y, e1.y); tl[i] = pk2(e0.z, e1.z); w[i] = pk2(e0.w, e1.w);
+            }
+            sph_g_pack<NS, MP, SER>(q, th, tl, rr, g);
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+#pragma unroll
+                for (int i = 0; i < MP; ++i)
+                    acc[s][i] = __ffma2_rn(w[i], __fmul2_rn(g[s][i], g[s][i]), acc[s][i]);
+        }
+    }
     // NS contributions at once: ONE vote selects the series variant for the whole chunk, so
     // the NS x QPT evaluations form a single basic block that ptxas can interleave freely
     template <int QPT, int NS>
@@ -361,26 +387,21 @@ template <> struct FastOps<MCSAS_SPHERE> {
                 if constexpr (QPT % 2 == 0) {
                     constexpr int MP = QPT / 2;
                     float2 acc[NS][MP];
+                    // The series branch (x < 1) is needed by no element of the chunk when the smallest
+                    // unsmeared q times the smallest radius is >= 1 and no location lies below its q point
+                    // (qt.smmono: slit profiles, 2-D profiles without negative offsets): ONE vote per chunk,
+                    // as in the unsmeared evaluator; the variants agree bit for bit where x >= 1.
+                    bool ser = true;
+                    if (qt.smmono) {
+                        float rmin = rr[0], qmin = Q[0].q;
 #pragma unroll
-                    for (int s = 0; s < NS; ++s)
+                        for (int s = 1; s < NS; ++s) rmin = fminf(rmin, rr[s]);
 #pragma unroll
-                        for (int i = 0; i < MP; ++i) acc[s][i] = pk1(0.f);
-#pragma unroll 1
-                    for (int k = 0; k < qt.nsm; ++k) {
-                        float2 q[MP], th[MP], tl[MP], w[MP], g[NS][MP];
-#pragma unroll
-                        for (int i = 0; i < MP; ++i) {
-                            const float4 e0 = __ldg(qt.smloc + (size_t)k * qt.smstride + 2 * i);
-                            const float4 e1 = __ldg(qt.smloc + (size_t)k * qt.smstride + 2 * i + 1);
-                            q[i] = pk2(e0.x, e1.x); th[i] = pk2(e0.y, e1.y); tl[i] = pk2(e0.z, e1.z); w[i] = pk2(e0.w, e1.w);
-                        }
-                        sph_g_pack<NS, MP, true>(q, th, tl, rr, g);
-#pragma unroll
-                        for (int s = 0; s < NS; ++s)
-#pragma unroll
-                            for (int i = 0; i < MP; ++i)
-                                acc[s][i] = __ffma2_rn(w[i], __fmul2_rn(g[s][i], g[s][i]), acc[s][i]);
+                        for (int j = 1; j < QPT; ++j) qmin = fminf(qmin, Q[j].q);
+                        ser = __any_sync(0xffffffffu, qmin * rmin < 1.f);
                     }
+                    if (ser) smear_pack<NS, MP, true>(qt, rr, acc);
+                    else smear_pack<NS, MP, false>(qt, rr, acc);
 #pragma unroll
                     for (int s = 0; s < NS; ++s)
 #pragma unroll
@@ -804,7 +825,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     if (C > 1) cluster_sync_all(); else __syncthreads();         // every rank's mbarriers are initialised
     const QuadTab<float> qt = { D, a.mp.quad_rule, s_qx, s_qw, &a.smear, SMEAR ? a.smear.n : 0,
                                 SMEAR && a.smloc ? a.smloc + ((size_t)set * a.smear.n * a.smloc_row + (size_t)(rank * TQ + qtid) * QPT) : nullptr,
-                                a.smloc_row };
+                                a.smloc_row, SMEAR ? a.smloc_mono : 0 };
     const float qref = (float)(ds.q_ref * 1e-9);   // 1/nm
 
     // ---- per-thread resident state of q points (rank*TQ + qtid)*QPT + j, j < QPT (contiguous:

@@ -105,6 +105,7 @@ struct ChainArgs {
     const float4 *smloc;         // fp32 sphere kernel, smeared data: NULL or [set][profile point][smloc_row] table of
                                  // (q, split q/(2 pi), weight * (q_ref/q)^6) at the smeared locations of every q point
     int smloc_row;               // entries per profile point (>= q points of the largest chain layout)
+    int smloc_mono;              // 1: every smeared location >= its q point (the series vote may use the unsmeared q)
 };
 
 struct EvalArgs {

@@ -215,6 +215,7 @@ template <class Real> struct QuadTab {
                              // instantiations for unsmeared data (their hot loops carry no smear code)
     const float4 *smloc;     // fp32 sphere kernel: this thread's column of the smeared-location table
     int smstride;            // (ChainArgs::smloc), entries between two profile points; NULL: none
+    int smmono;              // 1: no tabulated location lies below its q point (slit profile / offsets >= 0)
 };
 
 template <int MODEL, class Real> struct Ops;
