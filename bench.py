@@ -383,6 +383,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # one rank per GPU shares the host's cores: the few host-side tensor copies of a gather must not
+        # fan out into cpu_count() threads per rank
+        torch.set_num_threads(max(1, (os.cpu_count() or world) // (2 * world)))
     q, I, sig = config2_data()
     data = SASData(q, I, sig)
 
