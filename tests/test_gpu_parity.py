@@ -448,6 +448,13 @@ def test_results_do_not_depend_on_cluster_size_or_slicing(nq, N):
     for bb in (1, -1):
         out, info = run(tuning=dict(big_batch=bb))
         _assert_same_results(ref, out, "auto scheduler big_batch=%d" % bb)
+    # the L2 eviction priorities of the contribution-row cache are hints: everything evict_last (-1) or
+    # only the first few rows of every chain (1 % of the L2 for the resident chains' rows)
+    for pct in (-1, 1):
+        out, info = run(tuning=dict(l2_keep_pct=pct))
+        _assert_same_results(ref, out, "auto scheduler l2_keep_pct=%d" % pct)
+        out, info = run(tuning=dict(l2_keep_pct=pct), cluster_size=2, slice_steps=-1)
+        _assert_same_results(ref, out, "2 CTAs l2_keep_pct=%d" % pct)
 
 
 def test_smeared_production_results_do_not_depend_on_the_schedule_or_the_batch():
@@ -477,6 +484,25 @@ def test_smeared_production_results_do_not_depend_on_the_schedule_or_the_batch()
     assert (ref["conval"] < ref["conval0"]).all()
     for over in (dict(cluster_size=4, slice_steps=-1), dict(cluster_size=8, slice_steps=-1), dict()):
         _assert_same_results(ref, run(sets, **over), "smeared, %s" % (over,))
+    # a 2-D profile with negative offsets: smeared locations below their q point, so the chunk evaluator may not
+    # take its series vote from the unsmeared q (ChainArgs::smloc_mono = 0) -- and one without (vote on)
+    for lo in (-1e7, 0.):
+        qo2 = np.linspace(lo, 2e7, 7)
+        w2 = np.full(7, 1. / 7.)
+
+        def run2(**over):
+            eng = _sphere_engine(sets)
+            eng.set_smearing(qo2, w2, True)
+            c = dict(kw)
+            c.update(over)
+            eng.run(Engine.make_config(**c))
+            out = eng.fetch()
+            eng.close()
+            return out
+        ref2 = run2(cluster_size=1, slice_steps=-1)
+        assert (ref2["conval"] < ref2["conval0"]).all()
+        for over in (dict(cluster_size=4, slice_steps=-1), dict(cluster_size=2, slice_steps=500), dict()):
+            _assert_same_results(ref2, run2(**over), "2-D smeared from %g, %s" % (lo, over))
     alone = run(sets[1:2], first_chain=3, cluster_size=1, slice_steps=-1)       # same global chain ids
     for k in RESULT_KEYS:
         np.testing.assert_array_equal(alone[k][0], ref[k][1], err_msg="second dataset alone: %s" % k)
