@@ -128,6 +128,8 @@ typedef struct mcsas_tuning {
     int l2_keep_pct;   /* fp32 kernel, contribution-row cache: percentage of the L2 the evict_last part of the resident
                           chains' rows may take (the rest of every chain's rows is streamed evict_first): 0 = default
                           (50: measured optimum on B200, whose L2 keeps about half of its 126 MB for lines of this kind), -1 = off (every row evict_last, plain LRU) */
+    int backup_top;    /* at most this many backup attempts alive at a time, the chains with the largest chi-squared
+                          first: 0 = default (no bound) */
 } mcsas_tuning;
 
 /* -- context ------------------------------------------------------------- */

@@ -1039,6 +1039,7 @@ extern "C" int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms)
         const int bpct0 = ctx->tune.backup_pct > 0 ? ctx->tune.backup_pct : 40;
         const int bpct = n_primary * 4 <= ctx->prop.multiProcessorCount ? (hpct < bpct0 ? hpct : bpct0) : bpct0;
         const int epct = ctx->tune.early_pct > 0 ? ctx->tune.early_pct : 30;
+        const int btop = ctx->tune.backup_top > 0 ? ctx->tune.backup_top : 0;   // at most this many backups alive (largest chi-squared first), 0 = no bound
         const int etop = ctx->tune.early_top > 0 ? ctx->tune.early_top : 0;   // (measured on config 2: no gain at 8..24 chains from 25..35 %, off by default)
         auto start_backup = [&](int c) -> int {
             const int pslot = ctx->cur[c];
@@ -1063,13 +1064,16 @@ extern "C" int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms)
                 if (ctx->bak[c] >= 0) { ++n_bak_alive; continue; }
                 const int pslot = ctx->cur[c];
                 if (status[pslot] != 0 || attempts[pslot] >= ctx->max_attempts) continue;
-                if (idle && 100 * num_iter[pslot] >= (long long)bpct * ctx->max_iter) start_backup(c);
-                else if (!idle && etop > 0 && 100 * num_iter[pslot] >= (long long)epct * ctx->max_iter)
+                if (idle && 100 * num_iter[pslot] >= (long long)bpct * ctx->max_iter) {
+                    if (btop > 0) cand.push_back(std::make_pair(-ctx->h_conval[pslot], c));
+                    else start_backup(c);
+                } else if (!idle && etop > 0 && 100 * num_iter[pslot] >= (long long)epct * ctx->max_iter)
                     cand.push_back(std::make_pair(-ctx->h_conval[pslot], c));
             }
-            if (!idle && !cand.empty()) {
+            if (!cand.empty()) {
                 std::sort(cand.begin(), cand.end());
-                for (size_t i = 0; i < cand.size() && n_bak_alive < etop; ++i, ++n_bak_alive) start_backup(cand[i].second);
+                const int cap = idle ? btop : etop;
+                for (size_t i = 0; i < cand.size() && n_bak_alive < cap; ++i, ++n_bak_alive) start_backup(cand[i].second);
             }
         }
         if (new_backups) {                                  // nothing runs between slices: whole arrays

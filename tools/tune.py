@@ -74,6 +74,9 @@ if __name__ == "__main__":
     if "late" in which:
         for d in (-1, 20000, 30000, 40000, 50000, -1):
             run("late_steps=%d" % d, {"late_steps": d}, seeds=(1, 2, 4, 7, 9, 11))
+    if "btop" in which:
+        for bt in [int(x) for x in os.environ.get("BTOP", "0,8,16,24,36,0").split(",")]:
+            run("backup_top=%d" % bt, {"backup_top": bt}, seeds=(1, 2, 4, 7, 9, 11, 13, 17, 19))
     if "l2" in which:
         for pct in [int(x) for x in os.environ.get("L2_PCT", "-1,40,55,70,85,-1").split(",")]:
             saturated("l2_keep_pct=%d" % pct, {"l2_keep_pct": pct})
