@@ -301,16 +301,23 @@ template <> struct FastOps<MCSAS_SPHERE> {
                 // smeared (sasmodel.py:56-73): sum over the profile points of w g(loc r)^2 at the tabulated
                 // locations (location, its split phase factor and weight * (q_ref/loc)^6 come from ONE
                 // 16-byte load: no fp64 square root, no phase split in the loop)
+                // (the table of a 1000-point dataset is 26 x 16 KB: its entries come from the L2, so the next
+                // profile point's entries are requested before this one's are evaluated)
                 float acc[QPT];
+                float4 nx[QPT];
 #pragma unroll
-                for (int j = 0; j < QPT; ++j) acc[j] = 0.f;
-#pragma unroll 2
+                for (int j = 0; j < QPT; ++j) { acc[j] = 0.f; nx[j] = __ldg(qt.smloc + j); }
+#pragma unroll 1
                 for (int k = 0; k < qt.nsm; ++k) {
                     float q[QPT], th[QPT], tl[QPT], r[QPT], w[QPT], g[QPT];
 #pragma unroll
                     for (int j = 0; j < QPT; ++j) {
-                        const float4 e = __ldg(qt.smloc + (size_t)k * qt.smstride + j);
+                        const float4 e = nx[j];
                         q[j] = e.x; th[j] = e.y; tl[j] = e.z; w[j] = e.w; r[j] = cc.c[0];
+                    }
+                    if (k + 1 < qt.nsm) {
+#pragma unroll
+                        for (int j = 0; j < QPT; ++j) nx[j] = __ldg(qt.smloc + (size_t)(k + 1) * qt.smstride + j);
                     }
                     // (the series variant for every point: a vote per profile point costs more than it saves)
                     sph_g_vec<QPT, true>(q, th, tl, r, g);
@@ -348,14 +355,22 @@ template <> struct FastOps<MCSAS_SPHERE> {
         for (int s = 0; s < NS; ++s)
 #pragma unroll
             for (int i = 0; i < MP; ++i) acc[s][i] = pk1(0.f);
+        // (table entries come from the L2 -- 26 x 16 KB per 1000-point dataset: the next profile point's entries are
+        // requested before this one's are evaluated)
+        float4 nx[2 * MP];
+#pragma unroll
+        for (int i = 0; i < 2 * MP; ++i) nx[i] = __ldg(qt.smloc + i);
 #pragma unroll 1
         for (int k = 0; k < qt.nsm; ++k) {
             float2 q[MP], th[MP], tl[MP], w[MP], g[NS][MP];
 #pragma unroll
             for (int i = 0; i < MP; ++i) {
-                const float4 e0 = __ldg(qt.smloc + (size_t)k * qt.smstride + 2 * i);
-                const float4 e1 = __ldg(qt.smloc + (size_t)k * qt.smstride + 2 * i + 1);
+                const float4 e0 = nx[2 * i], e1 = nx[2 * i + 1];
                 q[i] = pk2(e0.x, e1.x); th[i] = pk2(e0.y, e1.y); tl[i] = pk2(e0.z, e1.z); w[i] = pk2(e0.w, e1.w);
+            }
+            if (k + 1 < qt.nsm) {
+#pragma unroll
+                for (int i = 0; i < 2 * MP; ++i) nx[i] = __ldg(qt.smloc + (size_t)(k + 1) * qt.smstride + i);
             }
             sph_g_pack<NS, MP, SER>(q, th, tl, rr, g);
 #pragma unroll
@@ -415,13 +430,20 @@ template <> struct FastOps<MCSAS_SPHERE> {
                     for (int s = 0; s < NS; ++s)
 #pragma unroll
                         for (int j = 0; j < QPT; ++j) acc[s][j] = 0.f;
+                    float4 nx[QPT];
+#pragma unroll
+                    for (int j = 0; j < QPT; ++j) nx[j] = __ldg(qt.smloc + j);
 #pragma unroll 1
                     for (int k = 0; k < qt.nsm; ++k) {
                         float q[QPT], th[QPT], tl[QPT], w[QPT];
 #pragma unroll
                         for (int j = 0; j < QPT; ++j) {
-                            const float4 e = __ldg(qt.smloc + (size_t)k * qt.smstride + j);
+                            const float4 e = nx[j];
                             q[j] = e.x; th[j] = e.y; tl[j] = e.z; w[j] = e.w;
+                        }
+                        if (k + 1 < qt.nsm) {
+#pragma unroll
+                            for (int j = 0; j < QPT; ++j) nx[j] = __ldg(qt.smloc + (size_t)(k + 1) * qt.smstride + j);
                         }
 #pragma unroll
                         for (int s = 0; s < NS; ++s) {

@@ -13,8 +13,15 @@ for cl in [int(x) for x in os.environ.get("CLUSTERS", "1,2,4,8").split(",")]:
     eng.upload_datasets([(q, I, sig)])
     eng.set_model(0, [10e-9, 1e14], [0], [1e-9], [100e-9], [0])
     eng.set_tuning(profile=1)
+    if os.environ.get("SMEAR"):                          # the 26-point slit profile of tools/smear_throughput.py
+        import numpy as np
+        qo = np.linspace(0., 5e7, 26)
+        w = np.ones(26)
+        w[13:] = np.linspace(1., 0., 13)
+        w /= 2. * np.trapezoid(w, qo)
+        eng.set_smearing(qo, w, False)
     reps = int(os.environ.get('REPS', '16'))
-    cfg = Engine.make_config(n_contribs=300, n_reps=reps, precision=FP32, seed=7919, max_iter=100000, max_retries=-1,
+    cfg = Engine.make_config(n_contribs=300, n_reps=reps, precision=FP32, seed=7919, max_iter=int(os.environ.get('MAXIT', '100000')), max_retries=-1,
                              cluster_size=cl)
     print("== cluster %d, %d chains" % (cl, reps), flush=True)
     sys.stderr.flush()
