@@ -289,6 +289,51 @@ template <> struct FastOps<MCSAS_SPHERE> {
         sph_g_vec<1, true>(q, th, tl, r, g);
         return (g[0] * g[0]) * cc.c[2];
     }
+    // smeared, tabulated locations, ONE radius (row build, the update after a move, batches shorter than a
+    // chunk): four profile points per pass, so that 4 x MP independent packed evaluations are in flight where a
+    // point-by-point loop has MP; the sum over the profile points is accumulated in their order, with the
+    // operations of the chunk evaluator (smear_pack) -- the same bits
+    template <int MP, bool SER>
+    __device__ __forceinline__ static void smear_one(const QuadTab<float> &qt, float r, float2 (&acc)[MP])
+    {
+        constexpr int KU = 4;
+        const float rr[1] = {r};
+#pragma unroll
+        for (int i = 0; i < MP; ++i) acc[i] = pk1(0.f);
+        int k = 0;
+#pragma unroll 1
+        for (; k + KU <= qt.nsm; k += KU) {
+            float2 q[KU * MP], th[KU * MP], tl[KU * MP], w[KU * MP], g[1][KU * MP];
+#pragma unroll
+            for (int u = 0; u < KU; ++u)
+#pragma unroll
+                for (int i = 0; i < MP; ++i) {
+                    const float4 e0 = __ldg(qt.smloc + (size_t)(k + u) * qt.smstride + 2 * i);
+                    const float4 e1 = __ldg(qt.smloc + (size_t)(k + u) * qt.smstride + 2 * i + 1);
+                    q[u * MP + i] = pk2(e0.x, e1.x); th[u * MP + i] = pk2(e0.y, e1.y);
+                    tl[u * MP + i] = pk2(e0.z, e1.z); w[u * MP + i] = pk2(e0.w, e1.w);
+                }
+            sph_g_pack<1, KU * MP, SER>(q, th, tl, rr, g);
+#pragma unroll
+            for (int u = 0; u < KU; ++u)
+#pragma unroll
+                for (int i = 0; i < MP; ++i)
+                    acc[i] = __ffma2_rn(w[u * MP + i], __fmul2_rn(g[0][u * MP + i], g[0][u * MP + i]), acc[i]);
+        }
+#pragma unroll 1
+        for (; k < qt.nsm; ++k) {
+            float2 q[MP], th[MP], tl[MP], w[MP], g[1][MP];
+#pragma unroll
+            for (int i = 0; i < MP; ++i) {
+                const float4 e0 = __ldg(qt.smloc + (size_t)k * qt.smstride + 2 * i);
+                const float4 e1 = __ldg(qt.smloc + (size_t)k * qt.smstride + 2 * i + 1);
+                q[i] = pk2(e0.x, e1.x); th[i] = pk2(e0.y, e1.y); tl[i] = pk2(e0.z, e1.z); w[i] = pk2(e0.w, e1.w);
+            }
+            sph_g_pack<1, MP, SER>(q, th, tl, rr, g);
+#pragma unroll
+            for (int i = 0; i < MP; ++i) acc[i] = __ffma2_rn(w[i], __fmul2_rn(g[0][i], g[0][i]), acc[i]);
+        }
+    }
     // q ascends along the lanes, so "some x < 1" is warp-uniform for all but one warp per
     // radius: one vote per proposal selects the variant without the series.  Callers are
     // warp-convergent.
@@ -301,6 +346,16 @@ template <> struct FastOps<MCSAS_SPHERE> {
                 // smeared (sasmodel.py:56-73): sum over the profile points of w g(loc r)^2 at the tabulated
                 // locations (location, its split phase factor and weight * (q_ref/loc)^6 come from ONE
                 // 16-byte load: no fp64 square root, no phase split in the loop)
+                if constexpr (QPT % 2 == 0) {
+                    float2 a2[QPT / 2];
+                    smear_one<QPT / 2, true>(qt, cc.c[0], a2);
+#pragma unroll
+                    for (int i = 0; i < QPT / 2; ++i) {
+                        const float2 v = __fmul2_rn(a2[i], pk1(cc.c[2]));
+                        d[2 * i] = v.x; d[(2 * i + 1) % QPT] = v.y;
+                    }
+                    return;
+                }
                 // (the table of a 1000-point dataset is 26 x 16 KB: its entries come from the L2, so the next
                 // profile point's entries are requested before this one's are evaluated)
                 float acc[QPT];
@@ -351,6 +406,10 @@ template <> struct FastOps<MCSAS_SPHERE> {
     template <int NS, int MP, bool SER>
     __device__ __forceinline__ static void smear_pack(const QuadTab<float> &qt, const float (&rr)[NS], float2 (&acc)[NS][MP])
     {
+        if constexpr (NS == 1) {
+            smear_one<MP, SER>(qt, rr[0], acc[0]);
+            return;
+        }
 #pragma unroll
         for (int s = 0; s < NS; ++s)
 #pragma unroll
