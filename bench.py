@@ -365,6 +365,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sub-records", action="store_true")
+    ap.add_argument("--tune", default="", help="experiments: scheduler knobs of struct mcsas_tuning, k=v[,k=v...]")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -400,6 +401,8 @@ def main():
         return algo
 
     algo = make_algo(N_REPS, rank * N_REPS)                         # weak scaling: 100 repetitions per rank
+    if args.tune:
+        algo.engine.set_tuning(**{k: int(v) for k, v in (kv.split("=") for kv in args.tune.split(","))})
     s_first, s_count = mdist.partition(N_REPS, world, rank)         # strong scaling: ONE fit over all ranks
     algo_strong = make_algo(max(1, s_count), s_first) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2

@@ -130,6 +130,8 @@ typedef struct mcsas_tuning {
                           (50: measured optimum on B200, whose L2 keeps about half of its 126 MB for lines of this kind), -1 = off (every row evict_last, plain LRU) */
     int backup_top;    /* at most this many backup attempts alive at a time, the chains with the largest chi-squared
                           first: 0 = default (no bound) */
+    int retry_pct;     /* ... and the backup threshold (percentage of maxIterations) for a repetition whose current attempt
+                          is already a retry: 0 = default (at once), -1 = as for first attempts (backup_pct) */
 } mcsas_tuning;
 
 /* -- context ------------------------------------------------------------- */

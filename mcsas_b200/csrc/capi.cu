@@ -652,7 +652,23 @@ static int launch_slice(mcsas_ctx *ctx, int n_live, bool resume)
         const double room = pct / 100. * (double)ctx->prop.l2CacheSize;
         if (bytes > room) a.keep_rows = (int)(ctx->args.n_contribs * room / bytes);
     }
-    CK(cudaMemcpyAsync(ctx->d_ids, ctx->h_ids.data(), sizeof(int) * n_live, cudaMemcpyHostToDevice, ctx->stream));
+    // A slice is over when its primaries are: backup attempts (flagged in the id list) leave their launch at the
+    // next batch boundary once the count of primaries still in theirs -- d_ids[n_live], decremented by every
+    // primary on its way out -- is zero.  Without it the LAST slice of a fit ran to its full budget whenever the
+    // repetition that finished last had a backup attempt alive (1 ms of the fit on average).
+    {
+        std::vector<int> up((size_t)n_live + 1);
+        int needed = 0;
+        for (int i = 0; i < n_live; ++i) {
+            const int slot = ctx->h_ids[i];
+            const bool primary = ctx->cur[slot % ctx->n_chains] == slot;
+            needed += primary ? 1 : 0;
+            up[i] = primary ? slot : (slot | CHAIN_ID_BACKUP);
+        }
+        up[n_live] = needed;
+        CK(cudaMemcpyAsync(ctx->d_ids, up.data(), sizeof(int) * ((size_t)n_live + 1), cudaMemcpyHostToDevice, ctx->stream));
+        a.needed_left = ctx->d_ids + n_live;
+    }
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     // chains are sorted by level descending (upgrades are prefixes of the priority order)
     int pos = 0, nside = 0;
@@ -782,7 +798,7 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
         CK(regrow(&ctx->d_scal, (size_t)n_slots * SCAL_N));
         CK(regrow(&ctx->d_cnt, (size_t)n_slots * 4));
         CK(regrow(&ctx->d_att, (size_t)n_slots * ATT_N));
-        CK(regrow(&ctx->d_ids, (size_t)n_slots));
+        CK(regrow(&ctx->d_ids, (size_t)n_slots + 1));           // (+ the slice's count of primaries, below)
         ctx->slot_cap = (size_t)n_slots;
     }
     if ((size_t)n_slots > ctx->pin_cap) {
@@ -1039,6 +1055,10 @@ extern "C" int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms)
         const int bpct0 = ctx->tune.backup_pct > 0 ? ctx->tune.backup_pct : 40;
         const int bpct = n_primary * 4 <= ctx->prop.multiProcessorCount ? (hpct < bpct0 ? hpct : bpct0) : bpct0;
         const int epct = ctx->tune.early_pct > 0 ? ctx->tune.early_pct : 30;
+        // a repetition whose current attempt is already a retry is a hard one (it failed before, and a fit waits for
+        // the repetition that fails twice: 36 % of the config-2 fits have one): its next attempt starts at once
+        // (tools/tune.py retry, 25 seeds: 29.9 -> 29.0 ms per fit, fits with a double failure -2.5 .. -4.6 ms)
+        const int rpct = ctx->tune.retry_pct > 0 ? ctx->tune.retry_pct : (ctx->tune.retry_pct < 0 ? bpct : 0);
         const int btop = ctx->tune.backup_top > 0 ? ctx->tune.backup_top : 0;   // at most this many backups alive (largest chi-squared first), 0 = no bound
         const int etop = ctx->tune.early_top > 0 ? ctx->tune.early_top : 0;   // (measured on config 2: no gain at 8..24 chains from 25..35 %, off by default)
         auto start_backup = [&](int c) -> int {
@@ -1064,7 +1084,8 @@ extern "C" int mcsas_wait(mcsas_ctx *ctx, float *kernel_ms)
                 if (ctx->bak[c] >= 0) { ++n_bak_alive; continue; }
                 const int pslot = ctx->cur[c];
                 if (status[pslot] != 0 || attempts[pslot] >= ctx->max_attempts) continue;
-                if (idle && 100 * num_iter[pslot] >= (long long)bpct * ctx->max_iter) {
+                const int thr = attempts[pslot] >= 1 ? rpct : bpct;   // a repetition that failed before is a hard one
+                if (idle && 100 * num_iter[pslot] >= (long long)thr * ctx->max_iter) {
                     if (btop > 0) cand.push_back(std::make_pair(-ctx->h_conval[pslot], c));
                     else start_backup(c);
                 } else if (!idle && etop > 0 && 100 * num_iter[pslot] >= (long long)epct * ctx->max_iter)

@@ -821,7 +821,9 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
     const int rank = C > 1 ? (int)cluster_ctarank() : 0;
     const int GW = C * WQ, gw = rank * WQ + wq;    // warps of the whole chain / this warp's place among them
     const int slot = blockIdx.x / C;
-    const int chain = a.chain_ids ? a.chain_ids[slot] : slot;
+    const int chain_id = a.chain_ids ? a.chain_ids[slot] : slot;
+    const int chain = chain_id & ~CHAIN_ID_BACKUP;
+    const bool is_backup = (chain_id & CHAIN_ID_BACKUP) != 0;   // a backup attempt: its launch ends with the primaries'
     // `chain` is a state slot: slots >= n_chains hold a chain's other attempt (retry prepared or
     // run ahead of time by the host scheduler, capi.cu)
     const int base_chain = chain % a.n_chains;
@@ -1236,7 +1238,8 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
             }
             if (grp == 0) {
                 if (lane == 5) {                                 // time budget of this launch (any warp may end it)
-                    const bool over = a.slice_ns > 0 && globaltimer_ns() > *(volatile unsigned long long *)&s_cold->deadline;
+                    bool over = a.slice_ns > 0 && globaltimer_ns() > *(volatile unsigned long long *)&s_cold->deadline;
+                    if (is_backup && a.needed_left && *(volatile int *)a.needed_left <= 0) over = true;
                     xsend8(xbs + 5, xbar, C, over ? 1. : 0.);
                 }
             }
@@ -1737,6 +1740,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         a.attempts[chain] = attempt + 1;
         a.elapsed_s[chain] = (a.resume ? a.elapsed_s[chain] : 0.) + 1e-9 * (double)(globaltimer_ns() - s_cold->t_start);
         a.status[chain] = status;
+        if (!is_backup && a.needed_left) atomicSub(a.needed_left, 1);
     }
     if (CACHE) {
         __syncthreads();

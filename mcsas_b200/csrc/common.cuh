@@ -44,6 +44,7 @@ struct DatasetDesc {
     double i_scale;     // max |I|: the fp32 kernel normalises I and sigma by it
 };
 
+#define CHAIN_ID_BACKUP 0x40000000   // flag in ChainArgs::chain_ids: the slot runs a backup attempt (capi.cu)
 struct ChainArgs {
     ModelParams mp;
     SmearTab smear;
@@ -70,6 +71,8 @@ struct ChainArgs {
     int gw_cap;                  // fp32 kernel: capacity (in warps of a whole chain) of the exchange buffers
     int xp_cap;                  // ... and in proposals per batch (>= spec_max: FAST_KCAP where it fits, else FAST_KDEF)
     const int *chain_ids;        // chains of this launch (grid = n * cluster) or NULL
+    int *needed_left;            // fp32 kernel: NULL or the primaries (ids without CHAIN_ID_BACKUP) of this time slice that
+                                 // are still in their launch; a backup attempt ends its launch when it is 0
     int *status;                 // per chain: 1 finished, 0 needs another slice
     int first_chain;
     int record_trace;

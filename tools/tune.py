@@ -17,6 +17,8 @@ VERBOSE = int(os.environ.get("TUNE_VERBOSE", "0"))
 
 
 def run(tag, tuning, seeds=(1, 2, 4, 7), **cfgkw):
+    if os.environ.get("SEEDS"):
+        seeds = tuple(int(x) for x in os.environ["SEEDS"].split(","))
     q, I, sig = synth.sphere_curve(nq=NQ)
     eng = Engine(0)
     eng.upload_datasets([(q, I, sig)])
@@ -65,6 +67,8 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["base"]
     if "base" in which:
         run("auto", {})
+    if "seeds" in which:                                 # fit time by seed (the first run warms up and is not printed)
+        run("auto", {}, seeds=tuple(range(1, 27)))
     if "maxc" in which:
         for c in (8, 4, 2, 1, 8):
             run("max cluster=%d" % c, {"max_cluster": c}, seeds=(1, 2, 4, 7, 9, 11))
@@ -74,6 +78,9 @@ if __name__ == "__main__":
     if "late" in which:
         for d in (-1, 20000, 30000, 40000, 50000, -1):
             run("late_steps=%d" % d, {"late_steps": d}, seeds=(1, 2, 4, 7, 9, 11))
+    if "retry" in which:
+        for rp in [int(x) for x in os.environ.get("RETRY_PCT", "-1,0,10,20,-1").split(",")]:
+            run("retry_pct=%d" % rp, {"retry_pct": rp}, seeds=tuple(range(1, 27)))
     if "btop" in which:
         for bt in [int(x) for x in os.environ.get("BTOP", "0,8,16,24,36,0").split(",")]:
             run("backup_top=%d" % bt, {"backup_top": bt}, seeds=(1, 2, 4, 7, 9, 11, 13, 17, 19))
