@@ -132,6 +132,8 @@ typedef struct mcsas_tuning {
                           first: 0 = default (no bound) */
     int retry_pct;     /* ... and the backup threshold (percentage of maxIterations) for a repetition whose current attempt
                           is already a retry: 0 = default (at once), -1 = as for first attempts (backup_pct) */
+    int repack_pct;    /* a time slice also ends once chains holding this percentage of the SMs have left their launches
+                          (the freed SMs go to the remaining chains at once): 0 = default (off) */
 } mcsas_tuning;
 
 /* -- context ------------------------------------------------------------- */

@@ -41,7 +41,7 @@ class Tuning(C.Structure):
     _fields_ = [("max_cluster", C.c_int), ("slice_us", C.c_int), ("backups", C.c_int),
                 ("backup_div", C.c_int), ("gram", C.c_int), ("qpt", C.c_int), ("profile", C.c_int),
                 ("verbose", C.c_int), ("half", C.c_int), ("backup_pct", C.c_int), ("hedge_pct", C.c_int), ("early_pct", C.c_int), ("early_top", C.c_int), ("late_steps", C.c_int), ("big_batch", C.c_int), ("gram_in", C.c_int), ("gram_out", C.c_int), ("gpc_pack", C.c_int),
-                ("l2_keep_pct", C.c_int), ("backup_top", C.c_int), ("retry_pct", C.c_int)]
+                ("l2_keep_pct", C.c_int), ("backup_top", C.c_int), ("retry_pct", C.c_int), ("repack_pct", C.c_int)]
 
 
 _lib = None

@@ -657,7 +657,7 @@ static int launch_slice(mcsas_ctx *ctx, int n_live, bool resume)
     // primary on its way out -- is zero.  Without it the LAST slice of a fit ran to its full budget whenever the
     // repetition that finished last had a backup attempt alive (1 ms of the fit on average).
     {
-        std::vector<int> up((size_t)n_live + 1);
+        std::vector<int> up((size_t)n_live + 2);
         int needed = 0;
         for (int i = 0; i < n_live; ++i) {
             const int slot = ctx->h_ids[i];
@@ -666,8 +666,12 @@ static int launch_slice(mcsas_ctx *ctx, int n_live, bool resume)
             up[i] = primary ? slot : (slot | CHAIN_ID_BACKUP);
         }
         up[n_live] = needed;
-        CK(cudaMemcpyAsync(ctx->d_ids, up.data(), sizeof(int) * ((size_t)n_live + 1), cudaMemcpyHostToDevice, ctx->stream));
+        up[n_live + 1] = 0;                                  // CTAs whose chain has left its launch (re-pack trigger)
+        CK(cudaMemcpyAsync(ctx->d_ids, up.data(), sizeof(int) * ((size_t)n_live + 2), cudaMemcpyHostToDevice, ctx->stream));
         a.needed_left = ctx->d_ids + n_live;
+        // re-pack trigger: once chains holding this many CTAs have left, the others end their launch at the next
+        // batch boundary, so that the freed SMs go to the chains that are left (larger clusters) at once
+        a.repack_ctas = ctx->tune.repack_pct > 0 ? std::max(1, sms * ctx->tune.repack_pct / 100) : 0;
     }
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     // chains are sorted by level descending (upgrades are prefixes of the priority order)
@@ -798,7 +802,7 @@ extern "C" int mcsas_run_async(mcsas_ctx *ctx, const mcsas_run_config *cfg,
         CK(regrow(&ctx->d_scal, (size_t)n_slots * SCAL_N));
         CK(regrow(&ctx->d_cnt, (size_t)n_slots * 4));
         CK(regrow(&ctx->d_att, (size_t)n_slots * ATT_N));
-        CK(regrow(&ctx->d_ids, (size_t)n_slots + 1));           // (+ the slice's count of primaries, below)
+        CK(regrow(&ctx->d_ids, (size_t)n_slots + 2));           // (+ the slice's counters, below)
         ctx->slot_cap = (size_t)n_slots;
     }
     if ((size_t)n_slots > ctx->pin_cap) {

@@ -1240,6 +1240,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
                 if (lane == 5) {                                 // time budget of this launch (any warp may end it)
                     bool over = a.slice_ns > 0 && globaltimer_ns() > *(volatile unsigned long long *)&s_cold->deadline;
                     if (is_backup && a.needed_left && *(volatile int *)a.needed_left <= 0) over = true;
+                    if (a.repack_ctas > 0 && *(volatile int *)(a.needed_left + 1) >= a.repack_ctas) over = true;
                     xsend8(xbs + 5, xbar, C, over ? 1. : 0.);
                 }
             }
@@ -1741,6 +1742,7 @@ chain_fast_kernel(const __grid_constant__ ChainArgs a)
         a.elapsed_s[chain] = (a.resume ? a.elapsed_s[chain] : 0.) + 1e-9 * (double)(globaltimer_ns() - s_cold->t_start);
         a.status[chain] = status;
         if (!is_backup && a.needed_left) atomicSub(a.needed_left, 1);
+        if (a.repack_ctas > 0) atomicAdd(a.needed_left + 1, C);
     }
     if (CACHE) {
         __syncthreads();

@@ -73,6 +73,8 @@ struct ChainArgs {
     const int *chain_ids;        // chains of this launch (grid = n * cluster) or NULL
     int *needed_left;            // fp32 kernel: NULL or the primaries (ids without CHAIN_ID_BACKUP) of this time slice that
                                  // are still in their launch; a backup attempt ends its launch when it is 0
+    int repack_ctas;             // > 0: every chain ends its launch once chains holding this many CTAs have left theirs
+                                 // (needed_left[1] counts them)
     int *status;                 // per chain: 1 finished, 0 needs another slice
     int first_chain;
     int record_trace;

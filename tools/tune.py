@@ -85,6 +85,9 @@ if __name__ == "__main__":
         for pct in [int(x) for x in os.environ.get("BPCT", "40,25,30,35,50,40").split(",")]:
             for bd in [int(x) for x in os.environ.get("BDIV", "2").split(",")]:
                 run("backup_pct=%d,div=%d" % (pct, bd), {"backup_pct": pct, "backup_div": bd}, seeds=tuple(range(1, 27)))
+    if "repack" in which:
+        for rp in [int(x) for x in os.environ.get("REPACK", "0,15,25,40,0").split(",")]:
+            run("repack_pct=%d" % rp, {"repack_pct": rp}, seeds=tuple(range(1, 27)))
     if "btop" in which:
         for bt in [int(x) for x in os.environ.get("BTOP", "0,8,16,24,36,0").split(",")]:
             run("backup_top=%d" % bt, {"backup_top": bt}, seeds=(1, 2, 4, 7, 9, 11, 13, 17, 19))
