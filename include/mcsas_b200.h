@@ -127,7 +127,9 @@ typedef struct mcsas_tuning {
                           lives inside one GPC): 0 = default (on), -1 = off (count CTAs only) */
     int l2_keep_pct;   /* fp32 kernel, contribution-row cache: percentage of the L2 the evict_last part of the resident
                           chains' rows may take (the rest of every chain's rows is streamed evict_first): 0 = default
-                          (50: measured optimum on B200, whose L2 keeps about half of its 126 MB for lines of this kind), -1 = off (every row evict_last, plain LRU) */
+                          (50, applied only when every SM holds a chain -- measured optimum on B200, whose L2 keeps
+                          about half of its 126 MB for lines of this kind), > 0 = that percentage, in every slice,
+                          -1 = off (every row evict_last, plain LRU) */
     int backup_top;    /* at most this many backup attempts alive at a time, the chains with the largest chi-squared
                           first: 0 = default (no bound) */
     int retry_pct;     /* ... and the backup threshold (percentage of maxIterations) for a repetition whose current attempt
